@@ -1,0 +1,175 @@
+/*
+ * sonar3d.h -- C-ABI of the B200-native sonar -> voxel log-odds hot path.
+ *
+ * The reference (luckkim123/sonar_3d_reconstruction) is pure Python and has no FFI of its
+ * own: its operator API for this path is the Python class pair SonarTo3DMapper / SimpleOctree
+ * in scripts/3d_mapper.py.  The entry points below are what a binding for exactly those
+ * methods needs; each one names the reference lines it replaces.  The Python mirror of the
+ * reference classes (sonar_3d_reconstruction_b200/mapper.py) is the only caller, via ctypes.
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions: every function returns 0 on success and a negative S3D_E* code on failure;
+ * s3d_last_error() gives the message of the calling thread's last failure.  All pointers are
+ * plain host pointers unless the name says `_dev`.  Buffers are caller-owned and borrowed for
+ * the duration of the call only.  Voxel keys cross the ABI as int32 triples (i, j, k), the
+ * reference's tuple keys (scripts/3d_mapper.py:53-66); each axis must lie in
+ * [-2^20, 2^20) (S3D_KEY_LIMIT) -- the table packs 3 x 21 bits into one 64-bit word.
+ * One map = one CUDA device + one stream; calls on one map must come from one thread at a
+ * time (the reference is single-threaded, scripts/3d_mapper_node.py:536).
+ */
+#ifndef SONAR3D_H
+#define SONAR3D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S3D_ABI_VERSION 1
+#define S3D_KEY_LIMIT (1 << 20)
+
+enum {
+    S3D_OK = 0,
+    S3D_EINVAL = -1,      /* bad argument / tables or params not set */
+    S3D_ECUDA = -2,       /* CUDA runtime error (message has the detail) */
+    S3D_ENOMEM = -3,      /* device or host allocation failed */
+    S3D_EKEYRANGE = -4,   /* a voxel key fell outside +-S3D_KEY_LIMIT (or a coordinate was NaN) */
+    S3D_ETABLEFULL = -5,  /* the voxel table could not grow enough; map state is unspecified */
+    S3D_ESCRATCH = -6     /* per-frame dedupe scratch overflow (internal sizing bug) */
+};
+
+typedef struct s3d_map s3d_map; /* opaque */
+
+/* Live tunables.  The reference reads these from public mutable attributes at update time
+ * (SimpleOctree: scripts/3d_mapper.py:33-51; mapper: :259-270), so the host passes them
+ * again whenever they change. */
+typedef struct s3d_params {
+    double resolution;          /* SimpleOctree.resolution, divisor of world_to_key (:63-65) */
+    double log_odds_occupied;   /* :42  delta of an occupied sample (:481) */
+    double log_odds_free;       /* :43  delta of a free sample (:446) */
+    double log_odds_min;        /* :44  clamp (:110) */
+    double log_odds_max;        /* :45 */
+    double adaptive_threshold;  /* :50 */
+    double adaptive_max_ratio;  /* :51 */
+    double z_filter_min;        /* :269, test at :443/:478 */
+    int32_t adaptive_update;    /* :49 */
+    int32_t z_filter_enabled;   /* :270 */
+    int32_t intensity_threshold;/* integer t with (pixel > t) == (pixel > self.intensity_threshold)
+                                   for every uint8 pixel (:407, :452); -1 = every pixel passes,
+                                   255 = none */
+    int32_t reserved;
+} s3d_params;
+
+/* Host-built geometry tables for one image shape.  All trigonometry is evaluated on the host
+ * with the reference's own expressions so that voxel keys are bit-exact;
+ * the device only multiplies and adds. */
+typedef struct s3d_tables {
+    int32_t H, W;               /* range bins (rows), bearings (cols): polar_image.shape (:508) */
+    int32_t n_beams;            /* processed beams: range(0, W, max(1, W//256)) that pass the FOV gate (:528-535) */
+    int32_t nv_max;             /* largest fan half-width in nv_free/nv_occ */
+    int32_t free_step;          /* 10  (:419) */
+    int32_t occ_window;         /* 50  (:451) */
+    const int32_t *beam_col;    /* [n_beams] image column of each processed beam */
+    const double *cos_b;        /* [n_beams] cos(bearing_angles[col]) (:434) */
+    const double *sin_b;        /* [n_beams] sin(bearing_angles[col]) (:435) */
+    const double *range_m;      /* [H] r_idx * (max_range / H) (:404, :421) */
+    const int32_t *nv_free;     /* [H] max(1, int(range*tan(ha)/(res*4))) (:427); 0 = bin skipped (range < min_range, :422) */
+    const int32_t *nv_occ;      /* [H] max(2, int(range*tan(ha)/(res*1.5))) (:463); 0 = bin skipped (:456) */
+    const double *cos_va;       /* [nv_max*(nv_max+2)] cos((v/max(1,nv))*ha); row nv starts at nv*nv-1, v=-nv..nv (:430,:466) */
+    const double *sin_va;       /* same layout, sin */
+} s3d_tables;
+
+/* Per-frame counters = the integer entries of the reference's stats dict (:587-595). */
+typedef struct s3d_frame_stats {
+    int64_t num_occupied;  /* voxels updated with type 'occupied' this frame (:564) */
+    int64_t num_free;      /* voxels updated with type 'free' (:567) */
+    int64_t num_voxels;    /* len(octree.voxels) after the frame (:592) */
+    int64_t num_samples;   /* samples emitted by all rays after the z filter (len of the :542 loop) */
+} s3d_frame_stats;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+
+/* Create a map on CUDA device `device` with room for `initial_capacity` voxel slots (rounded
+ * up to a power of two; 0 = default).  The table grows by rehashing when needed.
+ * Replaces SimpleOctree.__init__ (:25-51). */
+int s3d_create(int device, uint64_t initial_capacity, s3d_map **out);
+int s3d_destroy(s3d_map *map);
+const char *s3d_last_error(void);
+int s3d_abi_version(void);
+
+int s3d_set_params(s3d_map *map, const s3d_params *params);
+int s3d_set_tables(s3d_map *map, const s3d_tables *tables);
+
+/* ---- ingest: SonarTo3DMapper.process_sonar_image (:485-595) ----------------------------- */
+
+/* One frame.  `image` is uint8[H*W] row-major (rows = range), `T` the row-major 4x4
+ * T_sonar_to_world (:521).  Runs first-hit scan, free/occupied expansion, transform, key
+ * quantisation, per-frame dedupe and the adaptive clamped log-odds update on the device and
+ * returns the counters.  Synchronous. */
+int s3d_ingest(s3d_map *map, const uint8_t *image, const double T[16], s3d_frame_stats *out);
+
+/* `n` frames in sequence order (frame f is fully applied before frame f+1, as N successive
+ * process_sonar_image calls would).  images: uint8[n*H*W]; T: double[n*16]; out: [n] or NULL.
+ * Synchronous: returns when all frames are applied and `out` is filled. */
+int s3d_ingest_batch(s3d_map *map, const uint8_t *images, int64_t n, const double *T,
+                     s3d_frame_stats *out);
+
+/* Same with inputs already resident in device memory (bench `value` path; multi-GPU path).
+ * Asynchronous on the map's stream when out == NULL; s3d_sync() or any synchronous call
+ * orders after it.  `stats_dev`, if not NULL, receives n s3d_frame_stats in device memory. */
+int s3d_ingest_batch_dev(s3d_map *map, const uint8_t *images_dev, int64_t n, const double *T_dev,
+                         s3d_frame_stats *out, s3d_frame_stats *stats_dev);
+
+/* Make sure the table can take `n_frames` more frames without growing inside a timed region. */
+int s3d_reserve(s3d_map *map, uint64_t n_voxels);
+int s3d_sync(s3d_map *map);
+/* The map's cudaStream_t (for CUDA-event timing on the launching stream). */
+void *s3d_stream(s3d_map *map);
+
+/* ---- store: SimpleOctree (:83-125, :190-194) -------------------------------------------- */
+
+/* update_voxel (:83-115) for n (key, delta, adaptive) triples, applied in array order (equal
+ * keys are applied one after the other exactly as n successive calls would). */
+int s3d_apply_updates(s3d_map *map, const int32_t *ijk, const double *delta,
+                      const uint8_t *adaptive, int64_t n);
+/* get_log_odds (:117-120): absent -> 0.0 and found = 0; never inserts. */
+int s3d_query(s3d_map *map, const int32_t *ijk, int64_t n, double *log_odds, uint8_t *found);
+/* len(voxels) (:592) */
+int s3d_count(s3d_map *map, uint64_t *count);
+/* voxels.items() (:147, :173): up to `cap` (key, log-odds) pairs in table order. */
+int s3d_dump(s3d_map *map, int32_t *ijk, double *log_odds, uint64_t cap, uint64_t *n_out);
+/* Bulk insert/overwrite of (key, log-odds) pairs: restore of a dump. */
+int s3d_load(s3d_map *map, const int32_t *ijk, const double *log_odds, int64_t n);
+/* clear (:190-194) */
+int s3d_clear(s3d_map *map);
+/* Integer bounding box of every key ever updated; min/max_bounds (:113-115) follow as
+ * (k + 0.5) * resolution.  empty map: kmin > kmax. */
+int s3d_bounds(s3d_map *map, int32_t kmin[3], int32_t kmax[3]);
+uint64_t s3d_capacity(s3d_map *map);
+
+/* ---- export: get_occupied_voxels / get_all_voxels_classified (:127-188) ------------------ */
+
+#define S3D_CLASS_FREE 0
+#define S3D_CLASS_UNKNOWN 1
+#define S3D_CLASS_OCCUPIED 2
+
+/* Scan the table once on the device.  A voxel is FREE if L < thr_free (:177), else OCCUPIED
+ * if L > thr_occ (:148, :179), else UNKNOWN.  Voxels whose class bit is set in `class_mask`
+ * are compacted into a device staging buffer (centre = (k+0.5)*resolution (:78-80),
+ * probability = 1/(1+exp(-L)) (:150, :175)).  counts[3] receives the per-class totals,
+ * *n_out the number staged.  Pass thr_free = -inf for the occupied-only query. */
+int s3d_export_begin(s3d_map *map, double thr_occ, double thr_free, uint32_t class_mask,
+                     uint64_t counts[3], uint64_t *n_out);
+/* Copy the staged result to host arrays (any may be NULL): xyz double[n*3], prob double[n],
+ * cls int8[n], ijk int32[n*3].  n must equal *n_out of the last s3d_export_begin. */
+int s3d_export_read(s3d_map *map, double *xyz, double *prob, int8_t *cls, int32_t *ijk, uint64_t n);
+/* Same result as the PointCloud2 payload of the reference node: little-endian float32
+ * x, y, z, intensity=probability, 16-byte stride (scripts/3d_mapper_node.py:419-443). */
+int s3d_export_read_xyzi32(s3d_map *map, float *xyzi, uint64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SONAR3D_H */

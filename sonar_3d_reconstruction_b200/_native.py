@@ -1,0 +1,244 @@
+"""ctypes binding of libsonar3d.so (include/sonar3d.h).  No CPU fallback: if the CUDA library
+is missing or no GPU is visible, construction fails loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libsonar3d.so")
+
+# every symbol include/sonar3d.h declares (tests check the list against the header and the .so)
+SYMBOLS = (
+    "s3d_create", "s3d_destroy", "s3d_last_error", "s3d_abi_version", "s3d_set_params", "s3d_set_tables",
+    "s3d_ingest", "s3d_ingest_batch", "s3d_ingest_batch_dev", "s3d_reserve", "s3d_sync", "s3d_stream",
+    "s3d_apply_updates", "s3d_query", "s3d_count", "s3d_dump", "s3d_load", "s3d_clear", "s3d_bounds",
+    "s3d_capacity", "s3d_export_begin", "s3d_export_read", "s3d_export_read_xyzi32",
+)
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libsonar3d error {code}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [("resolution", C.c_double), ("log_odds_occupied", C.c_double), ("log_odds_free", C.c_double),
+                ("log_odds_min", C.c_double), ("log_odds_max", C.c_double), ("adaptive_threshold", C.c_double),
+                ("adaptive_max_ratio", C.c_double), ("z_filter_min", C.c_double), ("adaptive_update", C.c_int32),
+                ("z_filter_enabled", C.c_int32), ("intensity_threshold", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Tables(C.Structure):
+    _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("n_beams", C.c_int32), ("nv_max", C.c_int32),
+                ("free_step", C.c_int32), ("occ_window", C.c_int32),
+                ("beam_col", C.POINTER(C.c_int32)), ("cos_b", C.POINTER(C.c_double)), ("sin_b", C.POINTER(C.c_double)),
+                ("range_m", C.POINTER(C.c_double)), ("nv_free", C.POINTER(C.c_int32)), ("nv_occ", C.POINTER(C.c_int32)),
+                ("cos_va", C.POINTER(C.c_double)), ("sin_va", C.POINTER(C.c_double))]
+
+
+class FrameStats(C.Structure):
+    _fields_ = [("num_occupied", C.c_int64), ("num_free", C.c_int64), ("num_voxels", C.c_int64),
+                ("num_samples", C.c_int64)]
+
+
+STATS_DTYPE = np.dtype([("num_occupied", "<i8"), ("num_free", "<i8"), ("num_voxels", "<i8"), ("num_samples", "<i8")])
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; raise (never fall back) if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  sonar_3d_reconstruction_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, u8p, dp, i32p, i8p, u64p = (C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_int8), C.POINTER(C.c_uint64))
+    sp = C.POINTER(FrameStats)
+    L.s3d_last_error.restype = C.c_char_p
+    L.s3d_abi_version.restype = C.c_int
+    L.s3d_create.argtypes = [C.c_int, C.c_uint64, C.POINTER(vp)]
+    L.s3d_destroy.argtypes = [vp]
+    L.s3d_set_params.argtypes = [vp, C.POINTER(Params)]
+    L.s3d_set_tables.argtypes = [vp, C.POINTER(Tables)]
+    L.s3d_ingest.argtypes = [vp, vp, dp, sp]
+    L.s3d_ingest_batch.argtypes = [vp, vp, C.c_int64, dp, vp]
+    L.s3d_ingest_batch_dev.argtypes = [vp, vp, C.c_int64, vp, vp, vp]
+    L.s3d_reserve.argtypes = [vp, C.c_uint64]
+    L.s3d_sync.argtypes = [vp]
+    L.s3d_stream.argtypes = [vp]
+    L.s3d_stream.restype = vp
+    L.s3d_apply_updates.argtypes = [vp, i32p, dp, u8p, C.c_int64]
+    L.s3d_query.argtypes = [vp, i32p, C.c_int64, dp, u8p]
+    L.s3d_count.argtypes = [vp, u64p]
+    L.s3d_dump.argtypes = [vp, i32p, dp, C.c_uint64, u64p]
+    L.s3d_load.argtypes = [vp, i32p, dp, C.c_int64]
+    L.s3d_clear.argtypes = [vp]
+    L.s3d_bounds.argtypes = [vp, i32p, i32p]
+    L.s3d_capacity.argtypes = [vp]
+    L.s3d_capacity.restype = C.c_uint64
+    L.s3d_export_begin.argtypes = [vp, C.c_double, C.c_double, C.c_uint32, u64p, u64p]
+    L.s3d_export_read.argtypes = [vp, dp, dp, i8p, i32p, C.c_uint64]
+    L.s3d_export_read_xyzi32.argtypes = [vp, C.POINTER(C.c_float), C.c_uint64]
+    for name in SYMBOLS:
+        getattr(L, name)          # AttributeError here = header / library mismatch
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise NativeError(rc, load_library().s3d_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a: Optional[np.ndarray], typ):
+    return None if a is None else a.ctypes.data_as(C.POINTER(typ))
+
+
+class NativeMap:
+    """One GPU-resident voxel hash table + the per-frame kernels (opaque s3d_map handle)."""
+
+    CLASS_FREE, CLASS_UNKNOWN, CLASS_OCCUPIED = 0, 1, 2
+
+    def __init__(self, device: int = 0, capacity: int = 0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        _check(self._lib.s3d_create(int(device), int(capacity), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self._keep = None       # keeps the table arrays alive for the duration of set_tables
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.s3d_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration ------------------------------------------------------------------
+    def set_params(self, p: Params):
+        _check(self._lib.s3d_set_params(self._h, C.byref(p)))
+
+    def set_tables(self, t: "HostTables"):
+        s = Tables()
+        s.H, s.W, s.n_beams, s.nv_max = t.H, t.W, len(t.beam_col), t.nv_max
+        s.free_step, s.occ_window = t.free_step, t.occ_window
+        s.beam_col = _ptr(t.beam_col, C.c_int32)
+        s.cos_b, s.sin_b = _ptr(t.cos_b, C.c_double), _ptr(t.sin_b, C.c_double)
+        s.range_m = _ptr(t.range_m, C.c_double)
+        s.nv_free, s.nv_occ = _ptr(t.nv_free, C.c_int32), _ptr(t.nv_occ, C.c_int32)
+        s.cos_va, s.sin_va = _ptr(t.cos_va, C.c_double), _ptr(t.sin_va, C.c_double)
+        _check(self._lib.s3d_set_tables(self._h, C.byref(s)))
+
+    # -- ingest -------------------------------------------------------------------------
+    def ingest(self, image_u8: np.ndarray, T: np.ndarray) -> Tuple[int, int, int, int]:
+        st = FrameStats()
+        T = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        _check(self._lib.s3d_ingest(self._h, image_u8.ctypes.data, _ptr(T, C.c_double), C.byref(st)))
+        return st.num_occupied, st.num_free, st.num_voxels, st.num_samples
+
+    def ingest_batch(self, images_u8: np.ndarray, T: np.ndarray) -> np.ndarray:
+        n = int(images_u8.shape[0])
+        T = np.ascontiguousarray(T, dtype=np.float64).reshape(n, 16)
+        out = np.zeros(n, dtype=STATS_DTYPE)
+        _check(self._lib.s3d_ingest_batch(self._h, images_u8.ctypes.data, n, _ptr(T, C.c_double), out.ctypes.data))
+        return out
+
+    def ingest_batch_dev(self, images_ptr: int, n: int, T_ptr: int, want_stats: bool = True,
+                         stats_dev_ptr: int = 0) -> Optional[np.ndarray]:
+        out = np.zeros(n, dtype=STATS_DTYPE) if want_stats else None
+        _check(self._lib.s3d_ingest_batch_dev(self._h, images_ptr, int(n), T_ptr,
+                                              out.ctypes.data if want_stats else None, stats_dev_ptr or None))
+        return out
+
+    def reserve(self, n_voxels: int):
+        _check(self._lib.s3d_reserve(self._h, int(n_voxels)))
+
+    def sync(self):
+        _check(self._lib.s3d_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.s3d_stream(self._h) or 0)
+
+    @property
+    def capacity(self) -> int:
+        return int(self._lib.s3d_capacity(self._h))
+
+    # -- store --------------------------------------------------------------------------
+    def apply_updates(self, ijk: np.ndarray, delta: np.ndarray, adaptive: np.ndarray):
+        ijk = np.ascontiguousarray(ijk, dtype=np.int32).reshape(-1, 3)
+        delta = np.ascontiguousarray(delta, dtype=np.float64).reshape(-1)
+        adaptive = np.ascontiguousarray(adaptive, dtype=np.uint8).reshape(-1)
+        _check(self._lib.s3d_apply_updates(self._h, _ptr(ijk, C.c_int32), _ptr(delta, C.c_double),
+                                           _ptr(adaptive, C.c_uint8), len(ijk)))
+
+    def query(self, ijk: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        ijk = np.ascontiguousarray(ijk, dtype=np.int32).reshape(-1, 3)
+        L = np.zeros(len(ijk), dtype=np.float64)
+        found = np.zeros(len(ijk), dtype=np.uint8)
+        _check(self._lib.s3d_query(self._h, _ptr(ijk, C.c_int32), len(ijk), _ptr(L, C.c_double), _ptr(found, C.c_uint8)))
+        return L, found.astype(bool)
+
+    def count(self) -> int:
+        n = C.c_uint64()
+        _check(self._lib.s3d_count(self._h, C.byref(n)))
+        return int(n.value)
+
+    def dump(self) -> Tuple[np.ndarray, np.ndarray]:
+        cap = self.count()
+        ijk = np.empty((cap, 3), dtype=np.int32)
+        L = np.empty(cap, dtype=np.float64)
+        n = C.c_uint64()
+        _check(self._lib.s3d_dump(self._h, _ptr(ijk, C.c_int32), _ptr(L, C.c_double), cap, C.byref(n)))
+        k = min(cap, int(n.value))
+        return ijk[:k], L[:k]
+
+    def load(self, ijk: np.ndarray, log_odds: np.ndarray):
+        ijk = np.ascontiguousarray(ijk, dtype=np.int32).reshape(-1, 3)
+        log_odds = np.ascontiguousarray(log_odds, dtype=np.float64).reshape(-1)
+        _check(self._lib.s3d_load(self._h, _ptr(ijk, C.c_int32), _ptr(log_odds, C.c_double), len(ijk)))
+
+    def clear(self):
+        _check(self._lib.s3d_clear(self._h))
+
+    def bounds(self) -> Tuple[np.ndarray, np.ndarray]:
+        kmin = np.zeros(3, dtype=np.int32)
+        kmax = np.zeros(3, dtype=np.int32)
+        _check(self._lib.s3d_bounds(self._h, _ptr(kmin, C.c_int32), _ptr(kmax, C.c_int32)))
+        return kmin, kmax
+
+    # -- export -------------------------------------------------------------------------
+    def export(self, thr_occ: float, thr_free: float, class_mask: int, want=("xyz", "prob", "cls")):
+        counts = (C.c_uint64 * 3)()
+        n = C.c_uint64()
+        _check(self._lib.s3d_export_begin(self._h, float(thr_occ), float(thr_free), int(class_mask), counts, C.byref(n)))
+        n = int(n.value)
+        out = {"counts": [int(c) for c in counts], "n": n}
+        xyz = np.empty((n, 3), dtype=np.float64) if "xyz" in want else None
+        prob = np.empty(n, dtype=np.float64) if "prob" in want else None
+        cls = np.empty(n, dtype=np.int8) if "cls" in want else None
+        ijk = np.empty((n, 3), dtype=np.int32) if "ijk" in want else None
+        if n and (xyz is not None or prob is not None or cls is not None or ijk is not None):
+            _check(self._lib.s3d_export_read(self._h, _ptr(xyz, C.c_double), _ptr(prob, C.c_double),
+                                             _ptr(cls, C.c_int8), _ptr(ijk, C.c_int32), n))
+        if "xyzi32" in want:
+            blob = np.empty((n, 4), dtype=np.float32)
+            if n:
+                _check(self._lib.s3d_export_read_xyzi32(self._h, blob.ctypes.data_as(C.POINTER(C.c_float)), n))
+            out["xyzi32"] = blob
+        out.update(xyz=xyz, prob=prob, cls=cls, ijk=ijk)
+        return out

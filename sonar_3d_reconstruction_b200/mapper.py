@@ -1,0 +1,488 @@
+"""Drop-in mirror of the reference's Python operator API for the hot path.
+
+`SimpleOctree` and `SonarTo3DMapper` keep the names, arguments, attributes, return shapes and
+error behaviour of luckkim123/sonar_3d_reconstruction scripts/3d_mapper.py (classes at :19 and
+:197), but the voxel store is a GPU-resident hash table and every per-frame step runs in the
+sm_100a kernels of csrc/sonar3d.cu, reached through the C-ABI of include/sonar3d.h.  The host
+keeps only what the reference itself does once per frame in a handful of flops: the pose ->
+4x4 chain (:346-380, :520-521), evaluated with the same numpy expressions so the matrix that
+reaches the device is bit-identical to the reference's.
+
+There is no CPU fallback: constructing either class without the built CUDA library or
+without a visible GPU raises.
+"""
+from __future__ import annotations
+
+import time
+from collections import defaultdict
+from collections.abc import Sequence
+from typing import Any, Dict, Iterator, List, Optional, Tuple
+
+import numpy as np
+
+from . import tables as _tables
+from ._native import NativeMap, Params
+
+__all__ = ["SimpleOctree", "SonarTo3DMapper"]
+
+
+def _threshold_to_int(thr) -> int:
+    """Integer t such that (pixel > t) == (pixel > thr) for every uint8 pixel (:407, :452)."""
+    try:
+        t = float(thr)
+    except (TypeError, ValueError):
+        raise TypeError(f"intensity_threshold must be a number, got {thr!r}")
+    if t != t:          # NaN: nothing is > NaN
+        return 255
+    return int(min(255.0, max(-1.0, np.floor(t))))
+
+
+class _PointProbSeq(Sequence):
+    """Read-only sequence of (point ndarray[3], probability) pairs over two device-exported
+    arrays: what get_occupied_voxels / get_all_voxels_classified return as Python lists in the
+    reference (:151, :178-182), without materialising one tuple per voxel up front."""
+
+    __slots__ = ("points", "probabilities")
+
+    def __init__(self, points: np.ndarray, probabilities: np.ndarray):
+        self.points = points
+        self.probabilities = probabilities
+
+    def __len__(self) -> int:
+        return len(self.probabilities)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return _PointProbSeq(self.points[i], self.probabilities[i])
+        return (self.points[i], float(self.probabilities[i]))
+
+    def __iter__(self) -> Iterator[Tuple[np.ndarray, float]]:
+        for p, q in zip(self.points, self.probabilities.tolist()):
+            yield (p, q)
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+
+class _VoxelView:
+    """Device-backed stand-in for the reference's `voxels` defaultdict(float) (:34): keys are
+    (i, j, k) int tuples, values float log-odds.  Reads go to the GPU table on demand."""
+
+    def __init__(self, octree: "SimpleOctree"):
+        self._o = octree
+
+    @staticmethod
+    def _key(key) -> np.ndarray:
+        k = np.asarray(key, dtype=np.int64).reshape(3)
+        return k
+
+    def __len__(self) -> int:
+        return self._o._native.count()
+
+    def __contains__(self, key) -> bool:
+        _, found = self._o._native.query(self._key(key)[None])
+        return bool(found[0])
+
+    def get(self, key, default=None):
+        L, found = self._o._native.query(self._key(key)[None])
+        return float(L[0]) if found[0] else default
+
+    def __getitem__(self, key) -> float:
+        # defaultdict(float): a missing key is created with 0.0
+        L, found = self._o._native.query(self._key(key)[None])
+        if not found[0]:
+            self._o._native.load(self._key(key)[None], np.zeros(1))
+            return 0.0
+        return float(L[0])
+
+    def __setitem__(self, key, value):
+        self._o._native.load(self._key(key)[None], np.asarray([float(value)]))
+
+    def items(self):
+        ijk, L = self._o._native.dump()
+        return list(zip(map(tuple, ijk.tolist()), L.tolist()))
+
+    def keys(self):
+        ijk, _ = self._o._native.dump()
+        return [tuple(k) for k in ijk.tolist()]
+
+    def values(self):
+        _, L = self._o._native.dump()
+        return L.tolist()
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def clear(self):
+        self._o._native.clear()
+
+    def to_arrays(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(keys int32[n,3], log-odds float64[n]) in one device pass (extension)."""
+        return self._o._native.dump()
+
+
+class SimpleOctree:
+    """Sparse voxel store with log-odds values (reference: scripts/3d_mapper.py:19-194), kept
+    in a GPU open-addressing hash table."""
+
+    def __init__(self, resolution: float = 0.03, dynamic_expansion: bool = True, *, device: int = 0,
+                 capacity: int = 0):
+        self.resolution = resolution
+        self.dynamic_expansion = dynamic_expansion
+        # log-odds parameters, public and mutable as in the reference (:42-51)
+        self.log_odds_occupied = 1.5
+        self.log_odds_free = -2.0
+        self.log_odds_min = -10.0
+        self.log_odds_max = 10.0
+        self.log_odds_threshold = 0.0
+        self.adaptive_update = True
+        self.adaptive_threshold = 0.5
+        self.adaptive_max_ratio = 0.5
+        self._native = NativeMap(device=device, capacity=capacity)
+        self.voxels = _VoxelView(self)
+        # bounds contributed by direct update_voxel(point) calls; ingest bounds live on the device
+        self._pt_min = np.array([float("inf")] * 3)
+        self._pt_max = np.array([-float("inf")] * 3)
+        # mapper-owned settings that travel in the same parameter block
+        self._z_filter_min = -5.0
+        self._z_filter_enabled = False
+        self._intensity_threshold = 35
+        self._pushed = None
+
+    # -- parameter block ------------------------------------------------------------------
+    def _push_params(self):
+        sig = (float(self.resolution), float(self.log_odds_occupied), float(self.log_odds_free),
+               float(self.log_odds_min), float(self.log_odds_max), float(self.adaptive_threshold),
+               float(self.adaptive_max_ratio), float(self._z_filter_min), int(bool(self.adaptive_update)),
+               int(bool(self._z_filter_enabled)), _threshold_to_int(self._intensity_threshold))
+        if sig != self._pushed:
+            p = Params(*sig, 0)
+            self._native.set_params(p)
+            self._pushed = sig
+
+    # -- key <-> world (:53-81) -----------------------------------------------------------
+    def world_to_key(self, x: float, y: float, z: float) -> Tuple[int, int, int]:
+        i = int(np.floor(x / self.resolution))
+        j = int(np.floor(y / self.resolution))
+        k = int(np.floor(z / self.resolution))
+        return (i, j, k)
+
+    def key_to_world(self, key: Tuple[int, int, int]) -> np.ndarray:
+        x = (key[0] + 0.5) * self.resolution
+        y = (key[1] + 0.5) * self.resolution
+        z = (key[2] + 0.5) * self.resolution
+        return np.array([x, y, z])
+
+    # -- update / query (:83-125) ---------------------------------------------------------
+    def update_voxel(self, point: np.ndarray, log_odds_update: float, adaptive: bool = True):
+        key = self.world_to_key(point[0], point[1], point[2])
+        self._push_params()
+        self._native.apply_updates(np.asarray([key], dtype=np.int64), np.asarray([float(log_odds_update)]),
+                                   np.asarray([1 if adaptive else 0], dtype=np.uint8))
+        if self.dynamic_expansion:
+            self._pt_min = np.minimum(self._pt_min, point)
+            self._pt_max = np.maximum(self._pt_max, point)
+
+    def update_voxels(self, points: np.ndarray, log_odds_updates: np.ndarray, adaptive=True):
+        """Bulk update_voxel (extension): same result as calling update_voxel row by row."""
+        points = np.asarray(points, dtype=np.float64).reshape(-1, 3)
+        keys = np.floor(points / self.resolution).astype(np.int64)
+        n = len(keys)
+        adp = np.broadcast_to(np.asarray(adaptive, dtype=np.uint8), (n,))
+        self._push_params()
+        self._native.apply_updates(keys, np.asarray(log_odds_updates, dtype=np.float64), adp)
+        if self.dynamic_expansion and n:
+            self._pt_min = np.minimum(self._pt_min, points.min(axis=0))
+            self._pt_max = np.maximum(self._pt_max, points.max(axis=0))
+
+    def get_log_odds(self, x: float, y: float, z: float) -> float:
+        key = self.world_to_key(x, y, z)
+        L, _ = self._native.query(np.asarray([key], dtype=np.int64))
+        return float(L[0])
+
+    def get_probability(self, x: float, y: float, z: float) -> float:
+        log_odds = self.get_log_odds(x, y, z)
+        return 1.0 / (1.0 + np.exp(-log_odds))
+
+    # -- bounds (:113-115) ----------------------------------------------------------------
+    def _bounds(self) -> Tuple[np.ndarray, np.ndarray]:
+        mn, mx = self._pt_min.copy(), self._pt_max.copy()
+        if self.dynamic_expansion:
+            kmin, kmax = self._native.bounds()
+            if (kmin <= kmax).all():
+                # centres of the extreme voxels: key_to_world is monotone in the key
+                mn = np.minimum(mn, (kmin.astype(np.float64) + 0.5) * self.resolution)
+                mx = np.maximum(mx, (kmax.astype(np.float64) + 0.5) * self.resolution)
+        return mn, mx
+
+    @property
+    def min_bounds(self) -> np.ndarray:
+        return self._bounds()[0]
+
+    @property
+    def max_bounds(self) -> np.ndarray:
+        return self._bounds()[1]
+
+    # -- export (:127-188) ----------------------------------------------------------------
+    def _occupied_threshold(self, min_probability: float) -> float:
+        if min_probability >= 1.0:
+            return self.log_odds_max - 0.01
+        if min_probability <= 0.0:
+            return self.log_odds_min
+        return float(np.log(min_probability / (1.0 - min_probability)))
+
+    def _export_occupied(self, min_probability: float, want=("xyz", "prob")):
+        self._push_params()
+        thr = self._occupied_threshold(min_probability)
+        return self._native.export(thr, -float("inf"), 1 << NativeMap.CLASS_OCCUPIED, want=want)
+
+    def get_occupied_voxels(self, min_probability: float = 0.5) -> Sequence:
+        r = self._export_occupied(min_probability)
+        return _PointProbSeq(r["xyz"], r["prob"])
+
+    def get_all_voxels_classified(self, min_probability: float = 0.7) -> Dict[str, Sequence]:
+        self._push_params()
+        free_threshold = float(np.log(0.3 / 0.7))
+        occupied_threshold = float(np.log(min_probability / (1.0 - min_probability)))
+        r = self._native.export(occupied_threshold, free_threshold, 0b111)
+        out = {}
+        for name, c in (("free", NativeMap.CLASS_FREE), ("unknown", NativeMap.CLASS_UNKNOWN),
+                        ("occupied", NativeMap.CLASS_OCCUPIED)):
+            sel = r["cls"] == c
+            out[name] = _PointProbSeq(r["xyz"][sel], r["prob"][sel])
+        return out
+
+    def clear(self):
+        self._native.clear()
+        self._pt_min = np.array([float("inf")] * 3)
+        self._pt_max = np.array([-float("inf")] * 3)
+
+
+class SonarTo3DMapper:
+    """Sonar image + pose -> probabilistic voxel map (reference: scripts/3d_mapper.py:197-650)."""
+
+    def __init__(self, config: Optional[Dict[str, Any]] = None):
+        # library defaults (:220-250); `config` overrides them (:253-254)
+        default_config = {
+            'horizontal_fov': 130.0, 'vertical_aperture': 20.0, 'max_range': 10.0, 'min_range': 0.5,
+            'intensity_threshold': 35, 'image_width': 512, 'image_height': 500,
+            'sonar_position': [0.0, 0.0, -0.5], 'sonar_orientation': [0.0, 1.5708, 0.0],
+            'voxel_resolution': 0.05, 'min_probability': 0.6, 'dynamic_expansion': True,
+            'adaptive_update': True, 'adaptive_threshold': 0.5, 'adaptive_max_ratio': 0.3,
+            'log_odds_occupied': 1.5, 'log_odds_free': -2.0, 'log_odds_min': -10.0, 'log_odds_max': 10.0,
+        }
+        if config:
+            default_config.update(config)
+        c = default_config
+        self.horizontal_fov = np.radians(c['horizontal_fov'])
+        self.vertical_aperture = np.radians(c['vertical_aperture'])
+        self.max_range = c['max_range']
+        self.min_range = c['min_range']
+        self.intensity_threshold = c['intensity_threshold']
+        self.image_width = c['image_width']
+        self.image_height = c['image_height']
+        self.voxel_resolution = c['voxel_resolution']
+        self.min_probability = c['min_probability']
+        self.dynamic_expansion = c['dynamic_expansion']
+        self.z_filter_min = c.get('z_filter_min', -5.0)
+        self.z_filter_enabled = c.get('z_filter_enabled', False)
+        self.sonar_position = np.array(c['sonar_position'])
+        self.sonar_orientation = np.array(c['sonar_orientation'])
+        self.T_sonar_to_base = self.create_transform_matrix(self.sonar_position, self.sonar_orientation)
+
+        # extensions (not in the reference): which GPU, and the initial table size
+        self.octree = SimpleOctree(self.voxel_resolution, self.dynamic_expansion,
+                                   device=int(c.get('device', 0)), capacity=int(c.get('table_capacity', 0)))
+        self.octree.log_odds_occupied = c['log_odds_occupied']
+        self.octree.log_odds_free = c['log_odds_free']
+        self.octree.log_odds_min = c['log_odds_min']
+        self.octree.log_odds_max = c['log_odds_max']
+        self.octree.adaptive_update = c['adaptive_update']
+        self.octree.adaptive_threshold = c['adaptive_threshold']
+        self.octree.adaptive_max_ratio = c['adaptive_max_ratio']
+
+        self.bearing_angles = np.linspace(-self.horizontal_fov / 2, self.horizontal_fov / 2, self.image_width)
+
+        self.frame_count = 0
+        self.processed_frame_count = 0
+        # debug-only counters of the reference (:307-308); kept as (empty) attributes
+        self.voxel_update_counts = defaultdict(int)
+        self.frame_update_counts = defaultdict(int)
+        self.last_processing_time = 0.0
+        self.total_processing_time = 0.0
+        self.last_num_samples = 0
+        self._tables_sig = None
+
+    # -- transforms: same numpy expressions as the reference (:314-380) -----------------------
+    def create_transform_matrix(self, position: np.ndarray, rpy: np.ndarray) -> np.ndarray:
+        cr, sr = np.cos(rpy[0]), np.sin(rpy[0])
+        cp, sp = np.cos(rpy[1]), np.sin(rpy[1])
+        cy, sy = np.cos(rpy[2]), np.sin(rpy[2])
+        R = np.array([
+            [cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+            [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr],
+            [-sp, cp * sr, cp * cr],
+        ])
+        T = np.eye(4)
+        T[:3, :3] = R
+        T[:3, 3] = position
+        return T
+
+    def quaternion_to_matrix(self, quaternion: List[float]) -> np.ndarray:
+        x, y, z, w = quaternion
+        return np.array([
+            [1 - 2 * (y**2 + z**2), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+            [2 * (x * y + w * z), 1 - 2 * (x**2 + z**2), 2 * (y * z - w * x)],
+            [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x**2 + y**2)],
+        ])
+
+    def create_odometry_transform(self, position: List[float], quaternion: List[float]) -> np.ndarray:
+        T = np.eye(4)
+        T[:3, :3] = self.quaternion_to_matrix(quaternion)
+        T[:3, 3] = position
+        return T
+
+    def is_bearing_in_valid_fov(self, bearing_angle: float) -> bool:
+        return abs(bearing_angle) <= self.horizontal_fov / 2
+
+    # -- device configuration -------------------------------------------------------------------
+    def _sync_device_config(self, H: int, W: int):
+        oc = self.octree
+        oc._z_filter_min = self.z_filter_min
+        oc._z_filter_enabled = self.z_filter_enabled
+        oc._intensity_threshold = self.intensity_threshold
+        oc._push_params()
+        sig = (H, W, float(self.horizontal_fov), float(self.vertical_aperture), float(self.max_range),
+               float(self.min_range), float(self.voxel_resolution), self.bearing_angles.tobytes())
+        if sig != self._tables_sig:
+            t = _tables.build_tables(self.bearing_angles, self.horizontal_fov, self.vertical_aperture,
+                                     self.max_range, self.min_range, self.voxel_resolution, H, W)
+            oc._native.set_tables(t)
+            self._tables_sig = sig
+
+    def _as_device_image(self, polar_image: np.ndarray) -> np.ndarray:
+        """uint8, C-contiguous image whose `> threshold` mask equals the input's (:407, :452)."""
+        if polar_image.dtype == np.uint8:
+            return np.ascontiguousarray(polar_image)
+        # other dtypes (the node always sends uint8): keep only what the algorithm reads
+        return np.ascontiguousarray(np.where(polar_image > self.intensity_threshold, 255, 0).astype(np.uint8))
+
+    def _check_width(self, bearing_bins: int):
+        if bearing_bins != self.image_width:                                     # :511-517
+            self.bearing_angles = np.linspace(-self.horizontal_fov / 2, self.horizontal_fov / 2, bearing_bins)
+            self.image_width = bearing_bins
+
+    # -- ingest (:485-595) ------------------------------------------------------------------------
+    def process_sonar_image(self, polar_image: np.ndarray, robot_position: List[float],
+                            robot_orientation: List[float]) -> Dict[str, Any]:
+        self.frame_count += 1
+        start_time = time.time()
+        self.processed_frame_count += 1
+        if not isinstance(polar_image, np.ndarray):
+            polar_image = np.array(polar_image)
+        range_bins, bearing_bins = polar_image.shape
+        self._check_width(bearing_bins)
+        T_base_to_world = self.create_odometry_transform(robot_position, robot_orientation)
+        T_sonar_to_world = T_base_to_world @ self.T_sonar_to_base
+        self._sync_device_config(range_bins, bearing_bins)
+        img = self._as_device_image(polar_image)
+        if img.dtype != polar_image.dtype:
+            saved, self.octree._intensity_threshold = self.octree._intensity_threshold, 0
+            self.octree._push_params()
+            n_occ, n_free, n_vox, n_samp = self.octree._native.ingest(img, T_sonar_to_world)
+            self.octree._intensity_threshold = saved
+        else:
+            n_occ, n_free, n_vox, n_samp = self.octree._native.ingest(img, T_sonar_to_world)
+        self.last_num_samples = n_samp
+        processing_time = time.time() - start_time
+        self.last_processing_time = processing_time
+        self.total_processing_time += processing_time
+        return {
+            'frame_count': self.frame_count,
+            'processed_count': self.processed_frame_count,
+            'num_occupied': n_occ,
+            'num_free': n_free,
+            'num_voxels': n_vox,
+            'processing_time': processing_time,
+            'avg_processing_time': self.total_processing_time / max(1, self.processed_frame_count),
+        }
+
+    def compose_transforms(self, positions, orientations) -> np.ndarray:
+        """T_sonar_to_world for each pose, float64[n,4,4], evaluated as the per-frame path does."""
+        out = np.empty((len(positions), 4, 4))
+        for f in range(len(positions)):
+            out[f] = self.create_odometry_transform(positions[f], orientations[f]) @ self.T_sonar_to_base
+        return out
+
+    def process_sonar_images(self, polar_images: np.ndarray, robot_positions, robot_orientations
+                             ) -> List[Dict[str, Any]]:
+        """Batched ingest (extension; BASELINE config 5): the frames are applied in order, with
+        the same result as calling process_sonar_image once per frame, in one C-ABI call."""
+        start_time = time.time()
+        polar_images = np.asarray(polar_images)
+        n, range_bins, bearing_bins = polar_images.shape
+        if polar_images.dtype != np.uint8:
+            raise TypeError("process_sonar_images expects uint8 images")
+        self._check_width(bearing_bins)
+        T = self.compose_transforms(robot_positions, robot_orientations)
+        self._sync_device_config(range_bins, bearing_bins)
+        st = self.octree._native.ingest_batch(np.ascontiguousarray(polar_images), T)
+        dt = time.time() - start_time
+        out = []
+        for f in range(n):
+            self.frame_count += 1
+            self.processed_frame_count += 1
+            self.last_processing_time = dt / n
+            self.total_processing_time += dt / n
+            out.append({'frame_count': self.frame_count, 'processed_count': self.processed_frame_count,
+                        'num_occupied': int(st['num_occupied'][f]), 'num_free': int(st['num_free'][f]),
+                        'num_voxels': int(st['num_voxels'][f]), 'processing_time': dt / n,
+                        'avg_processing_time': self.total_processing_time / max(1, self.processed_frame_count)})
+        if n:
+            self.last_num_samples = int(st['num_samples'][-1])
+        return out
+
+    # -- export (:597-642) ------------------------------------------------------------------------
+    def get_point_cloud(self, include_free: bool = False) -> Dict[str, Any]:
+        if include_free:
+            classified = self.octree.get_all_voxels_classified(self.min_probability)
+            return {
+                'occupied': classified['occupied'],
+                'free': classified['free'],
+                'unknown': classified['unknown'],
+                'num_voxels': len(self.octree.voxels),
+                'num_occupied': len(classified['occupied']),
+                'num_free': len(classified['free']),
+                'num_unknown': len(classified['unknown']),
+                'frame_count': self.frame_count,
+                'processed_count': self.processed_frame_count,
+                'bounds': {
+                    'min': self.octree.min_bounds.copy() if self.octree.dynamic_expansion else None,
+                    'max': self.octree.max_bounds.copy() if self.octree.dynamic_expansion else None,
+                },
+            }
+        r = self.octree._export_occupied(self.min_probability)
+        n = r["n"]
+        points = r["xyz"] if n else np.empty((0, 3))
+        probabilities = r["prob"] if n else np.empty(0)
+        return {
+            'points': points,
+            'probabilities': probabilities,
+            'num_voxels': len(self.octree.voxels),
+            'num_occupied': n,
+            'frame_count': self.frame_count,
+            'processed_count': self.processed_frame_count,
+        }
+
+    def get_point_cloud_xyzi32(self) -> np.ndarray:
+        """Occupied voxels as the node's PointCloud2 payload: float32[n,4] = x, y, z, probability
+        (scripts/3d_mapper_node.py:419-443), packed on the device (extension)."""
+        r = self.octree._export_occupied(self.min_probability, want=("xyzi32",))
+        return r["xyzi32"]
+
+    def reset_map(self):
+        self.octree.clear()
+        self.frame_count = 0
+        self.processed_frame_count = 0
+        self.total_processing_time = 0.0
+        print("Map reset")

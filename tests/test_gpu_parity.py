@@ -1,0 +1,206 @@
+"""CUDA path (through the Python mirror -> C-ABI -> sm_100a kernels) vs the golden vectors of
+the unmodified reference and vs the CPU oracle.  Bar (BASELINE.json north_star): voxel-key sets
+bit-exact, per-frame counters exact, |d log-odds| <= 1e-5 per voxel."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, assert_same_map, golden_config, load_golden, sort_by_key
+
+pytestmark = pytest.mark.gpu
+
+LOGODDS_ATOL = 1e-5          # north_star tolerance
+SEQS = ["seq_cfg1_default", "seq_kiro_yaml", "seq_small_noadapt", "seq_wide_step4", "seq_overlap_clamp"]
+
+
+@pytest.fixture(scope="module")
+def s3d():
+    import sonar_3d_reconstruction_b200 as pkg
+    return pkg
+
+
+def _stats3(st):
+    return [st["num_occupied"], st["num_free"], st["num_voxels"]]
+
+
+def test_selftest_known_answers(s3d):
+    """The reference's own __main__ sequence (scripts/3d_mapper.py:653-683)."""
+    with open(os.path.join(GOLDEN, "selftest_known_answers.json")) as f:
+        ka = json.load(f)
+    m = s3d.SonarTo3DMapper({"voxel_resolution": 0.1, "min_probability": 0.6, "intensity_threshold": 30})
+    img = np.zeros((500, 512), dtype=np.uint8)
+    img[100:150, 200:300] = 100
+    img[300:350, 100:150] = 150
+    stats = [_stats3(m.process_sonar_image(img, [i * 0.1, 0, 0], [0, 0, 0, 1])) for i in range(3)]
+    assert stats == ka["stats"]
+    keys, vals = m.octree.voxels.to_arrays()
+    ks, vs = sort_by_key(keys, vals)
+    assert hashlib.sha256(ks.tobytes()).hexdigest()[:16] == ka["sha_keys"]
+    assert abs(float(vs.sum()) - ka["sum_logodds"]) <= 1e-6
+    assert float(vs.min()) == ka["min_logodds"] and abs(float(vs.max()) - ka["max_logodds"]) <= LOGODDS_ATOL
+    pc = m.get_point_cloud()
+    assert pc["num_occupied"] == ka["num_occupied"] and pc["num_voxels"] == 84325
+    assert pc["points"].shape == (5710, 3) and pc["probabilities"].shape == (5710,)
+    pcf = m.get_point_cloud(include_free=True)
+    assert [pcf["num_occupied"], pcf["num_free"], pcf["num_unknown"]] == ka["counts"]
+    assert pcf["bounds"]["min"].tolist() == ka["min_bounds"] and pcf["bounds"]["max"].tolist() == ka["max_bounds"]
+    assert (pcf["frame_count"], pcf["processed_count"]) == (3, 3)
+
+
+@pytest.mark.parametrize("name", SEQS)
+def test_golden_sequences(s3d, name):
+    g = load_golden(name)
+    m = s3d.SonarTo3DMapper(golden_config(g))
+    for f in range(len(g["images"])):
+        st = m.process_sonar_image(g["images"][f], list(g["positions"][f]), list(g["quaternions"][f]))
+        assert _stats3(st) == g["stats"][f].tolist(), f"frame {f}"
+        if f"ckpt{f}_keys" in g:
+            k, v = m.octree.voxels.to_arrays()
+            assert_same_map(k, v, g[f"ckpt{f}_keys"], g[f"ckpt{f}_logodds"], LOGODDS_ATOL, f"{name} ckpt {f}")
+    keys, vals = m.octree.voxels.to_arrays()
+    err = assert_same_map(keys, vals, g["keys"], g["logodds"], LOGODDS_ATOL, name)
+    assert err <= 1e-9, f"log-odds drifted more than fp64 rounding explains: {err}"
+    # export: same occupied set, centres bit-exact, probabilities to fp64 rounding
+    pc = m.get_point_cloud()
+    res = m.voxel_resolution
+    kg, pg, qg = sort_by_key(np.floor(pc["points"] / res), pc["points"], pc["probabilities"])
+    kr, pr, qr = sort_by_key(np.floor(g["pc_points"] / res), g["pc_points"], g["pc_prob"])
+    assert np.array_equal(kg, kr) and np.array_equal(pg, pr)
+    assert np.abs(qg - qr).max(initial=0.0) <= 1e-9
+    pcf = m.get_point_cloud(True)
+    assert [pcf["num_occupied"], pcf["num_free"], pcf["num_unknown"]] == g["counts"].tolist()
+    assert len(pcf["occupied"]) == g["counts"][0]
+    assert np.array_equal(m.octree.min_bounds, g["min_bounds"]) and np.array_equal(m.octree.max_bounds, g["max_bounds"])
+    assert np.array_equal(m.bearing_angles, g["bearing_angles"])
+    assert np.array_equal(m.T_sonar_to_base, g["T_sonar_to_base"])
+
+
+def test_edge_frames(s3d):
+    g = load_golden("edge_frames")
+    cfg = golden_config(g)
+    for name in ("nohit", "allhit", "hit_at_zero", "late_hit", "random", "equal_thr"):
+        m = s3d.SonarTo3DMapper(cfg)
+        st = m.process_sonar_image(g[f"{name}__image"], list(g["positions"][0]), list(g["quaternions"][0]))
+        assert [_stats3(st)] == g[f"{name}__stats"].tolist(), name
+        k, v = m.octree.voxels.to_arrays()
+        assert_same_map(k, v, g[f"{name}__keys"], g[f"{name}__logodds"], LOGODDS_ATOL, name)
+    m = s3d.SonarTo3DMapper(dict(cfg, intensity_threshold=99.5))       # float threshold, W = 1
+    st = m.process_sonar_image(g["onebeam__image"], list(g["positions"][0]), list(g["quaternions"][0]))
+    assert [_stats3(st)] == g["onebeam__stats"].tolist()
+    k, v = m.octree.voxels.to_arrays()
+    assert_same_map(k, v, g["onebeam__keys"], g["onebeam__logodds"], LOGODDS_ATOL, "onebeam")
+    # empty map exports
+    e = s3d.SonarTo3DMapper(cfg)
+    pc = e.get_point_cloud()
+    assert pc["points"].shape == (0, 3) and pc["probabilities"].shape == (0,) and pc["num_voxels"] == 0
+    pcf = e.get_point_cloud(True)
+    assert len(pcf["occupied"]) == len(pcf["free"]) == len(pcf["unknown"]) == 0
+    assert np.isinf(pcf["bounds"]["min"]).all() and np.isinf(pcf["bounds"]["max"]).all()
+
+
+def test_stage_vectors(s3d):
+    """Sample count and the key multiset of one frame against process_sonar_ray / world_to_key."""
+    g = load_golden("stage_vectors")
+    cfg = golden_config(g)
+    m = s3d.SonarTo3DMapper(cfg)
+    st = m.process_sonar_image(g["image"], list(g["position"]), list(g["quaternion"]))
+    assert m.last_num_samples == len(g["xyz"])
+    uk, inv = np.unique(g["keys"].astype(np.int64), axis=0, return_inverse=True)
+    occ_any = np.zeros(len(uk), dtype=bool)
+    np.logical_or.at(occ_any, inv.reshape(-1), g["occupied"].astype(bool))
+    assert st["num_occupied"] == int(occ_any.sum()) and st["num_free"] == int((~occ_any).sum())
+    k, _ = m.octree.voxels.to_arrays()
+    assert np.array_equal(sort_by_key(k)[0], sort_by_key(uk)[0])
+
+
+def test_store_vectors(s3d):
+    """SimpleOctree driven directly (scripts/3d_mapper.py:83-188)."""
+    g = load_golden("store_vectors")
+    oc = s3d.SimpleOctree(resolution=0.05, dynamic_expansion=True)
+    oc.adaptive_max_ratio = 0.3
+    n_single = 64
+    for p, u, a in zip(g["points"][:n_single], g["updates"][:n_single], g["adaptive"][:n_single]):
+        oc.update_voxel(p, float(u), adaptive=bool(a))
+    oc.update_voxels(g["points"][n_single:], g["updates"][n_single:], g["adaptive"][n_single:])
+    k, v = oc.voxels.to_arrays()
+    assert_same_map(k, v, g["keys"], g["logodds"], 1e-12, "store")
+    lo = np.array([oc.get_log_odds(*p) for p in g["query_points"]])
+    pr = np.array([oc.get_probability(*p) for p in g["query_points"]])
+    assert np.abs(lo - g["query_logodds"]).max() <= 1e-12 and np.abs(pr - g["query_prob"]).max() <= 1e-12
+    assert len(oc.voxels) == len(g["keys"])                       # queries never insert
+    assert np.array_equal(oc.min_bounds, g["min_bounds"]) and np.array_equal(oc.max_bounds, g["max_bounds"])
+    edge = json.loads(str(g["edge_thr_json"]))
+    assert len(oc.get_occupied_voxels(1.0)) == edge["p1"]
+    assert len(oc.get_occupied_voxels(0.0)) == edge["p0"]
+    assert len(oc.get_occupied_voxels(0.5)) == edge["p05"]
+    occ = oc.get_occupied_voxels(0.6)
+    pts = np.array([p for p, _ in occ]).reshape(-1, 3)
+    assert np.array_equal(sort_by_key(np.floor(pts / 0.05), pts)[1], sort_by_key(np.floor(g["occ_points"] / 0.05), g["occ_points"])[1])
+    cls = oc.get_all_voxels_classified(0.7)
+    assert [len(cls["free"]), len(cls["unknown"]), len(cls["occupied"])] == g["cls_counts"].tolist()
+    # voxels view
+    key0 = tuple(int(x) for x in g["keys"][0])
+    assert key0 in oc.voxels and abs(oc.voxels.get(key0) - g["logodds"][0]) <= 1e-12
+    assert (9999, 9999, 9999) not in oc.voxels and oc.voxels.get((9999, 9999, 9999), 0.0) == 0.0
+    assert dict(oc.voxels.items())[key0] == oc.voxels.get(key0)
+    oc.clear()
+    assert len(oc.voxels) == 0 and np.isinf(oc.min_bounds).all()
+
+
+@pytest.mark.parametrize("cfg_name,n_frames", [("cfg1", 4), ("cfg2", 6), ("cfg3", 2)])
+def test_vs_oracle_full_size(s3d, cfg_name, n_frames):
+    """BASELINE.json configs at full image size against the CPU oracle on the same seeded input."""
+    from oracle.oracle import OracleMapper
+    from sonar_3d_reconstruction_b200 import synthetic
+    images, pos, quat, cfg = synthetic.make_sequence(cfg_name, n_frames, seed=0)
+    gpu, cpu = s3d.SonarTo3DMapper(cfg), OracleMapper(cfg)
+    for f in range(n_frames):
+        a = gpu.process_sonar_image(images[f], list(pos[f]), list(quat[f]))
+        b = cpu.process_sonar_image(images[f], pos[f], quat[f])
+        assert _stats3(a) == _stats3(b), f"{cfg_name} frame {f}"
+        assert gpu.last_num_samples == b["num_samples"]
+    kg, vg = gpu.octree.voxels.to_arrays()
+    kc, vc = cpu.dump()
+    err = assert_same_map(kg, vg, kc, vc, LOGODDS_ATOL, cfg_name)
+    assert err <= 1e-9
+    assert gpu.get_point_cloud()["num_occupied"] == cpu.get_point_cloud()["num_occupied"]
+
+
+def test_batch_equals_sequential_and_growth(s3d):
+    """One s3d_ingest_batch call == the same frames one call each; a tiny initial table forces
+    several rehash-grows on the way and must not change anything."""
+    from sonar_3d_reconstruction_b200 import synthetic
+    spec = dict(H=160, W=200, config=dict(voxel_resolution=0.06, intensity_threshold=45, max_range=8.0), step_m=0.03)
+    images, pos, quat, cfg = synthetic.make_sequence(spec, 40, seed=3)
+    a = s3d.SonarTo3DMapper(cfg)
+    b = s3d.SonarTo3DMapper(dict(cfg, table_capacity=1024))
+    sa = [_stats3(a.process_sonar_image(images[f], list(pos[f]), list(quat[f]))) for f in range(len(images))]
+    sb = [_stats3(s) for s in b.process_sonar_images(images, pos, quat)]
+    assert sa == sb
+    ka, va = a.octree.voxels.to_arrays()
+    kb, vb = b.octree.voxels.to_arrays()
+    assert_same_map(ka, va, kb, vb, 0.0, "batch vs sequential")
+    assert b.frame_count == a.frame_count == 40
+
+
+def test_dump_load_roundtrip_and_xyzi32(s3d):
+    from sonar_3d_reconstruction_b200 import synthetic
+    images, pos, quat, cfg = synthetic.make_sequence(dict(H=120, W=96, config=dict(voxel_resolution=0.1)), 5, seed=9)
+    m = s3d.SonarTo3DMapper(cfg)
+    m.process_sonar_images(images, pos, quat)
+    k, v = m.octree.voxels.to_arrays()
+    other = s3d.SimpleOctree(resolution=0.1)
+    other._push_params()
+    other._native.load(k, v)
+    k2, v2 = other.voxels.to_arrays()
+    assert_same_map(k, v, k2, v2, 0.0, "dump -> load")
+    pc = m.get_point_cloud()
+    blob = m.get_point_cloud_xyzi32()
+    assert blob.dtype == np.float32 and blob.shape == (pc["num_occupied"], 4)
+    want = np.concatenate([pc["points"], pc["probabilities"][:, None]], axis=1).astype(np.float32)
+    assert np.array_equal(blob[np.lexsort(blob.T[::-1])], want[np.lexsort(want.T[::-1])])
+    m.reset_map()
+    assert m.frame_count == 0 and m.get_point_cloud()["num_voxels"] == 0
