@@ -1,0 +1,346 @@
+#!/usr/bin/env python3
+"""bench.py -- sonar frames/s and voxel log-odds updates/s of the B200 hot path.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line.
+A *step* is one pass of the hot path over one batch of `--frames-per-step` posed synthetic
+M750D-shaped frames (KIRO bags are not available offline).  Workload at N=1: BASELINE.json
+configs[1] ("cfg2": KIRO water-tank YAML values at 0.05 m voxels, tilt 60 deg).
+
+  value  frames/s with the frames already resident in HBM (CUDA events on the map's stream)
+  e2e    frames/s through the reference-facing Python API with pinned HOST buffers
+         (host->device copies and the stats read-back inside the timed region)
+  roofline / cpu_baseline: see DESIGN.md section "Measurement".
+
+`--impl reference` times the CPU oracle port of the reference path (the Python reference
+itself cannot travel to the GPU box) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from sonar_3d_reconstruction_b200 import synthetic  # noqa: E402
+
+METRIC = "sonar_frames_per_s"
+UNIT = "frames/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu_index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(name: str, n_frames: int, seed: int, distinct_images: int):
+    images, pos, quat, cfg = synthetic.make_sequence(name, n_frames, seed=seed, distinct_images=distinct_images)
+    return images, pos, quat, cfg
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the reference path, single-threaded like the reference."""
+    if rank != 0:
+        return
+    from oracle.oracle import OracleMapper
+    spec = synthetic.CONFIGS[args.workload]
+    per_step = min(args.frames_per_step, args.ref_frames_per_step)
+    total = (args.steps + args.warmup) * per_step
+    images, pos, quat, cfg = make_workload(args.workload, total, args.seed, min(total, 64))
+    m = OracleMapper(cfg)
+    f = 0
+    for _ in range(args.warmup):
+        for _ in range(per_step):
+            m.process_sonar_image(images[f], pos[f], quat[f]); f += 1
+    updates = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(per_step):
+            st = m.process_sonar_image(images[f], pos[f], quat[f]); f += 1
+            updates += st["num_occupied"] + st["num_free"]
+    dt = time.perf_counter() - t0
+    fps = args.steps * per_step / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "voxel_updates_per_s": updates / dt,
+        "config": {"workload": f"{args.workload}: {spec['H']}x{spec['W']} frames, "
+                               f"{cfg['voxel_resolution']} m voxels", "frames_per_step": per_step,
+                   "note": "bounded sample: each step is the first frames of the GPU arm's step"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{args.steps}x{per_step} frames of {args.workload} through oracle/sonar_oracle.c "
+                                   f"(C restatement of scripts/3d_mapper.py; the Python reference cannot travel; "
+                                   f"it measured 0.33 frames/s in the build container, SURVEY.md section 6)",
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from sonar_3d_reconstruction_b200 import SonarTo3DMapper
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: sonar_3d_reconstruction_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    spec = synthetic.CONFIGS[args.workload]
+    H, W = spec["H"], spec["W"]
+    fps_step = args.frames_per_step
+    n_total = (args.steps + args.warmup) * fps_step
+    # weak scaling: every rank maps its own survey leg (independent sub-map), no data-path collective
+    images, pos, quat, cfg = make_workload(args.workload, n_total, args.seed + rank, args.distinct_images)
+    cfg = dict(cfg, device=local_rank)
+
+    # ------------------------------------------------------------- value: inputs resident in HBM
+    mapper = SonarTo3DMapper(cfg)
+    native = mapper.octree._native
+    mapper._check_width(W)
+    mapper._sync_device_config(H, W)
+    T_all = mapper.compose_transforms(pos, quat).reshape(n_total, 16)
+    d_img = torch.from_numpy(images).to(f"cuda:{local_rank}")
+    d_T = torch.from_numpy(T_all).to(f"cuda:{local_rank}")
+    d_stats = torch.zeros((n_total, 4), dtype=torch.int64, device=f"cuda:{local_rank}")
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(native.stream, device=local_rank)
+    img_bytes = H * W
+
+    def step_dev(s):
+        f0 = s * fps_step
+        native.ingest_batch_dev(d_img.data_ptr() + f0 * img_bytes, fps_step, d_T.data_ptr() + f0 * 128,
+                                want_stats=False, stats_dev_ptr=d_stats.data_ptr() + f0 * 32)
+
+    for s in range(args.warmup):
+        step_dev(s)
+    native.sync()
+    # pre-size the table for the timed frames from the growth rate seen in warm-up, as a user
+    # who knows the survey length would; rehash-grows inside the timed region would be counted
+    st_w = d_stats[: args.warmup * fps_step].cpu().numpy()
+    rate = (int(st_w[-1, 2]) - int(st_w[len(st_w) // 2, 2])) / max(1, len(st_w) - len(st_w) // 2)
+    native.reserve(int(1.3 * rate * fps_step * args.steps) + 100000)
+    native.profile_enable(True)
+    native.profile_read()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for s in range(args.warmup, args.warmup + args.steps):
+        step_dev(s)
+    ev1.record(stream)
+    native.sync()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    prof = native.profile_read()
+    native.profile_enable(False)
+    st = d_stats[args.warmup * fps_step:].cpu().numpy()
+    n_frames = args.steps * fps_step
+    updates = int((st[:, 0] + st[:, 1]).sum())
+    samples = int(st[:, 3].sum())
+    n_voxels = int(st[-1, 2])
+    cap = native.capacity
+
+    # ------------------------------------------------------------- e2e: public API, host buffers
+    del mapper, native
+    if args.no_e2e:
+        e2e_s, e2e_steps = float("nan"), 0
+    mapper2 = SonarTo3DMapper(cfg) if not args.no_e2e else None
+    if not args.no_e2e:
+        pin = torch.from_numpy(images).pin_memory()
+        images_pinned = pin.numpy()
+        e2e_steps = args.steps
+        for s in range(args.warmup):
+            f0 = s * fps_step
+            mapper2.process_sonar_images(images_pinned[f0:f0 + fps_step], pos[f0:f0 + fps_step], quat[f0:f0 + fps_step])
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.warmup, args.warmup + e2e_steps):
+            f0 = s * fps_step
+            out = mapper2.process_sonar_images(images_pinned[f0:f0 + fps_step], pos[f0:f0 + fps_step],
+                                               quat[f0:f0 + fps_step])
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e_voxels = out[-1]["num_voxels"]
+        assert e2e_voxels == n_voxels, (e2e_voxels, n_voxels)      # both arms built the same map
+
+    # ------------------------------------------------------------- aggregate over ranks
+    t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+    tot = torch.tensor([n_frames, updates, samples], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_total, e2e_s = float(t[0]), float(t[1])
+    frames_all, updates_all, samples_all = (float(x) for x in tot)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        # algorithmic bytes: image read once + per voxel update one 16 B slot read + 8 B write
+        alg_bytes = n_frames * H * W + 24 * updates
+        kms = prof["ms"]
+        group_ms = sum(kms.values())
+        dom = max(kms, key=kms.get)
+        per_kernel = {
+            "k_first_hit": {"ms": kms["k_first_hit"], "launches": prof["launches"]["k_first_hit"],
+                            "alg_bytes": n_frames * H * W},
+            "k_expand": {"ms": kms["k_expand"], "launches": prof["launches"]["k_expand"], "alg_bytes": 0,
+                         "samples_per_s": samples / (kms["k_expand"] * 1e-3) if kms["k_expand"] else None},
+            "k_apply": {"ms": kms["k_apply"], "launches": prof["launches"]["k_apply"], "alg_bytes": 24 * updates},
+        }
+        for k, v in per_kernel.items():
+            v["gbs"] = v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else None
+        achieved = alg_bytes / (group_ms * 1e-3) / 1e9 if group_ms else 0.0
+        line = {
+            "metric": METRIC, "value": frames_all / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "voxel_updates_per_s": updates_all / (ms_total * 1e-3),
+            "samples_per_s": samples_all / (ms_total * 1e-3),
+            "config": {"workload": f"{args.workload}: KIRO water-tank-shaped synthetic sequence, {H}x{W} frames "
+                                   f"(range x bearing), tilt 60 deg, {cfg['voxel_resolution']} m voxels"
+                       if args.workload == "cfg2" else f"{args.workload}: {H}x{W} frames, {cfg['voxel_resolution']} m voxels",
+                       "frames_per_step": fps_step, "frames_timed": n_frames,
+                       "updates_per_frame": updates / n_frames, "samples_per_frame": samples / n_frames,
+                       "map_voxels_end": n_voxels, "table_slots": cap,
+                       "chunk_retries": prof["retries"], "table_grows_timed": prof["grows"],
+                       "l2": "inputs streamed once: every step reads fresh frames (timed input "
+                             f"{n_frames * H * W / 2**20:.0f} MiB > L2), table {cap * 16 / 2**20:.0f} MiB",
+                       "parallelism": "1 map per GPU" if world > 1 else "single GPU"},
+            "e2e": {"value": frames_all / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": fps_step * (H * W + 128), "d2h_bytes_per_step": fps_step * 32,
+                    "api": "SonarTo3DMapper.process_sonar_images (pinned host images, poses on host)"},
+            "gpu_launches": prof["total_launches"],
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "kernel": "per-frame kernel group k_first_hit+k_expand+k_apply "
+                                   f"(dominant: {dom}); algorithmic bytes = H*W + 24*U per frame",
+                         "peak_source": peak_src, "kernels": per_kernel},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, images, pos, quat, cfg)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, images, pos, quat, cfg):
+    from oracle.oracle import OracleMapper
+    cfg = {k: v for k, v in cfg.items() if k != "device"}
+    m = OracleMapper(cfg)
+    n = min(len(images), args.cpu_frames)
+    upd = 0
+    t0 = time.perf_counter()
+    for f in range(n):
+        st = m.process_sonar_image(images[f], pos[f], quat[f])
+        upd += st["num_occupied"] + st["num_free"]
+        if time.perf_counter() - t0 > 25.0:
+            n = f + 1
+            break
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port", "voxel_updates_per_s": upd / dt,
+            "host_cpus": os.cpu_count(),
+            "sample": f"first {n} frames of the same sequence through oracle/sonar_oracle.c (single-threaded C "
+                      f"restatement of scripts/3d_mapper.py; the pure-Python reference itself ran at 0.33 frames/s "
+                      f"in the build container, SURVEY.md section 6)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(synthetic.CONFIGS))
+    ap.add_argument("--frames-per-step", type=int, default=250)
+    ap.add_argument("--ref-frames-per-step", type=int, default=40)
+    ap.add_argument("--distinct-images", type=int, default=250)
+    ap.add_argument("--cpu-frames", type=int, default=400)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (profiling runs only)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -122,7 +122,8 @@ int s3d_ingest_batch(s3d_map *map, const uint8_t *images, int64_t n, const doubl
 int s3d_ingest_batch_dev(s3d_map *map, const uint8_t *images_dev, int64_t n, const double *T_dev,
                          s3d_frame_stats *out, s3d_frame_stats *stats_dev);
 
-/* Make sure the table can take `n_frames` more frames without growing inside a timed region. */
+/* Pre-size the table for `n_voxels` more voxels (load <= 1/2) so that it does not have to
+ * rehash-grow later, e.g. inside a timed region. */
 int s3d_reserve(s3d_map *map, uint64_t n_voxels);
 int s3d_sync(s3d_map *map);
 /* The map's cudaStream_t (for CUDA-event timing on the launching stream). */
@@ -168,6 +169,28 @@ int s3d_export_read(s3d_map *map, double *xyz, double *prob, int8_t *cls, int32_
 /* Same result as the PointCloud2 payload of the reference node: little-endian float32
  * x, y, z, intensity=probability, 16-byte stride (scripts/3d_mapper_node.py:419-443). */
 int s3d_export_read_xyzi32(s3d_map *map, float *xyzi, uint64_t n);
+
+/* ---- measurement (bench.py) ----------------------------------------------------------------- */
+
+#define S3D_K_FIRST_HIT 0
+#define S3D_K_EXPAND 1
+#define S3D_K_APPLY 2
+#define S3D_K_COUNT 3
+
+/* Per-kernel device time measured with CUDA events on the map's stream, and launch counts.
+ * Enabling costs two event records per kernel group; the numbers accumulate until read. */
+typedef struct s3d_profile {
+    double ms[S3D_K_COUNT];          /* summed device time of each kernel class */
+    uint64_t launches[S3D_K_COUNT];  /* launches of each kernel class */
+    uint64_t frames;                 /* frames ingested while profiling was on */
+    uint64_t total_launches;         /* pipeline kernels launched since the last read */
+    uint64_t retries;                /* chunks re-run after the device gate asked for more room */
+    uint64_t grows;                  /* voxel-table rehash-grows */
+} s3d_profile;
+
+int s3d_profile_enable(s3d_map *map, int on);
+/* Synchronises the stream, fills `out`, resets the accumulators. */
+int s3d_profile_read(s3d_map *map, s3d_profile *out);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,7 @@ SYMBOLS = (
     "s3d_ingest", "s3d_ingest_batch", "s3d_ingest_batch_dev", "s3d_reserve", "s3d_sync", "s3d_stream",
     "s3d_apply_updates", "s3d_query", "s3d_count", "s3d_dump", "s3d_load", "s3d_clear", "s3d_bounds",
     "s3d_capacity", "s3d_export_begin", "s3d_export_read", "s3d_export_read_xyzi32",
+    "s3d_profile_enable", "s3d_profile_read",
 )
 
 
@@ -45,6 +46,13 @@ class FrameStats(C.Structure):
     _fields_ = [("num_occupied", C.c_int64), ("num_free", C.c_int64), ("num_voxels", C.c_int64),
                 ("num_samples", C.c_int64)]
 
+
+class Profile(C.Structure):
+    _fields_ = [("ms", C.c_double * 3), ("launches", C.c_uint64 * 3), ("frames", C.c_uint64),
+                ("total_launches", C.c_uint64), ("retries", C.c_uint64), ("grows", C.c_uint64)]
+
+
+KERNEL_NAMES = ("k_first_hit", "k_expand", "k_apply")
 
 STATS_DTYPE = np.dtype([("num_occupied", "<i8"), ("num_free", "<i8"), ("num_voxels", "<i8"), ("num_samples", "<i8")])
 
@@ -89,6 +97,8 @@ def load_library():
     L.s3d_export_begin.argtypes = [vp, C.c_double, C.c_double, C.c_uint32, u64p, u64p]
     L.s3d_export_read.argtypes = [vp, dp, dp, i8p, i32p, C.c_uint64]
     L.s3d_export_read_xyzi32.argtypes = [vp, C.POINTER(C.c_float), C.c_uint64]
+    L.s3d_profile_enable.argtypes = [vp, C.c_int]
+    L.s3d_profile_read.argtypes = [vp, C.POINTER(Profile)]
     for name in SYMBOLS:
         getattr(L, name)          # AttributeError here = header / library mismatch
     _lib = L
@@ -177,6 +187,18 @@ class NativeMap:
     @property
     def capacity(self) -> int:
         return int(self._lib.s3d_capacity(self._h))
+
+    # -- measurement --------------------------------------------------------------------
+    def profile_enable(self, on: bool = True):
+        _check(self._lib.s3d_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self) -> dict:
+        p = Profile()
+        _check(self._lib.s3d_profile_read(self._h, C.byref(p)))
+        return {"ms": {k: p.ms[i] for i, k in enumerate(KERNEL_NAMES)},
+                "launches": {k: int(p.launches[i]) for i, k in enumerate(KERNEL_NAMES)},
+                "frames": int(p.frames), "total_launches": int(p.total_launches),
+                "retries": int(p.retries), "grows": int(p.grows)}
 
     # -- store --------------------------------------------------------------------------
     def apply_updates(self, ijk: np.ndarray, delta: np.ndarray, adaptive: np.ndarray):

@@ -7,9 +7,9 @@
 //   :117-188 queries / export    -> k_query, k_export (K5, K6)
 //
 // Data layout in HBM (DESIGN.md has the full account):
-//   voxel table   Slot[cap]      16 B {packed key, fp64 log-odds}, open addressing, linear probing
-//   frame scratch SEntry[G][C]   16 B {packed key, n_occ<<32 | n_free}, one sub-table per in-flight frame
-//   touch list    u32[G][C]      scratch slots first touched this frame (so apply/reset are O(unique))
+//   voxel table    Slot[cap]    16 B {packed key, fp64 log-odds}, open addressing, linear probing
+//   chunk dedupe   u64 keys[C] + u64 counters[C][16]: one entry per voxel touched by a chunk of
+//                  up to 16 consecutive frames, one (n_occ<<32 | n_free) counter lane per frame
 // No tensor cores: the path has no dense contraction; it is integer/fp64 scatter work.
 #include "../../include/sonar3d.h"
 
@@ -20,6 +20,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <limits>
 #include <string>
 #include <unordered_map>
@@ -33,10 +34,11 @@ typedef unsigned int u32;
 constexpr u64 EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
 constexpr int KEY_BITS = 21;
 constexpr int KEY_BIAS = 1 << 20;
-constexpr u32 ERR_KEYRANGE = 1u, ERR_TABLEFULL = 2u, ERR_SCRATCH = 4u;
+constexpr int GF = 16;                                      // frames per chunk = counter lanes per dedupe entry
+constexpr u32 ERR_KEYRANGE = 1u, ERR_TABLEFULL = 2u;        // fatal
+constexpr u32 ABORT_SCRATCH = 1u, ABORT_TABLE = 2u;         // retryable: the host enlarges and re-runs the chunk
 
 struct __align__(16) Slot { u64 key; double val; };
-struct __align__(16) SEntry { u64 key; u64 cnt; };
 
 struct DevParams {
     double res, inv_res, lo_occ, lo_free, lo_min, lo_max, a_thr, a_ratio, zmin;
@@ -54,12 +56,20 @@ struct DevTables {
 
 struct MapCtr {       // device-resident map counters
     u64 count;        // live voxels
+    u64 abort_seq;    // first chunk (sequence number) that asked for a retry; ~0 = none
     int kmin[3], kmax[3];
-    u32 err;
-    u32 pad;
+    u32 err;          // fatal flags
+    u32 abort;        // retry flags; while set, every pipeline kernel returns without side effects
+    u32 last_new;     // voxels inserted by the last applied chunk
+    u32 last_unique;  // voxels touched by the last applied chunk
 };
 
-struct FrameCtr { u32 list_count; u32 ticket; };   // per in-flight frame slot
+struct ChunkCtr {     // working counters of the chunk in flight (chunks are serialised on the stream)
+    u64 count0;       // live voxels before the chunk
+    u32 n_unique;     // dedupe entries created by k_expand
+    u32 ticket;       // last-block-out election
+    u32 neu[GF];      // voxels first inserted at frame f of the chunk
+};
 
 struct DevStats { u64 n_occ, n_free, n_voxels, n_samples; };  // == s3d_frame_stats
 static_assert(sizeof(DevStats) == sizeof(s3d_frame_stats), "stats layout");
@@ -153,44 +163,50 @@ k_first_hit(const uint8_t *__restrict__ imgs, size_t img_stride, DevTables tab, 
 }
 
 // ------------------------------------------------------------------------------------ K2+K3
-// One block per (processed beam, in-flight frame).  The block lists the beam's range samples
+// One block per (processed beam, frame of the chunk).  The block lists the beam's range samples
 // (free: every free_step-th bin before the first hit; occupied: above-threshold bins in the
 // occ_window bins from the first hit), prefix-sums their fan sizes (2*nv+1), and its threads
 // then walk the flattened (range sample, vertical step) space: sonar-frame point from the
 // host trig tables, Sonar->Map transform, z filter, voxel key, and a count bump in the
-// frame's dedupe scratch table.
+// chunk's dedupe table: one entry per voxel touched by the chunk, one counter lane per frame.
 constexpr int EX_THREADS = 128;
+constexpr u32 SCRATCH_PROBE_LIMIT = 512;
 
 struct ExpandArgs {
     const uint8_t *imgs; size_t img_stride;
-    const double *T;             // [G][16]
+    const double *T;             // [g][16]
     DevTables tab; DevParams p;
-    const int *first_hit;        // [G][n_beams]
-    SEntry *scratch; u32 scratch_mask; size_t scratch_stride;   // per frame slot
-    u32 *lists; u32 list_cap;
-    FrameCtr *fctr;              // [G]
-    DevStats *stats;             // [G]
+    const int *first_hit;        // [g][n_beams]
+    u64 *skeys; u64 *scnt; u32 smask;   // chunk dedupe table: keys[C], counters[C][GF]
+    ChunkCtr *cc;
+    DevStats *stats;             // [g]
     MapCtr *mc;
+    u64 seq;                     // chunk sequence number (for abort bookkeeping)
+    u64 table_limit;             // gate: count + unique(chunk) must stay <= this
 };
 
-__device__ __forceinline__ void scratch_add(SEntry *S, u32 mask, u64 key, u64 inc, u32 *list, u32 list_cap,
-                                            FrameCtr *fc, MapCtr *mc)
+__device__ __forceinline__ void raise_abort(MapCtr *mc, u32 why, u64 seq)
 {
-    u32 slot = (u32)mix64(key) & mask;
-    for (u32 probe = 0; probe <= mask; ++probe) {
-        u64 cur = __ldcg(&S[slot].key);
+    atomicOr(&mc->abort, why);
+    atomicMin(&mc->abort_seq, seq);
+}
+
+// returns 1 if this call created the entry
+__device__ __forceinline__ int scratch_add(const ExpandArgs &a, u64 key, int lane, u64 inc)
+{
+    u32 slot = (u32)mix64(key) & a.smask;
+    for (u32 probe = 0; probe < SCRATCH_PROBE_LIMIT; ++probe) {
+        u64 cur = __ldcg(&a.skeys[slot]);
+        int created = 0;
         if (cur == EMPTY_KEY) {
-            cur = atomicCAS(&S[slot].key, EMPTY_KEY, key);
-            if (cur == EMPTY_KEY) {
-                const u32 idx = atomicAdd(&fc->list_count, 1u);
-                if (idx < list_cap) list[idx] = slot; else atomicOr(&mc->err, ERR_SCRATCH);
-                cur = key;
-            }
+            cur = atomicCAS(&a.skeys[slot], EMPTY_KEY, key);
+            if (cur == EMPTY_KEY) { cur = key; created = 1; }
         }
-        if (cur == key) { atomicAdd(&S[slot].cnt, inc); return; }
-        slot = (slot + 1) & mask;
+        if (cur == key) { atomicAdd(&a.scnt[(size_t)slot * GF + lane], inc); return created; }
+        slot = (slot + 1) & a.smask;
     }
-    atomicOr(&mc->err, ERR_SCRATCH);
+    raise_abort(a.mc, ABORT_SCRATCH, a.seq);     // table too loaded: the host enlarges it and retries
+    return 0;
 }
 
 __global__ void __launch_bounds__(EX_THREADS)
@@ -205,7 +221,9 @@ k_expand(ExpandArgs a)
     int *s_nv = s_rn + max_c;           // [max_c]
     __shared__ double s_T[12];
     __shared__ int s_total;
+    __shared__ bool s_last;
 
+    if (__ldcg(&a.mc->abort)) return;   // an earlier chunk must be retried first: stay side-effect free
     const int beam = blockIdx.x, g = blockIdx.y;
     const uint8_t *img = a.imgs + (size_t)g * a.img_stride;
     const int col = tab.beam_col[beam];
@@ -246,10 +264,7 @@ k_expand(ExpandArgs a)
     __syncthreads();
     const int total = s_total;
     const double cb = tab.cos_b[beam], sb = tab.sin_b[beam];
-    SEntry *S = a.scratch + (size_t)g * a.scratch_stride;
-    u32 *list = a.lists + (size_t)g * a.list_cap;
-    FrameCtr *fc = a.fctr + g;
-    int emitted = 0;
+    int emitted = 0, created = 0;
     for (int w = threadIdx.x; w < total; w += EX_THREADS) {
         int lo = 0, hi = nc;                      // largest c with s_off[c] <= w
         while (hi - lo > 1) {
@@ -282,11 +297,34 @@ k_expand(ExpandArgs a)
             atomicOr(&a.mc->err, ERR_KEYRANGE);
             continue;
         }
-        scratch_add(S, a.scratch_mask, pack_key(ki, kj, kk), occ ? (1ull << 32) : 1ull, list, a.list_cap, fc, a.mc);
+        created += scratch_add(a, pack_key(ki, kj, kk), g, occ ? (1ull << 32) : 1ull);
     }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
-    if ((threadIdx.x & 31) == 0 && emitted) atomicAdd(&a.stats[g].n_samples, (u64)emitted);
+    for (int d = 16; d > 0; d >>= 1) {
+        emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
+        created += __shfl_xor_sync(0xffffffffu, created, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (emitted) atomicAdd(&a.stats[g].n_samples, (u64)emitted);
+        if (created) atomicAdd(&a.cc->n_unique, (u32)created);
+    }
+    // last block out: the gate.  The chunk may be applied only if the table keeps its load bound
+    // even when every voxel of the chunk is new; otherwise the host grows the table and retries.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const u32 t = atomicAdd(&a.cc->ticket, 1u);
+        s_last = (t == gridDim.x * gridDim.y - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        const u32 nu = atomicAdd(&a.cc->n_unique, 0u);
+        const u64 cnt = atomicAdd(&a.mc->count, 0ull);
+        a.cc->count0 = cnt;
+        a.cc->ticket = 0;
+        if (cnt + nu > a.table_limit) raise_abort(a.mc, ABORT_TABLE, a.seq);
+    }
 }
 
 // ------------------------------------------------------------------------------------ K4
@@ -321,21 +359,28 @@ __device__ __forceinline__ u64 table_find_or_insert(Slot *table, u64 mask, u64 k
     return ~0ull;
 }
 
-struct LocalAcc { int n_occ, n_free, n_new; int kmin[3], kmax[3]; };
+struct LocalAcc { int n_new; int kmin[3], kmax[3]; };
 
 __device__ __forceinline__ void acc_init(LocalAcc &a)
 {
-    a.n_occ = a.n_free = a.n_new = 0;
+    a.n_new = 0;
     for (int q = 0; q < 3; ++q) { a.kmin[q] = INT_MAX; a.kmax[q] = INT_MIN; }
 }
 
-// warp-reduce the accumulators; lane 0 publishes (bounds only when they extend the box)
-__device__ __forceinline__ void acc_publish(LocalAcc &a, DevStats *st, MapCtr *mc)
+__device__ __forceinline__ void acc_key(LocalAcc &a, u64 key)
+{
+    int ki, kj, kk; unpack_key(key, ki, kj, kk);
+    a.kmin[0] = min(a.kmin[0], ki); a.kmax[0] = max(a.kmax[0], ki);
+    a.kmin[1] = min(a.kmin[1], kj); a.kmax[1] = max(a.kmax[1], kj);
+    a.kmin[2] = min(a.kmin[2], kk); a.kmax[2] = max(a.kmax[2], kk);
+}
+
+// warp-reduce; lane 0 publishes (bounds only when they extend the box).  add_count: also bump
+// the live-voxel counter (the chunk path does that once, from its per-frame totals).
+__device__ __forceinline__ void acc_publish(LocalAcc &a, MapCtr *mc, bool add_count)
 {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
-        a.n_occ += __shfl_xor_sync(0xffffffffu, a.n_occ, d);
-        a.n_free += __shfl_xor_sync(0xffffffffu, a.n_free, d);
         a.n_new += __shfl_xor_sync(0xffffffffu, a.n_new, d);
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
@@ -344,11 +389,7 @@ __device__ __forceinline__ void acc_publish(LocalAcc &a, DevStats *st, MapCtr *m
         }
     }
     if ((threadIdx.x & 31) == 0) {
-        if (st) {
-            if (a.n_occ) atomicAdd(&st->n_occ, (u64)a.n_occ);
-            if (a.n_free) atomicAdd(&st->n_free, (u64)a.n_free);
-        }
-        if (a.n_new) atomicAdd(&mc->count, (u64)a.n_new);
+        if (add_count && a.n_new) atomicAdd(&mc->count, (u64)a.n_new);
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
             if (a.kmin[q] < __ldcg(&mc->kmin[q])) atomicMin(&mc->kmin[q], a.kmin[q]);
@@ -358,54 +399,135 @@ __device__ __forceinline__ void acc_publish(LocalAcc &a, DevStats *st, MapCtr *m
 }
 
 constexpr int AP_THREADS = 256;
+constexpr int AP_TILE = 2048;      // dedupe slots scanned per block iteration
+constexpr int SUMT = 64;           // entries of the sequential-sum tables
 
-// One thread per voxel touched by the frame (3d_mapper.py:557-567): consume and reset the
-// scratch entry, form the per-voxel mean update, then read-modify-write the table slot.
-__global__ void __launch_bounds__(AP_THREADS)
-k_apply(SEntry *__restrict__ S, const u32 *__restrict__ list, FrameCtr *fc, DevStats *st,
-        Slot *table, u64 tmask, DevParams p, MapCtr *mc)
+// sum of n_free copies of lo_free followed by n_occ copies of lo_occ, added one by one as the
+// reference's `sum += log_odds` does (3d_mapper.py:546).  tab[0][n] / tab[1][n] hold the
+// running sums of n copies of lo_free / lo_occ; only counts >= SUMT or mixed voxels loop.
+__device__ __forceinline__ double seq_sum(u32 n_free, u32 n_occ, const double (*tab)[SUMT], const DevParams &p)
 {
-    const u32 n = fc->list_count;
-    LocalAcc acc; acc_init(acc);
-    for (u32 i = blockIdx.x * AP_THREADS + threadIdx.x; i < n; i += gridDim.x * AP_THREADS) {
-        const u32 s = list[i];
-        const ulonglong2 e = *reinterpret_cast<const ulonglong2 *>(&S[s]);
-        *reinterpret_cast<ulonglong2 *>(&S[s]) = make_ulonglong2(EMPTY_KEY, 0ull);   // ready for the next frame
-        const u64 key = e.x;
-        const u32 n_occ = (u32)(e.y >> 32), n_free = (u32)(e.y & 0xffffffffu);
-        // mean of the per-sample deltas, summed one by one as the reference does (:546, :559)
-        double sum = 0.0;
-        for (u32 q = 0; q < n_free; ++q) sum += p.lo_free;
-        for (u32 q = 0; q < n_occ; ++q) sum += p.lo_occ;
-        const double avg = sum / (double)(n_occ + n_free);
-        const bool occ_typed = n_occ > 0;                                            // :544-545
-        bool fresh; double L;
-        const u64 slot = table_find_or_insert(table, tmask, key, fresh, L);
-        if (slot == ~0ull) { atomicOr(&mc->err, ERR_TABLEFULL); continue; }
-        L = apply_one(L, avg, occ_typed, p);
-        table[slot].val = L;
-        if (occ_typed) ++acc.n_occ; else ++acc.n_free;
-        if (fresh) ++acc.n_new;
-        int ki, kj, kk; unpack_key(key, ki, kj, kk);
-        acc.kmin[0] = min(acc.kmin[0], ki); acc.kmax[0] = max(acc.kmax[0], ki);
-        acc.kmin[1] = min(acc.kmin[1], kj); acc.kmax[1] = max(acc.kmax[1], kj);
-        acc.kmin[2] = min(acc.kmin[2], kk); acc.kmax[2] = max(acc.kmax[2], kk);
+    double sum;
+    if (n_free < SUMT) sum = tab[0][n_free];
+    else { sum = tab[0][SUMT - 1]; for (u32 q = SUMT - 1; q < n_free; ++q) sum += p.lo_free; }
+    if (n_occ) {
+        if (n_free == 0 && n_occ < SUMT) sum = tab[1][n_occ];
+        else for (u32 q = 0; q < n_occ; ++q) sum += p.lo_occ;
     }
-    acc_publish(acc, st, mc);
-    // last block out: snapshot len(voxels) (:592) and re-arm the frame slot
+    return sum;
+}
+
+// One thread per voxel touched by the chunk.  A block scans a tile of the dedupe table,
+// compacts the live slots in shared memory, and then each thread consumes (and resets) one
+// entry, reads the voxel's table slot once, walks the chunk's frames in order -- for each frame
+// that touched the voxel: per-voxel mean of the sample deltas (3d_mapper.py:557-559), then
+// update_voxel (:562-567) -- and writes the slot back once.  Frames stay strictly ordered per
+// voxel, which is all the reference's sequential semantics require (voxels are independent).
+__global__ void __launch_bounds__(AP_THREADS)
+k_apply_chunk(u64 *__restrict__ skeys, u64 *__restrict__ scnt, u64 n_slots, int g, ChunkCtr *cc, DevStats *st,
+              Slot *table, u64 tmask, DevParams p, const double *__restrict__ sum_tab, MapCtr *mc)
+{
+    __shared__ u32 s_occ[GF], s_free[GF], s_new[GF];
+    __shared__ u32 s_list[AP_TILE];
+    __shared__ u32 s_n;
+    __shared__ double s_sum[2][SUMT];
     __shared__ bool s_last;
+    if (__ldcg(&mc->abort)) return;
+    if (threadIdx.x < GF) { s_occ[threadIdx.x] = 0; s_free[threadIdx.x] = 0; s_new[threadIdx.x] = 0; }
+    if (threadIdx.x < 2 * SUMT) (&s_sum[0][0])[threadIdx.x] = sum_tab[threadIdx.x];
+    const u32 lane = threadIdx.x & 31;
+    u32 w_occ = 0, w_free = 0, w_new = 0;      // lane f of each warp accumulates frame f
+    LocalAcc acc; acc_init(acc);
+    for (u64 tile = (u64)blockIdx.x * AP_TILE; tile < n_slots; tile += (u64)gridDim.x * AP_TILE) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < AP_TILE / AP_THREADS; ++j) {
+            const u64 s = tile + (u64)j * AP_THREADS + threadIdx.x;
+            if (s < n_slots && __ldcs(&skeys[s]) != EMPTY_KEY) s_list[atomicAdd(&s_n, 1u)] = (u32)(s - tile);
+        }
+        __syncthreads();
+        const u32 n_live = s_n;
+        for (u32 base = 0; base < n_live; base += AP_THREADS) {     // block-uniform trip count
+            const u32 i = base + threadIdx.x;
+            const bool live = i < n_live;
+            u64 key = 0, slot = ~0ull; bool fresh = false; double L = 0.0;
+            ulonglong2 c2[GF / 2];
+#pragma unroll
+            for (int q = 0; q < GF / 2; ++q) c2[q] = make_ulonglong2(0ull, 0ull);
+            if (live) {
+                const u64 s = tile + s_list[i];
+                key = skeys[s];
+                ulonglong2 *cp = reinterpret_cast<ulonglong2 *>(scnt + s * GF);
+#pragma unroll
+                for (int q = 0; q < GF / 2; ++q) c2[q] = __ldcs(cp + q);
+                skeys[s] = EMPTY_KEY;                               // ready for the next chunk
+#pragma unroll
+                for (int q = 0; q < GF / 2; ++q) cp[q] = make_ulonglong2(0ull, 0ull);
+                slot = table_find_or_insert(table, tmask, key, fresh, L);
+                if (slot == ~0ull) atomicOr(&mc->err, ERR_TABLEFULL);
+            }
+            bool pending_new = fresh;
+#pragma unroll
+            for (int f = 0; f < GF; ++f) {
+                if (f < g) {                                        // uniform
+                    const u64 c = (f & 1) ? c2[f >> 1].y : c2[f >> 1].x;
+                    const bool hit = c != 0ull;
+                    const u32 n_occ = (u32)(c >> 32), n_free = (u32)(c & 0xffffffffu);
+                    const bool occ_typed = n_occ > 0;               // occupied has priority (:544-545)
+                    if (hit) {
+                        const double avg = seq_sum(n_free, n_occ, s_sum, p) / (double)(n_occ + n_free);   // :559
+                        L = apply_one(L, avg, occ_typed, p);
+                    }
+                    const u32 b_occ = __ballot_sync(0xffffffffu, hit && occ_typed);
+                    const u32 b_free = __ballot_sync(0xffffffffu, hit && !occ_typed);
+                    const u32 b_new = __ballot_sync(0xffffffffu, hit && pending_new);
+                    if (hit) pending_new = false;
+                    if (lane == (u32)f) { w_occ += __popc(b_occ); w_free += __popc(b_free); w_new += __popc(b_new); }
+                }
+            }
+            if (live && slot != ~0ull) {
+                table[slot].val = L;
+                if (fresh) ++acc.n_new;
+                acc_key(acc, key);
+            }
+        }
+    }
+    acc_publish(acc, mc, false);
+    __syncthreads();
+    if (lane < GF) {
+        if (w_occ) atomicAdd(&s_occ[lane], w_occ);
+        if (w_free) atomicAdd(&s_free[lane], w_free);
+        if (w_new) atomicAdd(&s_new[lane], w_new);
+    }
+    __syncthreads();
+    if (threadIdx.x < g) {
+        const int f = threadIdx.x;
+        if (s_occ[f]) atomicAdd(&st[f].n_occ, (u64)s_occ[f]);
+        if (s_free[f]) atomicAdd(&st[f].n_free, (u64)s_free[f]);
+        if (s_new[f]) atomicAdd(&cc->neu[f], s_new[f]);
+    }
+    // last block out: len(voxels) after each frame (:592), publish the new count, re-arm the chunk
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        const u32 t = atomicAdd(&fc->ticket, 1u);
+        const u32 t = atomicAdd(&cc->ticket, 1u);
         s_last = (t == gridDim.x - 1);
     }
     __syncthreads();
     if (s_last && threadIdx.x == 0) {
         __threadfence();
-        st->n_voxels = atomicAdd(&mc->count, 0ull);
-        fc->list_count = 0;
-        fc->ticket = 0;
+        u64 run = cc->count0;
+        for (int f = 0; f < g; ++f) {
+            run += atomicAdd(&cc->neu[f], 0u);
+            st[f].n_voxels = run;
+            cc->neu[f] = 0;
+        }
+        mc->last_new = (u32)(run - cc->count0);
+        mc->last_unique = atomicAdd(&cc->n_unique, 0u);
+        atomicExch(&mc->count, run);
+        cc->n_unique = 0; cc->ticket = 0;
     }
 }
 
@@ -416,10 +538,16 @@ __global__ void k_fill_slots(Slot *t, u64 n)
         *reinterpret_cast<ulonglong2 *>(&t[i]) = make_ulonglong2(EMPTY_KEY, 0ull);
 }
 
-__global__ void k_fill_scratch(SEntry *t, u64 n)
+__global__ void k_fill_u64(u64 *t, u64 n, u64 v)
 {
-    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-        *reinterpret_cast<ulonglong2 *>(&t[i]) = make_ulonglong2(EMPTY_KEY, 0ull);
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) t[i] = v;
+}
+
+__global__ void k_clear_abort(MapCtr *mc, ChunkCtr *cc)
+{
+    mc->abort = 0; mc->abort_seq = ~0ull;
+    cc->count0 = 0; cc->n_unique = 0; cc->ticket = 0;
+    for (int f = 0; f < GF; ++f) cc->neu[f] = 0;
 }
 
 __global__ void k_rehash(const Slot *__restrict__ old_t, u64 old_n, Slot *new_t, u64 new_mask, MapCtr *mc)
@@ -449,11 +577,10 @@ __global__ void k_apply_direct(const u64 *__restrict__ keys, const double *__res
         else {
             table[slot].val = apply_one(L, delta[i], adaptive[i] != 0, p);
             if (fresh) ++acc.n_new;
-            int ki, kj, kk; unpack_key(key, ki, kj, kk);
-            acc.kmin[0] = acc.kmax[0] = ki; acc.kmin[1] = acc.kmax[1] = kj; acc.kmin[2] = acc.kmax[2] = kk;
+            acc_key(acc, key);
         }
     }
-    acc_publish(acc, nullptr, mc);
+    acc_publish(acc, mc, true);
 }
 
 __global__ void k_load(const u64 *__restrict__ keys, const double *__restrict__ vals, u64 n, Slot *table,
@@ -469,11 +596,10 @@ __global__ void k_load(const u64 *__restrict__ keys, const double *__restrict__ 
         else {
             table[slot].val = vals[i];
             if (fresh) ++acc.n_new;
-            int ki, kj, kk; unpack_key(key, ki, kj, kk);
-            acc.kmin[0] = acc.kmax[0] = ki; acc.kmin[1] = acc.kmax[1] = kj; acc.kmin[2] = acc.kmax[2] = kk;
+            acc_key(acc, key);
         }
     }
-    acc_publish(acc, nullptr, mc);
+    acc_publish(acc, mc, true);
 }
 
 __global__ void k_query(const u64 *__restrict__ keys, u64 n, const Slot *__restrict__ table, u64 tmask,
@@ -553,7 +679,7 @@ __global__ void k_pack_xyzi32(const double *__restrict__ xyz, const double *__re
 
 __global__ void k_reset_ctr(MapCtr *mc)
 {
-    mc->count = 0; mc->err = 0;
+    mc->count = 0; mc->err = 0; mc->abort = 0; mc->abort_seq = ~0ull; mc->last_new = 0; mc->last_unique = 0;
     for (int q = 0; q < 3; ++q) { mc->kmin[q] = INT_MAX; mc->kmax[q] = INT_MIN; }
 }
 
@@ -595,6 +721,14 @@ template <typename T> struct DevBuf {
 
 } // namespace
 
+struct Job {                         // one s3d_ingest_batch* call: frames [0, n) of caller-owned device buffers
+    u64 id = 0;
+    const uint8_t *imgs = nullptr; const double *T = nullptr; DevStats *stats = nullptr;
+    int64_t n = 0, next = 0;         // frames [0, next) have been enqueued
+};
+
+struct InFlight { u64 seq = ~0ull; u64 job = 0; int64_t base = 0; int g = 0; };
+
 struct s3d_map {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -603,8 +737,16 @@ struct s3d_map {
     Slot *table = nullptr; u64 cap = 0;
     MapCtr *mc = nullptr;            // device
     MapCtr *mc_host = nullptr;       // pinned mirror
-    u64 count_known = 0;             // exact count at last sync
-    u64 max_touched = 0;             // largest per-frame unique-voxel count seen
+    u64 count_known = 0;             // live voxels at the last sync / chunk snapshot
+    u64 unique_est = 0;              // voxels touched by a recent chunk (upper bound of what it can insert)
+    static constexpr int RING = 4;   // per-chunk counter snapshots (bounded launch-ahead)
+    MapCtr *snap_host = nullptr;     // pinned [RING]
+    cudaEvent_t snap_ev[RING] = {};
+    InFlight inflight[RING];
+    u64 chunk_seq = 0;               // chunks enqueued so far
+    u64 snap_floor = 0;              // snapshots older than this predate the last exact sync
+    std::deque<Job> jobs; u64 job_seq = 0;
+    u64 n_retries = 0, n_grows = 0;
     // params / tables
     bool have_params = false, have_tables = false;
     DevParams p{};
@@ -613,26 +755,56 @@ struct s3d_map {
     DevBuf<double> d_cos_b, d_sin_b, d_range, d_cos_va, d_sin_va;
     DevBuf<short> d_col_to_beam;
     u64 samples_max = 0;             // worst-case samples per frame for these tables
-    // in-flight frame slots
-    int G = 16;
-    DevBuf<SEntry> scratch; u64 scratch_cap = 0;   // per frame slot
-    DevBuf<u32> lists;
+    // chunk working set
+    DevBuf<u64> skeys, scnt; u64 scratch_cap = 0;
+    DevBuf<double> sum_tab;          // [2][SUMT] running sums of n copies of lo_free / lo_occ
     DevBuf<int> first_hit;
-    FrameCtr *fctr = nullptr;
+    ChunkCtr *cc = nullptr;
     DevBuf<DevStats> stats; DevStats *stats_host = nullptr; size_t stats_host_n = 0;
     // staging
     DevBuf<uint8_t> img_dev; DevBuf<double> T_dev;
-    uint8_t *img_pinned = nullptr; size_t img_pinned_n = 0;
-    double *T_pinned = nullptr; size_t T_pinned_n = 0;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> copy_ev;
     DevBuf<u64> io_keys; DevBuf<double> io_vals; DevBuf<uint8_t> io_flags;
     // export staging
     DevBuf<double> ex_xyz, ex_prob, ex_L; DevBuf<int8_t> ex_cls; DevBuf<int> ex_ijk; DevBuf<float4> ex_f32;
     u64 *ex_counts = nullptr; u64 *ex_counts_host = nullptr; u64 ex_n = 0; bool ex_valid = false;
+    // measurement
+    bool prof_on = false;
+    std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+    struct Span { size_t e0, e1; int kind; };
+    std::vector<Span> spans;
+    s3d_profile prof{};
+    u64 launches = 0;
 };
 
 namespace {
 
 int set_device(s3d_map *m) { CU(cudaSetDevice(m->device)); return 0; }
+
+// CUDA-event bracket around one kernel group, on the launching stream
+size_t prof_mark(s3d_map *m)
+{
+    if (m->ev_used == m->ev_pool.size()) {
+        cudaEvent_t e; cudaEventCreate(&e);
+        m->ev_pool.push_back(e);
+    }
+    cudaEventRecord(m->ev_pool[m->ev_used], m->stream);
+    return m->ev_used++;
+}
+
+int prof_collect(s3d_map *m)
+{
+    if (m->spans.empty()) { m->ev_used = 0; return 0; }
+    CU(cudaStreamSynchronize(m->stream));
+    for (const auto &sp : m->spans) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, m->ev_pool[sp.e0], m->ev_pool[sp.e1]));
+        m->prof.ms[sp.kind] += ms;
+    }
+    m->spans.clear(); m->ev_used = 0;
+    return 0;
+}
 
 int launch_fill_table(s3d_map *m, Slot *t, u64 n)
 {
@@ -642,22 +814,30 @@ int launch_fill_table(s3d_map *m, Slot *t, u64 n)
     return 0;
 }
 
-// read back the map counters (sync) and turn device error flags into return codes
+int pump(s3d_map *m, bool drain);
+
+int fatal_from_flags(s3d_map *m, u32 err)
+{
+    if (!err) return 0;
+    u32 zero = 0;   // clear so that the map stays usable after the caller handles the error
+    cudaMemcpyAsync(&m->mc->err, &zero, sizeof zero, cudaMemcpyHostToDevice, m->stream);
+    cudaStreamSynchronize(m->stream);
+    if (err & ERR_TABLEFULL) return fail(S3D_ETABLEFULL, "voxel table full (capacity %llu slots)", (unsigned long long)m->cap);
+    return fail(S3D_EKEYRANGE, "voxel key outside +-2^20 or non-finite coordinate");
+}
+
+// Finish every queued frame (re-running chunks that asked for a retry), then read back the map
+// counters and turn fatal device flags into return codes.  Every synchronous entry point
+// starts or ends here.
 int sync_counters(s3d_map *m)
 {
+    int rc = pump(m, true);
+    if (rc) return rc;
     CU(cudaMemcpyAsync(m->mc_host, m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, m->stream));
     CU(cudaStreamSynchronize(m->stream));
     m->count_known = m->mc_host->count;
-    const u32 err = m->mc_host->err;
-    if (err) {
-        u32 zero = 0;   // clear so that the map stays usable after the caller handles the error
-        cudaMemcpyAsync(&m->mc->err, &zero, sizeof zero, cudaMemcpyHostToDevice, m->stream);
-        cudaStreamSynchronize(m->stream);
-        if (err & ERR_TABLEFULL) return fail(S3D_ETABLEFULL, "voxel table full (capacity %llu slots)", (unsigned long long)m->cap);
-        if (err & ERR_SCRATCH) return fail(S3D_ESCRATCH, "per-frame dedupe scratch overflow");
-        if (err & ERR_KEYRANGE) return fail(S3D_EKEYRANGE, "voxel key outside +-2^20 or non-finite coordinate");
-    }
-    return 0;
+    m->snap_floor = m->chunk_seq;
+    return fatal_from_flags(m, m->mc_host->err);
 }
 
 int grow_table(s3d_map *m, u64 new_cap)
@@ -676,18 +856,22 @@ int grow_table(s3d_map *m, u64 new_cap)
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(m->stream));
         CU(cudaFree(m->table));
+        ++m->n_grows;
     }
     m->table = nt; m->cap = new_cap;
     m->ex_valid = false;
     return 0;
 }
 
-// keep load factor <= 1/2 for `extra` more voxels on top of the last known count
+// the device gate: a chunk is applied only if count + unique(chunk) stays within this
+u64 table_limit(const s3d_map *m) { return m->cap / 4 * 3; }
+
+// room for `extra` more voxels on top of the last known count (stream must be idle)
 int ensure_room(s3d_map *m, u64 extra)
 {
-    const u64 need = 2 * (m->count_known + extra);
-    if (need > m->cap) return grow_table(m, std::max(need, m->cap * 2));
-    return 0;
+    u64 cap = m->cap;
+    while (m->count_known + extra > cap / 2) cap *= 2;
+    return cap > m->cap ? grow_table(m, cap) : 0;
 }
 
 template <typename T> int upload(DevBuf<T> &b, const T *src, size_t n, cudaStream_t s)
@@ -697,67 +881,174 @@ template <typename T> int upload(DevBuf<T> &b, const T *src, size_t n, cudaStrea
     return 0;
 }
 
-int ensure_frame_slots(s3d_map *m)
+// (re)allocate and wipe the chunk dedupe table; the stream must be idle
+int ensure_scratch(s3d_map *m, u64 want_cap, bool wipe)
 {
-    // scratch sized for the worst-case number of samples a frame can emit (every sample a new key)
-    const u64 want = next_pow2(std::max<u64>(1024, m->samples_max + m->samples_max / 2));
-    if (want != m->scratch_cap || !m->scratch.p) {
-        CU(cudaStreamSynchronize(m->stream));
-        m->scratch_cap = want;
-        int rc = m->scratch.ensure((size_t)want * m->G); if (rc) return rc;
-        rc = m->lists.ensure((size_t)want * m->G); if (rc) return rc;
-        const u64 n = m->scratch.n;
-        const int blocks = (int)std::min<u64>((n + 255) / 256, (u64)m->n_sm * 16);
-        k_fill_scratch<<<blocks, 256, 0, m->stream>>>(m->scratch.p, n);
-        CU(cudaGetLastError());
-        CU(cudaMemsetAsync(m->fctr, 0, sizeof(FrameCtr) * m->G, m->stream));
+    want_cap = next_pow2(std::max<u64>(want_cap, 1u << 12));
+    if (want_cap > (1ull << 31)) return fail(S3D_ENOMEM, "chunk dedupe table would exceed 2^31 entries");
+    const bool realloc = want_cap > m->scratch_cap;
+    if (realloc) {
+        int rc = m->skeys.ensure((size_t)want_cap); if (rc) return rc;
+        rc = m->scnt.ensure((size_t)want_cap * GF); if (rc) return rc;
+        m->scratch_cap = want_cap;
     }
-    int rc = m->first_hit.ensure((size_t)m->G * std::max(1, m->tab.n_beams)); if (rc) return rc;
+    if (realloc || wipe) {
+        const int blocks = (int)std::min<u64>((m->scratch_cap + 255) / 256, (u64)m->n_sm * 16);
+        k_fill_u64<<<blocks, 256, 0, m->stream>>>(m->skeys.p, m->scratch_cap, EMPTY_KEY);
+        CU(cudaGetLastError());
+        CU(cudaMemsetAsync(m->scnt.p, 0, sizeof(u64) * (size_t)m->scratch_cap * GF, m->stream));
+    }
     return 0;
 }
 
-// The device pipeline for n frames whose images / transforms already sit in device memory.
-int run_frames(s3d_map *m, const uint8_t *imgs_dev, int64_t n, const double *T_dev, DevStats *stats_dev)
+int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
 {
     const DevTables &tab = m->tab;
     const size_t img_stride = (size_t)tab.H * tab.W;
+    const uint8_t *imgs = j.imgs + (size_t)base * img_stride;
+    const bool vec16 = (tab.W % 16 == 0) && ((uintptr_t)imgs % 16 == 0) && (img_stride % 16 == 0);
+    const int max_c = (tab.H + tab.free_step - 1) / tab.free_step + tab.occ_window;
+    const size_t ex_smem = sizeof(int) * (size_t)(3 * max_c + 1);
+    const size_t fh_smem = sizeof(int) * (size_t)tab.n_beams;
+    const size_t e0 = m->prof_on ? prof_mark(m) : 0;
+    CU(cudaMemsetAsync(m->first_hit.p, 0x7f, sizeof(int) * (size_t)g * tab.n_beams, m->stream));
+    dim3 g1((tab.H + FH_ROWS - 1) / FH_ROWS, g);
+    if (vec16) k_first_hit<16><<<g1, FH_THREADS, fh_smem, m->stream>>>(imgs, img_stride, tab, m->p.thr, m->first_hit.p);
+    else k_first_hit<1><<<g1, FH_THREADS, fh_smem, m->stream>>>(imgs, img_stride, tab, m->p.thr, m->first_hit.p);
+    const size_t e1 = m->prof_on ? prof_mark(m) : 0;
+    ExpandArgs a;
+    a.imgs = imgs; a.img_stride = img_stride;
+    a.T = j.T + base * 16;
+    a.tab = tab; a.p = m->p;
+    a.first_hit = m->first_hit.p;
+    a.skeys = m->skeys.p; a.scnt = m->scnt.p; a.smask = (u32)(m->scratch_cap - 1);
+    a.cc = m->cc; a.stats = j.stats + base; a.mc = m->mc;
+    a.seq = m->chunk_seq; a.table_limit = table_limit(m);
+    k_expand<<<dim3(tab.n_beams, g), EX_THREADS, ex_smem, m->stream>>>(a);
+    const size_t e2 = m->prof_on ? prof_mark(m) : 0;
+    const int ap_blocks = (int)std::min<u64>((m->scratch_cap + AP_TILE - 1) / AP_TILE, (u64)m->n_sm * 8);
+    k_apply_chunk<<<ap_blocks, AP_THREADS, 0, m->stream>>>(m->skeys.p, m->scnt.p, m->scratch_cap, g, m->cc,
+                                                          j.stats + base, m->table, m->cap - 1, m->p,
+                                                          m->sum_tab.p, m->mc);
+    CU(cudaGetLastError());
+    m->launches += 3;
+    if (m->prof_on) {
+        const size_t e3 = prof_mark(m);
+        m->spans.push_back({e0, e1, S3D_K_FIRST_HIT});
+        m->spans.push_back({e1, e2, S3D_K_EXPAND});
+        m->spans.push_back({e2, e3, S3D_K_APPLY});
+        for (int k = 0; k < S3D_K_COUNT; ++k) m->prof.launches[k] += 1;
+        m->prof.frames += (u64)g;
+    }
+    const int ri = (int)(m->chunk_seq % s3d_map::RING);
+    CU(cudaMemcpyAsync(&m->snap_host[ri], m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaEventRecord(m->snap_ev[ri], m->stream));
+    m->inflight[ri] = InFlight{m->chunk_seq, j.id, base, g};
+    ++m->chunk_seq;
+    m->ex_valid = false;
+    return 0;
+}
+
+// A chunk asked for a retry (dedupe table too loaded, or the voxel table would pass its load
+// bound).  Nothing of that chunk or of any later one has touched the voxel table.  Enlarge what
+// was short, wipe the chunk working set and rewind the job queue to the chunk's first frame.
+int recover(s3d_map *m)
+{
+    CU(cudaMemcpyAsync(m->mc_host, m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    const MapCtr mc = *m->mc_host;
+    if (!mc.abort) return 0;
+    const InFlight inf = m->inflight[mc.abort_seq % s3d_map::RING];
+    if (inf.seq != mc.abort_seq) return fail(S3D_ECUDA, "internal: lost track of chunk %llu", (unsigned long long)mc.abort_seq);
+    ++m->n_retries;
+    m->count_known = mc.count;
+    m->snap_floor = m->chunk_seq;
+    int rc;
+    if (mc.abort & ABORT_TABLE) {
+        if ((rc = grow_table(m, m->cap * 2))) return rc;
+    }
+    if ((rc = ensure_scratch(m, (mc.abort & ABORT_SCRATCH) ? m->scratch_cap * 2 : m->scratch_cap, true))) return rc;
+    k_clear_abort<<<1, 1, 0, m->stream>>>(m->mc, m->cc);
+    CU(cudaGetLastError());
+    bool hit = false;
+    for (Job &j : m->jobs) {
+        if (j.id == inf.job) { j.next = inf.base; hit = true; }
+        else if (hit) j.next = 0;
+        if (hit && j.next < j.n)
+            CU(cudaMemsetAsync(j.stats + j.next, 0, sizeof(DevStats) * (size_t)(j.n - j.next), m->stream));
+    }
+    if (!hit) return fail(S3D_ECUDA, "internal: retry for an unknown job");
+    return 0;
+}
+
+// Enqueue the queued frames chunk by chunk with a bounded launch-ahead; with `drain`, also wait
+// until everything is applied (re-running chunks that asked for a retry).
+int pump(s3d_map *m, bool drain)
+{
+    constexpr int LOOKAHEAD = 1;          // chunks allowed in flight behind the one being enqueued
+    static_assert(LOOKAHEAD + 2 <= s3d_map::RING, "snapshot ring too small");
+    for (;;) {
+        Job *job = nullptr;
+        for (Job &j : m->jobs) if (j.next < j.n) { job = &j; break; }
+        if (job) {
+            const u64 q = m->chunk_seq;
+            if (q >= m->snap_floor + 1 + LOOKAHEAD) {
+                // wait for the counters of chunk q-1-LOOKAHEAD: bounds the launch-ahead and is
+                // where retries and growth needs are noticed early
+                const int ri = (int)((q - 1 - LOOKAHEAD) % s3d_map::RING);
+                CU(cudaEventSynchronize(m->snap_ev[ri]));
+                const MapCtr &sn = m->snap_host[ri];
+                if (sn.abort) { int rc = recover(m); if (rc) return rc; continue; }
+                m->count_known = sn.count;
+                m->unique_est = std::max<u64>(sn.last_unique, m->unique_est - m->unique_est / 8);
+            }
+            // grow ahead of the gate when the chunks in flight could reach it (saves a retry)
+            if (m->count_known + (u64)(LOOKAHEAD + 2) * m->unique_est > table_limit(m) ||
+                2 * m->unique_est > m->scratch_cap) {
+                CU(cudaMemcpyAsync(m->mc_host, m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, m->stream));
+                CU(cudaStreamSynchronize(m->stream));
+                if (m->mc_host->abort) { int rc = recover(m); if (rc) return rc; continue; }
+                m->count_known = m->mc_host->count;
+                m->snap_floor = m->chunk_seq;
+                int rc;
+                if (m->count_known + (u64)(LOOKAHEAD + 2) * m->unique_est > table_limit(m) &&
+                    (rc = grow_table(m, m->cap * 2))) return rc;
+                if (2 * m->unique_est > m->scratch_cap && (rc = ensure_scratch(m, m->scratch_cap * 2, false))) return rc;
+            }
+            const int g = (int)std::min<int64_t>(GF, job->n - job->next);
+            if (m->prof_on && m->ev_used > 4096) { int rc = prof_collect(m); if (rc) return rc; }
+            int rc = enqueue_chunk(m, *job, job->next, g);
+            if (rc) return rc;
+            job->next += g;
+            continue;
+        }
+        if (!drain || m->jobs.empty()) return 0;
+        CU(cudaMemcpyAsync(m->mc_host, m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, m->stream));
+        CU(cudaStreamSynchronize(m->stream));
+        if (m->mc_host->abort) { int rc = recover(m); if (rc) return rc; continue; }
+        m->count_known = m->mc_host->count;
+        m->unique_est = std::max<u64>(m->unique_est, m->mc_host->last_unique);
+        m->snap_floor = m->chunk_seq;
+        m->jobs.clear();
+        return 0;
+    }
+}
+
+// queue n frames whose images / transforms sit in device memory
+int submit_frames(s3d_map *m, const uint8_t *imgs_dev, int64_t n, const double *T_dev, DevStats *stats_dev)
+{
     CU(cudaMemsetAsync(stats_dev, 0, sizeof(DevStats) * (size_t)n, m->stream));
-    if (tab.n_beams == 0 || tab.H == 0) {
-        // nothing to expand; num_voxels still has to be reported
+    if (m->tab.n_beams == 0 || m->tab.H == 0) {
+        // nothing to expand; len(voxels) still has to be reported
+        int rc = pump(m, true); if (rc) return rc;
         for (int64_t f = 0; f < n; ++f)
             CU(cudaMemcpyAsync(&stats_dev[f].n_voxels, &m->mc->count, sizeof(u64), cudaMemcpyDeviceToDevice, m->stream));
         return 0;
     }
-    const bool vec16 = (tab.W % 16 == 0) && ((uintptr_t)imgs_dev % 16 == 0);
-    const int max_c = (tab.H + tab.free_step - 1) / tab.free_step + tab.occ_window;
-    const size_t ex_smem = sizeof(int) * (size_t)(3 * max_c + 1);
-    const int apply_blocks = m->n_sm * 2;
-    for (int64_t base = 0; base < n; base += m->G) {
-        const int g = (int)std::min<int64_t>(m->G, n - base);
-        CU(cudaMemsetAsync(m->first_hit.p, 0x7f, sizeof(int) * (size_t)g * tab.n_beams, m->stream));
-        dim3 g1((tab.H + FH_ROWS - 1) / FH_ROWS, g);
-        const size_t fh_smem = sizeof(int) * (size_t)tab.n_beams;
-        if (vec16)
-            k_first_hit<16><<<g1, FH_THREADS, fh_smem, m->stream>>>(imgs_dev + base * img_stride, img_stride, tab, m->p.thr, m->first_hit.p);
-        else
-            k_first_hit<1><<<g1, FH_THREADS, fh_smem, m->stream>>>(imgs_dev + base * img_stride, img_stride, tab, m->p.thr, m->first_hit.p);
-        ExpandArgs a;
-        a.imgs = imgs_dev + base * img_stride; a.img_stride = img_stride;
-        a.T = T_dev + base * 16;
-        a.tab = tab; a.p = m->p;
-        a.first_hit = m->first_hit.p;
-        a.scratch = m->scratch.p; a.scratch_mask = (u32)(m->scratch_cap - 1); a.scratch_stride = m->scratch_cap;
-        a.lists = m->lists.p; a.list_cap = (u32)m->scratch_cap;
-        a.fctr = m->fctr; a.stats = stats_dev + base; a.mc = m->mc;
-        k_expand<<<dim3(tab.n_beams, g), EX_THREADS, ex_smem, m->stream>>>(a);
-        for (int f = 0; f < g; ++f)
-            k_apply<<<apply_blocks, AP_THREADS, 0, m->stream>>>(
-                m->scratch.p + (size_t)f * m->scratch_cap, m->lists.p + (size_t)f * m->scratch_cap, m->fctr + f,
-                stats_dev + base + f, m->table, m->cap - 1, m->p, m->mc);
-    }
-    CU(cudaGetLastError());
-    m->ex_valid = false;
-    return 0;
+    Job j;
+    j.id = ++m->job_seq; j.imgs = imgs_dev; j.T = T_dev; j.stats = stats_dev; j.n = n; j.next = 0;
+    m->jobs.push_back(j);
+    return pump(m, false);
 }
 
 int check_ready(s3d_map *m)
@@ -768,17 +1059,11 @@ int check_ready(s3d_map *m)
     return 0;
 }
 
-// room for n more frames: each frame can add at most its unique-voxel count; bounded by the
-// largest count seen so far (x1.5), or by the worst-case sample count before any frame ran.
-int reserve_frames(s3d_map *m, int64_t n)
-{
-    u64 per_frame = m->max_touched ? m->max_touched + m->max_touched / 2 + 1024 : m->samples_max;
-    per_frame = std::min<u64>(per_frame, m->samples_max);
-    return ensure_room(m, per_frame * (u64)n);
-}
-
 int finish_stats(s3d_map *m, const DevStats *stats_dev, int64_t n, s3d_frame_stats *out)
 {
+    int rc = sync_counters(m);
+    if (rc) return rc;
+    if (!out) return 0;
     if (m->stats_host_n < (size_t)n) {
         if (m->stats_host) cudaFreeHost(m->stats_host);
         m->stats_host = nullptr; m->stats_host_n = 0;
@@ -786,16 +1071,13 @@ int finish_stats(s3d_map *m, const DevStats *stats_dev, int64_t n, s3d_frame_sta
         m->stats_host_n = (size_t)n;
     }
     CU(cudaMemcpyAsync(m->stats_host, stats_dev, sizeof(DevStats) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
-    int rc = sync_counters(m);
+    CU(cudaStreamSynchronize(m->stream));
     for (int64_t f = 0; f < n; ++f) {
         const DevStats &s = m->stats_host[f];
-        m->max_touched = std::max<u64>(m->max_touched, s.n_occ + s.n_free);
-        if (out) {
-            out[f].num_occupied = (int64_t)s.n_occ; out[f].num_free = (int64_t)s.n_free;
-            out[f].num_voxels = (int64_t)s.n_voxels; out[f].num_samples = (int64_t)s.n_samples;
-        }
+        out[f].num_occupied = (int64_t)s.n_occ; out[f].num_free = (int64_t)s.n_free;
+        out[f].num_voxels = (int64_t)s.n_voxels; out[f].num_samples = (int64_t)s.n_samples;
     }
-    return rc;
+    return 0;
 }
 
 int pack_keys_host(const int32_t *ijk, int64_t n, std::vector<u64> &out)
@@ -837,8 +1119,11 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
     CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&m->mc, sizeof(MapCtr)));
     CU(cudaMallocHost(&m->mc_host, sizeof(MapCtr)));
-    CU(cudaMalloc(&m->fctr, sizeof(FrameCtr) * m->G));
-    CU(cudaMemsetAsync(m->fctr, 0, sizeof(FrameCtr) * m->G, m->stream));
+    CU(cudaMallocHost(&m->snap_host, sizeof(MapCtr) * s3d_map::RING));
+    for (int i = 0; i < s3d_map::RING; ++i) CU(cudaEventCreateWithFlags(&m->snap_ev[i], cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&m->cc, sizeof(ChunkCtr)));
+    CU(cudaMemsetAsync(m->cc, 0, sizeof(ChunkCtr), m->stream));
     CU(cudaMalloc(&m->ex_counts, sizeof(u64) * 4));
     CU(cudaMallocHost(&m->ex_counts_host, sizeof(u64) * 4));
     k_reset_ctr<<<1, 1, 0, m->stream>>>(m->mc);
@@ -857,17 +1142,20 @@ int s3d_destroy(s3d_map *m)
     if (m->table) cudaFree(m->table);
     if (m->mc) cudaFree(m->mc);
     if (m->mc_host) cudaFreeHost(m->mc_host);
-    if (m->fctr) cudaFree(m->fctr);
+    if (m->snap_host) cudaFreeHost(m->snap_host);
+    for (int i = 0; i < s3d_map::RING; ++i) if (m->snap_ev[i]) cudaEventDestroy(m->snap_ev[i]);
+    if (m->cc) cudaFree(m->cc);
+    for (cudaEvent_t e : m->copy_ev) cudaEventDestroy(e);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->ex_counts) cudaFree(m->ex_counts);
     if (m->ex_counts_host) cudaFreeHost(m->ex_counts_host);
     if (m->stats_host) cudaFreeHost(m->stats_host);
-    if (m->img_pinned) cudaFreeHost(m->img_pinned);
-    if (m->T_pinned) cudaFreeHost(m->T_pinned);
     m->d_beam_col.release(); m->d_nv_free.release(); m->d_nv_occ.release();
     m->d_cos_b.release(); m->d_sin_b.release(); m->d_range.release(); m->d_cos_va.release(); m->d_sin_va.release();
-    m->d_col_to_beam.release(); m->scratch.release(); m->lists.release(); m->first_hit.release(); m->stats.release();
+    m->d_col_to_beam.release(); m->skeys.release(); m->scnt.release(); m->sum_tab.release(); m->first_hit.release(); m->stats.release();
     m->img_dev.release(); m->T_dev.release(); m->io_keys.release(); m->io_vals.release(); m->io_flags.release();
     m->ex_xyz.release(); m->ex_prob.release(); m->ex_L.release(); m->ex_cls.release(); m->ex_ijk.release(); m->ex_f32.release();
+    for (cudaEvent_t e : m->ev_pool) cudaEventDestroy(e);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
     return 0;
@@ -885,6 +1173,16 @@ int s3d_set_params(s3d_map *m, const s3d_params *q)
     p.zmin = q->z_filter_min;
     p.adaptive = q->adaptive_update; p.zfilter = q->z_filter_enabled;
     p.thr = std::max(-1, std::min(255, q->intensity_threshold));
+    {
+        // running sums, one addition at a time, exactly as `sum += log_odds` accumulates them
+        int rc = set_device(m); if (rc) return rc;
+        if ((rc = pump(m, true))) return rc;
+        double tab[2][SUMT];
+        tab[0][0] = tab[1][0] = 0.0;
+        for (int n = 1; n < SUMT; ++n) { tab[0][n] = tab[0][n - 1] + p.lo_free; tab[1][n] = tab[1][n - 1] + p.lo_occ; }
+        if ((rc = upload(m->sum_tab, &tab[0][0], (size_t)2 * SUMT, m->stream))) return rc;
+        CU(cudaStreamSynchronize(m->stream));
+    }
     m->have_params = true;
     m->ex_valid = false;
     return 0;
@@ -898,7 +1196,7 @@ int s3d_set_tables(s3d_map *m, const s3d_tables *t)
     if (t->free_step < 1 || t->occ_window < 0) return fail(S3D_EINVAL, "bad free_step/occ_window");
     if (t->H >= (1 << 30)) return fail(S3D_EINVAL, "H too large");
     int rc = set_device(m); if (rc) return rc;
-    CU(cudaStreamSynchronize(m->stream));
+    if ((rc = sync_counters(m))) return rc;
     const size_t nb = (size_t)t->n_beams, H = (size_t)t->H;
     const size_t nfan = (size_t)t->nv_max * ((size_t)t->nv_max + 2);
     std::vector<short> c2b((size_t)t->W, (short)-1);
@@ -938,7 +1236,9 @@ int s3d_set_tables(s3d_map *m, const s3d_tables *t)
     d.nv_free = m->d_nv_free.p; d.nv_occ = m->d_nv_occ.p; d.cos_va = m->d_cos_va.p; d.sin_va = m->d_sin_va.p;
     d.col_to_beam = m->d_col_to_beam.p;
     m->have_tables = true;
-    return ensure_frame_slots(m);
+    if ((rc = m->first_hit.ensure((size_t)GF * std::max(1, t->n_beams)))) return rc;
+    // first guess for the chunk dedupe table; it doubles on demand (retry) from here
+    return ensure_scratch(m, std::min<u64>(1u << 20, std::max<u64>(1u << 14, m->samples_max / 4)), false);
 }
 
 int s3d_ingest_batch_dev(s3d_map *m, const uint8_t *images_dev, int64_t n, const double *T_dev,
@@ -948,10 +1248,13 @@ int s3d_ingest_batch_dev(s3d_map *m, const uint8_t *images_dev, int64_t n, const
     if (n < 0) return fail(S3D_EINVAL, "n < 0");
     if (n == 0) return 0;
     if ((rc = set_device(m))) return rc;
-    if ((rc = reserve_frames(m, n))) return rc;
     DevStats *sd = reinterpret_cast<DevStats *>(stats_dev);
-    if (!sd) { if ((rc = m->stats.ensure((size_t)n))) return rc; sd = m->stats.p; }
-    if ((rc = run_frames(m, images_dev, n, T_dev, sd))) return rc;
+    if (!sd) {
+        if ((rc = pump(m, true))) return rc;              // the internal stats buffer may be reallocated
+        if ((rc = m->stats.ensure((size_t)n))) return rc;
+        sd = m->stats.p;
+    }
+    if ((rc = submit_frames(m, images_dev, n, T_dev, sd))) return rc;
     if (out) return finish_stats(m, sd, n, out);
     return 0;
 }
@@ -963,18 +1266,34 @@ int s3d_ingest_batch(s3d_map *m, const uint8_t *images, int64_t n, const double 
     if (n == 0) return 0;
     if (!images || !T) return fail(S3D_EINVAL, "null input");
     if ((rc = set_device(m))) return rc;
-    if ((rc = reserve_frames(m, n))) return rc;
+    if ((rc = pump(m, true))) return rc;                  // staging buffers are about to be reused
     const size_t img_bytes = (size_t)m->tab.H * m->tab.W;
     if ((rc = m->stats.ensure((size_t)n))) return rc;
-    // frames travel in pieces of `piece` frames so the device staging stays bounded
-    const int64_t piece = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)((256u << 20) / std::max<size_t>(1, img_bytes))));
-    if ((rc = m->img_dev.ensure(std::max<size_t>(16, img_bytes * (size_t)piece)))) return rc;
-    if ((rc = m->T_dev.ensure(16 * (size_t)piece))) return rc;
-    for (int64_t base = 0; base < n; base += piece) {
-        const int64_t k = std::min<int64_t>(piece, n - base);
-        if (img_bytes) CU(cudaMemcpyAsync(m->img_dev.p, images + (size_t)base * img_bytes, img_bytes * (size_t)k, cudaMemcpyHostToDevice, m->stream));
+    // The whole call is staged in device memory (up to 1 GiB at a time), so a chunk that has
+    // to be re-run still finds its frames.  Copies go in sub-pieces on a second stream and
+    // overlap the kernels of the previous sub-piece.
+    const int64_t stage = std::max<int64_t>(GF, std::min<int64_t>(n, (int64_t)((1ull << 30) / std::max<size_t>(1, img_bytes))));
+    const int64_t sub = 2 * GF;
+    if ((rc = m->img_dev.ensure(std::max<size_t>(16, img_bytes * (size_t)stage)))) return rc;
+    if ((rc = m->T_dev.ensure(16 * (size_t)stage))) return rc;
+    for (int64_t base = 0; base < n; base += stage) {
+        const int64_t k = std::min<int64_t>(stage, n - base);
+        if (base > 0 && (rc = pump(m, true))) return rc;
         CU(cudaMemcpyAsync(m->T_dev.p, T + base * 16, sizeof(double) * 16 * (size_t)k, cudaMemcpyHostToDevice, m->stream));
-        if ((rc = run_frames(m, m->img_dev.p, k, m->T_dev.p, m->stats.p + base))) return rc;
+        size_t ei = 0;
+        for (int64_t s0 = 0; s0 < k; s0 += sub, ++ei) {
+            const int64_t kk = std::min<int64_t>(sub, k - s0);
+            if (ei == m->copy_ev.size()) {
+                cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                m->copy_ev.push_back(e);
+            }
+            if (img_bytes)
+                CU(cudaMemcpyAsync(m->img_dev.p + (size_t)s0 * img_bytes, images + (size_t)(base + s0) * img_bytes,
+                                   img_bytes * (size_t)kk, cudaMemcpyHostToDevice, m->copy_stream));
+            CU(cudaEventRecord(m->copy_ev[ei], m->copy_stream));
+            CU(cudaStreamWaitEvent(m->stream, m->copy_ev[ei], 0));
+            if ((rc = submit_frames(m, m->img_dev.p + (size_t)s0 * img_bytes, kk, m->T_dev.p + s0 * 16, m->stats.p + base + s0))) return rc;
+        }
     }
     return finish_stats(m, m->stats.p, n, out);
 }
@@ -1121,7 +1440,6 @@ int s3d_clear(s3d_map *m)
     if ((rc = launch_fill_table(m, m->table, m->cap))) return rc;
     k_reset_ctr<<<1, 1, 0, m->stream>>>(m->mc);
     CU(cudaGetLastError());
-    m->max_touched = 0;
     m->ex_valid = false;
     return sync_counters(m);
 }
@@ -1173,6 +1491,29 @@ int s3d_export_read_xyzi32(s3d_map *m, float *xyzi, uint64_t n)
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(xyzi, m->ex_f32.p, sizeof(float4) * n, cudaMemcpyDeviceToHost, m->stream));
     CU(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int s3d_profile_enable(s3d_map *m, int on)
+{
+    if (!m) return fail(S3D_EINVAL, "null map");
+    int rc = set_device(m); if (rc) return rc;
+    if ((rc = prof_collect(m))) return rc;
+    m->prof_on = on != 0;
+    return 0;
+}
+
+int s3d_profile_read(s3d_map *m, s3d_profile *out)
+{
+    if (!m || !out) return fail(S3D_EINVAL, "null argument");
+    int rc = set_device(m); if (rc) return rc;
+    if ((rc = prof_collect(m))) return rc;
+    CU(cudaStreamSynchronize(m->stream));
+    m->prof.total_launches = m->launches;
+    m->prof.retries = m->n_retries; m->prof.grows = m->n_grows;
+    *out = m->prof;
+    m->prof = s3d_profile{};
+    m->launches = 0; m->n_retries = 0; m->n_grows = 0;
     return 0;
 }
 
