@@ -20,6 +20,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <deque>
 #include <limits>
 #include <string>
@@ -42,6 +43,7 @@ struct __align__(16) Slot { u64 key; double val; };
 
 struct DevParams {
     double res, inv_res, lo_occ, lo_free, lo_min, lo_max, a_thr, a_ratio, zmin;
+    double l_skip;   // log-odds above which prob > a_thr for sure (+inf = never skip the exp)
     int adaptive, zfilter, thr;
 };
 
@@ -96,15 +98,28 @@ __host__ __device__ __forceinline__ void unpack_key(u64 key, int &i, int &j, int
     k = (int)(key & m) - KEY_BIAS;
 }
 
-// floor(w / res) exactly as IEEE division would give it (3d_mapper.py:63-65), but with the
-// division taken only when the reciprocal product lands within 1e-6 of an integer.
+// floor(w / res) exactly as IEEE division would give it (3d_mapper.py:63-65).  The reciprocal
+// product decides whenever it is not within 1e-6 of an integer (its error is < 1e-9 for
+// in-range keys); only the rare near-integer case pays for the division.
 __device__ __forceinline__ bool voxel_index(double w, double res, double inv_res, int &out)
 {
-    double q = w * inv_res;
-    if (!(fabs(q) < (double)(KEY_BIAS - 1))) return false;   // also rejects NaN/inf
-    if (fabs(q - rint(q)) < 1e-6) q = __ddiv_rn(w, res);
-    out = (int)floor(q);
+    const double q = w * inv_res;
+    const int k = __double2int_rd(q);                 // floor; saturates, NaN -> 0
+    const double fr = q - (double)k;
+    if (fr > 1e-6 && fr < 1.0 - 1e-6 && k > -KEY_BIAS && k < KEY_BIAS - 1) { out = k; return true; }
+    if (!(fabs(q) < (double)(KEY_BIAS - 1))) return false;   // out of range, NaN or inf
+    out = (int)floor(__ddiv_rn(w, res));
     return true;
+}
+
+// cheap 32-bit mix for the chunk dedupe table (the voxel table keeps the stronger mix64)
+__device__ __forceinline__ u32 mix32(u64 key)
+{
+    u32 h = (u32)key ^ ((u32)(key >> 32) * 0x9E3779B1u);
+    h ^= h >> 15; h *= 0x85EBCA77u;
+    h ^= h >> 13; h *= 0xC2B2AE3Du;
+    h ^= h >> 16;
+    return h;
 }
 
 // ------------------------------------------------------------------------------------ K1
@@ -170,6 +185,8 @@ k_first_hit(const uint8_t *__restrict__ imgs, size_t img_stride, DevTables tab, 
 // host trig tables, Sonar->Map transform, z filter, voxel key, and a count bump in the
 // chunk's dedupe table: one entry per voxel touched by the chunk, one counter lane per frame.
 constexpr int EX_THREADS = 128;
+constexpr int EX_BEAMS = EX_THREADS / 32;   // beams per block: warp b lists beam b
+constexpr int EX_ILP = 2;                   // samples per lane per pass
 constexpr u32 SCRATCH_PROBE_LIMIT = 512;
 
 struct ExpandArgs {
@@ -178,9 +195,11 @@ struct ExpandArgs {
     DevTables tab; DevParams p;
     const int *first_hit;        // [g][n_beams]
     u64 *skeys; u64 *scnt; u32 smask;   // chunk dedupe table: keys[C], counters[C][GF]
+    u32 *slist;                         // [C] slots of the entries created by this chunk, dense
     ChunkCtr *cc;
     DevStats *stats;             // [g]
     MapCtr *mc;
+    int dbg;                     // S3D_DEBUG_STAGE (timing experiments only): 1 = no dedupe, 2 = probe only
     u64 seq;                     // chunk sequence number (for abort bookkeeping)
     u64 table_limit;             // gate: count + unique(chunk) must stay <= this
 };
@@ -191,123 +210,266 @@ __device__ __forceinline__ void raise_abort(MapCtr *mc, u32 why, u64 seq)
     atomicMin(&mc->abort_seq, seq);
 }
 
-// returns 1 if this call created the entry
-__device__ __forceinline__ int scratch_add(const ExpandArgs &a, u64 key, int lane, u64 inc)
+// Bump lane `lane` of the entry of `key`, creating the entry if needed.  `cur` is the key word
+// already loaded from the home slot.  Returns the slot if this call created the entry, else ~0.
+__device__ __forceinline__ u32 scratch_resolve(const ExpandArgs &a, u64 key, u32 slot, u64 cur, int lane, u64 inc)
 {
-    u32 slot = (u32)mix64(key) & a.smask;
     for (u32 probe = 0; probe < SCRATCH_PROBE_LIMIT; ++probe) {
-        u64 cur = __ldcg(&a.skeys[slot]);
-        int created = 0;
+        bool created = false;
         if (cur == EMPTY_KEY) {
             cur = atomicCAS(&a.skeys[slot], EMPTY_KEY, key);
-            if (cur == EMPTY_KEY) { cur = key; created = 1; }
+            if (cur == EMPTY_KEY) { cur = key; created = true; }
         }
-        if (cur == key) { atomicAdd(&a.scnt[(size_t)slot * GF + lane], inc); return created; }
+        if (cur == key) {
+            // the counter lane is {n_free: low 32 bits, n_occ: high 32 bits}; bump the half that applies
+            u32 *half = reinterpret_cast<u32 *>(&a.scnt[(size_t)slot * GF + lane]);
+            if (inc >> 32) atomicAdd(half + 1, (u32)(inc >> 32)); else atomicAdd(half, (u32)inc);
+            return created ? slot : ~0u;
+        }
         slot = (slot + 1) & a.smask;
+        cur = __ldcg(&a.skeys[slot]);
     }
     raise_abort(a.mc, ABORT_SCRATCH, a.seq);     // table too loaded: the host enlarges it and retries
-    return 0;
+    return ~0u;
 }
 
+// One sample: sonar-frame point from the host trig tables, Sonar->Map transform, z filter, key.
+// Returns false if the sample is filtered out or its key is unusable.
+__device__ __forceinline__ bool sample_key(const ExpandArgs &a, const double *s_T, int r, int nv, int vi,
+                                           double cb, double sb, int &emitted, u64 &key)
+{
+    const DevTables &tab = a.tab;
+    const int ti = nv * nv - 1 + vi;                        // row nv, entry v_step + nv
+    const double cv = __ldg(&tab.cos_va[ti]), sv = __ldg(&tab.sin_va[ti]);
+    const double range = __ldg(&tab.range_m[r]);
+    // sonar frame, X fwd / Y right / Z down, products rounded left to right (:434-436)
+    const double rc = __dmul_rn(range, cv);
+    const double xs = __dmul_rn(rc, cb);
+    const double ys = -__dmul_rn(rc, sb);
+    const double zs = __dmul_rn(range, sv);
+    // T @ [x,y,z,1] as numpy evaluates it: (t0*x + t2*z) + (t1*y + t3) (:440)
+    double wv[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+        wv[q] = __dadd_rn(__dadd_rn(__dmul_rn(s_T[4 * q], xs), __dmul_rn(s_T[4 * q + 2], zs)),
+                          __dadd_rn(__dmul_rn(s_T[4 * q + 1], ys), s_T[4 * q + 3]));
+    if (a.p.zfilter && wv[2] < a.p.zmin) return false;      // :443, :478
+    ++emitted;
+    int ki, kj, kk;
+    if (voxel_index(wv[0], a.p.res, a.p.inv_res, ki) && voxel_index(wv[1], a.p.res, a.p.inv_res, kj) &&
+        voxel_index(wv[2], a.p.res, a.p.inv_res, kk)) {
+        key = pack_key(ki, kj, kk);
+        return true;
+    }
+    atomicOr(&a.mc->err, ERR_KEYRANGE);
+    return false;
+}
+
+constexpr int EX_WBUF = 128;      // per-warp staging of created dedupe slots (flushed in bulk)
+
+// move the warp's staged slots to the chunk's dense list: one atomic per flush
+__device__ __forceinline__ void flush_created(const ExpandArgs &a, u32 *wbuf, int &wn, int lane)
+{
+    if (wn == 0) return;
+    u32 base = 0;
+    if (lane == 0) base = atomicAdd(&a.cc->n_unique, (u32)wn);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    __syncwarp();
+    for (int q = lane; q < wn; q += 32) a.slist[(base + q) & a.smask] = wbuf[q];
+    __syncwarp();
+    wn = 0;
+}
+
+// Warp-wide commit of up to EX_ILP samples per lane into the chunk dedupe table.  Lanes that
+// hold the same voxel are merged first (adjacent range bins usually do), so only one lane per
+// distinct voxel touches the table; the home-slot probes of all samples are issued together.
+// Slots of entries created here are staged per warp and reach the chunk's dense list in bulk.
+__device__ __forceinline__ void commit_batch(const ExpandArgs &a, const bool (&ok)[EX_ILP], const u64 (&key)[EX_ILP],
+                                             bool occupied, int g, int lane, u32 *wbuf, int &wn)
+{
+    u32 slot[EX_ILP]; u64 inc[EX_ILP]; bool lead[EX_ILP];
+    if (a.dbg == 1) {
+        u64 x = 0;
+#pragma unroll
+        for (int j = 0; j < EX_ILP; ++j) x ^= ok[j] ? key[j] : 0ull;
+        if (x == 0x123456789ull) a.slist[0] = 1;
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < EX_ILP; ++j) {
+        const u32 m_ok = __ballot_sync(0xffffffffu, ok[j]);
+        lead[j] = false; slot[j] = 0; inc[j] = 0;
+        if (ok[j]) {
+            const u32 peers = __match_any_sync(m_ok, key[j]);
+            lead[j] = (lane == __ffs(peers) - 1);
+            const u64 n = (u64)__popc(peers);
+            inc[j] = occupied ? (n << 32) : n;
+            slot[j] = mix32(key[j]) & a.smask;
+        }
+    }
+    u64 cur[EX_ILP];
+#pragma unroll
+    for (int j = 0; j < EX_ILP; ++j) cur[j] = lead[j] ? __ldcg(&a.skeys[slot[j]]) : 0ull;
+    u32 made[EX_ILP];
+    int n_mine = 0;
+    if (a.dbg == 2) {
+        u64 x = 0;
+#pragma unroll
+        for (int j = 0; j < EX_ILP; ++j) x ^= cur[j];
+        if (x == 0x123456789ull) a.slist[0] = 1;
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < EX_ILP; ++j) {
+        made[j] = lead[j] ? scratch_resolve(a, key[j], slot[j], cur[j], g, inc[j]) : ~0u;
+        n_mine += made[j] != ~0u;
+    }
+    __syncwarp();
+    if (__any_sync(0xffffffffu, n_mine > 0)) {
+        int incl = n_mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        int dst = wn + incl - n_mine;
+#pragma unroll
+        for (int j = 0; j < EX_ILP; ++j)
+            if (made[j] != ~0u) wbuf[dst++] = made[j];
+        wn += __shfl_sync(0xffffffffu, incl, 31);
+        if (wn > EX_WBUF - 32 * EX_ILP) flush_created(a, wbuf, wn, lane);
+    }
+}
+
+// One warp per (processed beam, frame of the chunk); EX_BEAMS beams per block.
+//  1. list the beam's range samples: free = every free_step-th bin before the first hit (:420),
+//     occupied = above-threshold bins in the occ_window bins from the first hit (:451-452);
+//  2. free samples: the flattened (range sample, vertical step) space, 32 consecutive samples
+//     per pass (consecutive vertical steps => coalesced trig-table reads);
+//  3. occupied samples: a (vertical step, range bin) grid walked range-bin-fastest, so that
+//     the lanes of a pass are adjacent range bins at one vertical step -- they mostly fall into
+//     the same few voxels and are merged before touching the dedupe table.
 __global__ void __launch_bounds__(EX_THREADS)
 k_expand(ExpandArgs a)
 {
     extern __shared__ int s_dyn[];
     const DevTables &tab = a.tab;
     const int H = tab.H, W = tab.W;
-    const int max_c = (H + tab.free_step - 1) / tab.free_step + tab.occ_window;
-    int *s_off = s_dyn;                 // [max_c + 1] exclusive prefix of fan sizes
-    int *s_rn = s_dyn + max_c + 1;      // [max_c] r | (occupied << 30); fan half-width in s_nv
-    int *s_nv = s_rn + max_c;           // [max_c]
+    const int max_f = (H + tab.free_step - 1) / tab.free_step;        // free candidates per beam
+    const int per_warp = (max_f + 1) + max_f + 2 * tab.occ_window;
     __shared__ double s_T[12];
-    __shared__ int s_total;
     __shared__ bool s_last;
+    __shared__ u32 s_abort;
+    __shared__ u32 s_wbuf[EX_BEAMS][EX_WBUF];
 
-    if (__ldcg(&a.mc->abort)) return;   // an earlier chunk must be retried first: stay side-effect free
-    const int beam = blockIdx.x, g = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    u32 *wbuf = s_wbuf[warp];
+    int wn = 0;
+    const int g = blockIdx.y;
     const uint8_t *img = a.imgs + (size_t)g * a.img_stride;
-    const int col = tab.beam_col[beam];
-    int fh = a.first_hit[g * tab.n_beams + beam];
-    fh = fh < H ? fh : H;                                          // no hit -> whole ray is free (:412-413)
-    const int nfc = (fh + tab.free_step - 1) / tab.free_step;      // range(0, fh, free_step) (:420)
-    const int noc = fh < H ? min(tab.occ_window, H - fh) : 0;      // range(fh, min(fh+50, H)) (:451)
-    const int nc = nfc + noc;
+    if (threadIdx.x == 0) s_abort = __ldcg(&a.mc->abort);
     if (threadIdx.x < 12) s_T[threadIdx.x] = a.T[g * 16 + threadIdx.x];
-    for (int c = threadIdx.x; c < nc; c += EX_THREADS) {
-        int r, nv, occ;
-        if (c < nfc) { r = c * tab.free_step; nv = tab.nv_free[r]; occ = 0; }
-        else {
-            r = fh + (c - nfc); occ = 1;
-            nv = ((int)img[(size_t)r * W + col] > a.p.thr) ? tab.nv_occ[r] : 0;   // :452
-        }
-        s_rn[c] = r | (occ << 30);
-        s_nv[c] = nv;
-        s_off[c] = nv > 0 ? 2 * nv + 1 : 0;
-    }
     __syncthreads();
-    if (threadIdx.x < 32) {          // warp 0: exclusive scan of <= a few hundred fan sizes
-        int carry = 0;
-        for (int base = 0; base < nc; base += 32) {
-            const int c = base + threadIdx.x;
-            const int v = c < nc ? s_off[c] : 0;
+    if (s_abort) return;                // a chunk must be retried first: stay side-effect free (block-uniform)
+    int *f_off = s_dyn + warp * per_warp;      // [max_f + 1] exclusive prefix of free fan sizes
+    int *f_rn = f_off + (max_f + 1);           // [max_f] r | nv << 16 of free candidate c
+    int *o_r = f_rn + max_f;                   // [occ_window] range bin of occupied column
+    int *o_nv = o_r + tab.occ_window;          // [occ_window] its fan half-width
+    const int beam = blockIdx.x * EX_BEAMS + warp;
+    int emitted = 0;
+    if (beam < tab.n_beams) {
+        const int col = tab.beam_col[beam];
+        const double cb = tab.cos_b[beam], sb = tab.sin_b[beam];
+        int fh = a.first_hit[g * tab.n_beams + beam];
+        fh = fh < H ? fh : H;                                          // no hit -> whole ray is free (:412-413)
+        const int nfc = (fh + tab.free_step - 1) / tab.free_step;      // range(0, fh, free_step) (:420)
+        const int noc = fh < H ? min(tab.occ_window, H - fh) : 0;      // range(fh, min(fh+50, H)) (:451)
+        // ---- 1a. free candidates and the prefix sum of their fan sizes
+        int total_free = 0;
+        for (int base = 0; base < nfc; base += 32) {
+            const int c = base + lane;
+            int r = 0, nv = 0;
+            if (c < nfc) { r = c * tab.free_step; nv = tab.nv_free[r]; }
+            const int v = nv > 0 ? 2 * nv + 1 : 0;
             int incl = v;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                if ((int)threadIdx.x >= d) incl += t;
+                if (lane >= d) incl += t;
             }
-            if (c < nc) s_off[c] = carry + incl - v;
-            carry += __shfl_sync(0xffffffffu, incl, 31);
+            if (c < nfc) { f_off[c] = total_free + incl - v; f_rn[c] = r | (nv << 16); }
+            total_free += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (threadIdx.x == 0) { s_off[nc] = carry; s_total = carry; }
-    }
-    __syncthreads();
-    const int total = s_total;
-    const double cb = tab.cos_b[beam], sb = tab.sin_b[beam];
-    int emitted = 0, created = 0;
-    for (int w = threadIdx.x; w < total; w += EX_THREADS) {
-        int lo = 0, hi = nc;                      // largest c with s_off[c] <= w
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s_off[mid] <= w) lo = mid; else hi = mid;
+        if (lane == 0) f_off[nfc] = total_free;
+        // ---- 1b. occupied columns, compacted
+        int ncol = 0, nvmax = 0;
+        for (int base = 0; base < noc; base += 32) {
+            const int c = base + lane;
+            int r = 0, nv = 0;
+            if (c < noc) {
+                r = fh + c;
+                nv = ((int)img[(size_t)r * W + col] > a.p.thr) ? tab.nv_occ[r] : 0;       // :452, :456
+            }
+            const u32 m = __ballot_sync(0xffffffffu, nv > 0);
+            if (nv > 0) {
+                const int dst = ncol + __popc(m & ((1u << lane) - 1));
+                o_r[dst] = r; o_nv[dst] = nv;
+            }
+            ncol += __popc(m);
+            nvmax = max(nvmax, nv);
         }
-        const int c = lo;
-        const int rn = s_rn[c], nv = s_nv[c];
-        const int r = rn & 0x3fffffff, occ = rn >> 30;
-        const int vi = w - s_off[c];              // v_step + nv
-        const int ti = nv * nv - 1 + vi;
-        const double cv = __ldg(&tab.cos_va[ti]), sv = __ldg(&tab.sin_va[ti]);
-        const double range = __ldg(&tab.range_m[r]);
-        // sonar frame, X fwd / Y right / Z down, products rounded left to right (:434-436)
-        const double rc = __dmul_rn(range, cv);
-        const double xs = __dmul_rn(rc, cb);
-        const double ys = -__dmul_rn(rc, sb);
-        const double zs = __dmul_rn(range, sv);
-        // T @ [x,y,z,1] as numpy evaluates it: (t0*x + t2*z) + (t1*y + t3) (:440)
-        double wv[3];
 #pragma unroll
-        for (int q = 0; q < 3; ++q)
-            wv[q] = __dadd_rn(__dadd_rn(__dmul_rn(s_T[4 * q], xs), __dmul_rn(s_T[4 * q + 2], zs)),
-                              __dadd_rn(__dmul_rn(s_T[4 * q + 1], ys), s_T[4 * q + 3]));
-        if (a.p.zfilter && wv[2] < a.p.zmin) continue;          // :443, :478
-        ++emitted;
-        int ki, kj, kk;
-        if (!(voxel_index(wv[0], a.p.res, a.p.inv_res, ki) && voxel_index(wv[1], a.p.res, a.p.inv_res, kj) &&
-              voxel_index(wv[2], a.p.res, a.p.inv_res, kk))) {
-            atomicOr(&a.mc->err, ERR_KEYRANGE);
-            continue;
-        }
-        created += scratch_add(a, pack_key(ki, kj, kk), g, occ ? (1ull << 32) : 1ull);
-    }
+        for (int d = 16; d > 0; d >>= 1) nvmax = max(nvmax, __shfl_xor_sync(0xffffffffu, nvmax, d));
+        __syncwarp();
+        // ---- 2. free samples, EX_ILP x 32 consecutive samples per pass
+        {
+            int c[EX_ILP];
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
-        created += __shfl_xor_sync(0xffffffffu, created, d);
+            for (int j = 0; j < EX_ILP; ++j) c[j] = 0;
+            for (int base = 0; base < total_free; base += 32 * EX_ILP) {
+                bool ok[EX_ILP]; u64 key[EX_ILP];
+#pragma unroll
+                for (int j = 0; j < EX_ILP; ++j) {
+                    const int w = base + j * 32 + lane;
+                    ok[j] = false; key[j] = 0;
+                    if (w < total_free) {
+                        while (f_off[c[j] + 1] <= w) ++c[j];          // zero-size fans are skipped here
+                        const int rn = f_rn[c[j]];
+                        ok[j] = sample_key(a, s_T, rn & 0xffff, rn >> 16, w - f_off[c[j]], cb, sb, emitted, key[j]);
+                    }
+                }
+                commit_batch(a, ok, key, false, g, lane, wbuf, wn);
+            }
+        }
+        // ---- 3. occupied samples, range-bin-fastest
+        {
+            const int n_v = ncol > 0 ? 2 * nvmax + 1 : 0;
+            const int col_passes = (ncol + 31) / 32;
+            const int n_cells = n_v * col_passes;                   // one cell = (v slot, 32 columns)
+            for (int cell0 = 0; cell0 < n_cells; cell0 += EX_ILP) {
+                bool ok[EX_ILP]; u64 key[EX_ILP];
+#pragma unroll
+                for (int j = 0; j < EX_ILP; ++j) {
+                    const int cell = cell0 + j;
+                    ok[j] = false; key[j] = 0;
+                    if (cell < n_cells) {
+                        const int vs = cell / col_passes, cc = (cell - vs * col_passes) * 32 + lane;
+                        if (cc < ncol) {
+                            const int nv = o_nv[cc];
+                            const int v_step = vs - nvmax;            // fans are centred on the same slot
+                            if (v_step >= -nv && v_step <= nv)
+                                ok[j] = sample_key(a, s_T, o_r[cc], nv, v_step + nv, cb, sb, emitted, key[j]);
+                        }
+                    }
+                }
+                commit_batch(a, ok, key, true, g, lane, wbuf, wn);
+            }
+        }
     }
-    if ((threadIdx.x & 31) == 0) {
-        if (emitted) atomicAdd(&a.stats[g].n_samples, (u64)emitted);
-        if (created) atomicAdd(&a.cc->n_unique, (u32)created);
-    }
+    flush_created(a, wbuf, wn, lane);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
+    if (lane == 0 && emitted) atomicAdd(&a.stats[g].n_samples, (u64)emitted);
     // last block out: the gate.  The chunk may be applied only if the table keeps its load bound
     // even when every voxel of the chunk is new; otherwise the host grows the table and retries.
     __syncthreads();
@@ -332,8 +494,12 @@ k_expand(ExpandArgs a)
 __device__ __forceinline__ double apply_one(double L, double upd, bool adaptive, const DevParams &p)
 {
     if (adaptive && p.adaptive && upd > 0.0) {                  // :95
-        const double prob = 1.0 / (1.0 + exp(-L));              // :97
-        if (prob <= p.a_thr) upd *= (prob / p.a_thr) * p.a_ratio;   // :100-102
+        // :97 prob = 1/(1+exp(-L)).  Two cases need no exp: L == 0 gives exactly 0.5, and L well
+        // above logit(threshold) gives prob > threshold, i.e. no scaling at all.
+        if (!(L > p.l_skip)) {
+            const double prob = (L == 0.0) ? 0.5 : 1.0 / (1.0 + exp(-L));
+            if (prob <= p.a_thr) upd *= (prob / p.a_thr) * p.a_ratio;   // :100-102
+        }
     }
     L += upd;                                                   // :107
     L = fmin(fmax(L, p.lo_min), p.lo_max);                      // :110
@@ -398,15 +564,17 @@ __device__ __forceinline__ void acc_publish(LocalAcc &a, MapCtr *mc, bool add_co
     }
 }
 
-constexpr int AP_THREADS = 256;
-constexpr int AP_TILE = 2048;      // dedupe slots scanned per block iteration
+constexpr int AP_THREADS = 128;
 constexpr int SUMT = 64;           // entries of the sequential-sum tables
 
 // sum of n_free copies of lo_free followed by n_occ copies of lo_occ, added one by one as the
 // reference's `sum += log_odds` does (3d_mapper.py:546).  tab[0][n] / tab[1][n] hold the
-// running sums of n copies of lo_free / lo_occ; only counts >= SUMT or mixed voxels loop.
-__device__ __forceinline__ double seq_sum(u32 n_free, u32 n_occ, const double (*tab)[SUMT], const DevParams &p)
+// running sums of n copies of lo_free / lo_occ, tab[2][n] / tab[3][n] those sums divided by n;
+// only counts >= SUMT or mixed voxels take the loop.
+__device__ __forceinline__ double seq_avg(u32 n_free, u32 n_occ, const double (*tab)[SUMT], const DevParams &p)
 {
+    if (n_occ == 0 && n_free < SUMT) return tab[2][n_free];      // pure voxels: mean precomputed (sum/n)
+    if (n_free == 0 && n_occ < SUMT) return tab[3][n_occ];
     double sum;
     if (n_free < SUMT) sum = tab[0][n_free];
     else { sum = tab[0][SUMT - 1]; for (u32 q = SUMT - 1; q < n_free; ++q) sum += p.lo_free; }
@@ -414,99 +582,88 @@ __device__ __forceinline__ double seq_sum(u32 n_free, u32 n_occ, const double (*
         if (n_free == 0 && n_occ < SUMT) sum = tab[1][n_occ];
         else for (u32 q = 0; q < n_occ; ++q) sum += p.lo_occ;
     }
-    return sum;
+    return sum / (double)(n_occ + n_free);                       // :559
 }
 
-// One thread per voxel touched by the chunk.  A block scans a tile of the dedupe table,
-// compacts the live slots in shared memory, and then each thread consumes (and resets) one
-// entry, reads the voxel's table slot once, walks the chunk's frames in order -- for each frame
-// that touched the voxel: per-voxel mean of the sample deltas (3d_mapper.py:557-559), then
-// update_voxel (:562-567) -- and writes the slot back once.  Frames stay strictly ordered per
-// voxel, which is all the reference's sequential semantics require (voxels are independent).
+// One thread per voxel touched by the chunk (k_expand left a dense list of the dedupe entries
+// it created).  The thread consumes and resets its entry, reads the voxel's table slot once,
+// walks the chunk's frames in order -- for each frame that touched the voxel: per-voxel mean of
+// the sample deltas (3d_mapper.py:557-559), then update_voxel (:562-567) -- and writes the slot
+// back once.  Frames stay strictly ordered per voxel, which is all the reference's sequential
+// semantics require (voxels are independent of each other).
 __global__ void __launch_bounds__(AP_THREADS)
-k_apply_chunk(u64 *__restrict__ skeys, u64 *__restrict__ scnt, u64 n_slots, int g, ChunkCtr *cc, DevStats *st,
-              Slot *table, u64 tmask, DevParams p, const double *__restrict__ sum_tab, MapCtr *mc)
+k_apply_chunk(u64 *__restrict__ skeys, u64 *__restrict__ scnt, const u32 *__restrict__ slist, int g, ChunkCtr *cc,
+              DevStats *st, Slot *table, u64 tmask, DevParams p, const double *__restrict__ sum_tab, MapCtr *mc)
 {
     __shared__ u32 s_occ[GF], s_free[GF], s_new[GF];
-    __shared__ u32 s_list[AP_TILE];
-    __shared__ u32 s_n;
-    __shared__ double s_sum[2][SUMT];
+    __shared__ double s_sum[4][SUMT];
     __shared__ bool s_last;
-    if (__ldcg(&mc->abort)) return;
-    if (threadIdx.x < GF) { s_occ[threadIdx.x] = 0; s_free[threadIdx.x] = 0; s_new[threadIdx.x] = 0; }
-    if (threadIdx.x < 2 * SUMT) (&s_sum[0][0])[threadIdx.x] = sum_tab[threadIdx.x];
+    const u32 abort = __ldcg(&mc->abort);
+    const u32 n_live = __ldcg(&cc->n_unique);
+    if (abort) return;
+    const u32 i = blockIdx.x * AP_THREADS + threadIdx.x;
+    const bool live = i < n_live;
     const u32 lane = threadIdx.x & 31;
-    u32 w_occ = 0, w_free = 0, w_new = 0;      // lane f of each warp accumulates frame f
-    LocalAcc acc; acc_init(acc);
-    for (u64 tile = (u64)blockIdx.x * AP_TILE; tile < n_slots; tile += (u64)gridDim.x * AP_TILE) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_n = 0;
-        __syncthreads();
+    // entry -> registers; the loads are issued before anything waits on them
+    u64 key = 0; u32 s = 0;
+    ulonglong2 c2[GF / 2];
 #pragma unroll
-        for (int j = 0; j < AP_TILE / AP_THREADS; ++j) {
-            const u64 s = tile + (u64)j * AP_THREADS + threadIdx.x;
-            if (s < n_slots && __ldcs(&skeys[s]) != EMPTY_KEY) s_list[atomicAdd(&s_n, 1u)] = (u32)(s - tile);
+    for (int q = 0; q < GF / 2; ++q) c2[q] = make_ulonglong2(0ull, 0ull);
+    if (live) {
+        s = __ldcs(&slist[i]);
+        key = __ldcg(&skeys[s]);
+        const ulonglong2 *cp = reinterpret_cast<const ulonglong2 *>(scnt + (size_t)s * GF);
+#pragma unroll
+        for (int q = 0; q < GF / 2; ++q) c2[q] = __ldcg(cp + q);
+    }
+    if (threadIdx.x < GF) { s_occ[threadIdx.x] = 0; s_free[threadIdx.x] = 0; s_new[threadIdx.x] = 0; }
+    for (int q = threadIdx.x; q < 4 * SUMT; q += AP_THREADS) (&s_sum[0][0])[q] = sum_tab[q];
+    __syncthreads();
+    if (blockIdx.x * AP_THREADS < n_live) {             // block-uniform
+        u64 slot = ~0ull; bool fresh = false; double L = 0.0;
+        if (live) {
+            slot = table_find_or_insert(table, tmask, key, fresh, L);
+            if (slot == ~0ull) atomicOr(&mc->err, ERR_TABLEFULL);
+            skeys[s] = EMPTY_KEY;                                   // entry is ready for the next chunk
+            ulonglong2 *cp = reinterpret_cast<ulonglong2 *>(scnt + (size_t)s * GF);
+#pragma unroll
+            for (int q = 0; q < GF / 2; ++q) cp[q] = make_ulonglong2(0ull, 0ull);
         }
-        __syncthreads();
-        const u32 n_live = s_n;
-        for (u32 base = 0; base < n_live; base += AP_THREADS) {     // block-uniform trip count
-            const u32 i = base + threadIdx.x;
-            const bool live = i < n_live;
-            u64 key = 0, slot = ~0ull; bool fresh = false; double L = 0.0;
-            ulonglong2 c2[GF / 2];
+        u32 w_occ = 0, w_free = 0, w_new = 0;          // lane f of each warp accumulates frame f
+        bool pending_new = fresh;
 #pragma unroll
-            for (int q = 0; q < GF / 2; ++q) c2[q] = make_ulonglong2(0ull, 0ull);
-            if (live) {
-                const u64 s = tile + s_list[i];
-                key = skeys[s];
-                ulonglong2 *cp = reinterpret_cast<ulonglong2 *>(scnt + s * GF);
-#pragma unroll
-                for (int q = 0; q < GF / 2; ++q) c2[q] = __ldcs(cp + q);
-                skeys[s] = EMPTY_KEY;                               // ready for the next chunk
-#pragma unroll
-                for (int q = 0; q < GF / 2; ++q) cp[q] = make_ulonglong2(0ull, 0ull);
-                slot = table_find_or_insert(table, tmask, key, fresh, L);
-                if (slot == ~0ull) atomicOr(&mc->err, ERR_TABLEFULL);
-            }
-            bool pending_new = fresh;
-#pragma unroll
-            for (int f = 0; f < GF; ++f) {
-                if (f < g) {                                        // uniform
-                    const u64 c = (f & 1) ? c2[f >> 1].y : c2[f >> 1].x;
-                    const bool hit = c != 0ull;
-                    const u32 n_occ = (u32)(c >> 32), n_free = (u32)(c & 0xffffffffu);
-                    const bool occ_typed = n_occ > 0;               // occupied has priority (:544-545)
-                    if (hit) {
-                        const double avg = seq_sum(n_free, n_occ, s_sum, p) / (double)(n_occ + n_free);   // :559
-                        L = apply_one(L, avg, occ_typed, p);
-                    }
-                    const u32 b_occ = __ballot_sync(0xffffffffu, hit && occ_typed);
-                    const u32 b_free = __ballot_sync(0xffffffffu, hit && !occ_typed);
-                    const u32 b_new = __ballot_sync(0xffffffffu, hit && pending_new);
-                    if (hit) pending_new = false;
-                    if (lane == (u32)f) { w_occ += __popc(b_occ); w_free += __popc(b_free); w_new += __popc(b_new); }
-                }
-            }
-            if (live && slot != ~0ull) {
-                table[slot].val = L;
-                if (fresh) ++acc.n_new;
-                acc_key(acc, key);
+        for (int f = 0; f < GF; ++f) {
+            if (f < g) {                                            // uniform
+                const u64 c = (f & 1) ? c2[f >> 1].y : c2[f >> 1].x;
+                const bool hit = c != 0ull;
+                const u32 n_occ = (u32)(c >> 32), n_free = (u32)(c & 0xffffffffu);
+                const bool occ_typed = n_occ > 0;                   // occupied has priority (:544-545)
+                if (hit) L = apply_one(L, seq_avg(n_free, n_occ, s_sum, p), occ_typed, p);
+                const u32 b_occ = __ballot_sync(0xffffffffu, hit && occ_typed);
+                const u32 b_free = __ballot_sync(0xffffffffu, hit && !occ_typed);
+                const u32 b_new = __ballot_sync(0xffffffffu, hit && pending_new);
+                if (hit) pending_new = false;
+                if (lane == (u32)f) { w_occ = __popc(b_occ); w_free = __popc(b_free); w_new = __popc(b_new); }
             }
         }
-    }
-    acc_publish(acc, mc, false);
-    __syncthreads();
-    if (lane < GF) {
-        if (w_occ) atomicAdd(&s_occ[lane], w_occ);
-        if (w_free) atomicAdd(&s_free[lane], w_free);
-        if (w_new) atomicAdd(&s_new[lane], w_new);
-    }
-    __syncthreads();
-    if (threadIdx.x < g) {
-        const int f = threadIdx.x;
-        if (s_occ[f]) atomicAdd(&st[f].n_occ, (u64)s_occ[f]);
-        if (s_free[f]) atomicAdd(&st[f].n_free, (u64)s_free[f]);
-        if (s_new[f]) atomicAdd(&cc->neu[f], s_new[f]);
+        LocalAcc acc; acc_init(acc);
+        if (live && slot != ~0ull) {
+            table[slot].val = L;
+            acc_key(acc, key);
+        }
+        acc_publish(acc, mc, false);
+        if (lane < GF) {
+            if (w_occ) atomicAdd(&s_occ[lane], w_occ);
+            if (w_free) atomicAdd(&s_free[lane], w_free);
+            if (w_new) atomicAdd(&s_new[lane], w_new);
+        }
+        __syncthreads();
+        if (threadIdx.x < g) {
+            const int f = threadIdx.x;
+            if (s_occ[f]) atomicAdd(&st[f].n_occ, (u64)s_occ[f]);
+            if (s_free[f]) atomicAdd(&st[f].n_free, (u64)s_free[f]);
+            if (s_new[f]) atomicAdd(&cc->neu[f], s_new[f]);
+        }
     }
     // last block out: len(voxels) after each frame (:592), publish the new count, re-arm the chunk
     __syncthreads();
@@ -525,7 +682,7 @@ k_apply_chunk(u64 *__restrict__ skeys, u64 *__restrict__ scnt, u64 n_slots, int 
             cc->neu[f] = 0;
         }
         mc->last_new = (u32)(run - cc->count0);
-        mc->last_unique = atomicAdd(&cc->n_unique, 0u);
+        mc->last_unique = n_live;
         atomicExch(&mc->count, run);
         cc->n_unique = 0; cc->ticket = 0;
     }
@@ -756,8 +913,12 @@ struct s3d_map {
     DevBuf<short> d_col_to_beam;
     u64 samples_max = 0;             // worst-case samples per frame for these tables
     // chunk working set
-    DevBuf<u64> skeys, scnt; u64 scratch_cap = 0;
-    DevBuf<double> sum_tab;          // [2][SUMT] running sums of n copies of lo_free / lo_occ
+    // chunk dedupe table: one allocation {counters[C][GF], keys[C], list[C]} so that a single L2
+    // access-policy window can keep it resident between the kernels of a chunk
+    DevBuf<uint8_t> spool; u64 scratch_cap = 0;
+    u64 *skeys = nullptr, *scnt = nullptr; u32 *slist = nullptr;
+    size_t l2_persist_max = 0, l2_window_max = 0, l2_window = 0;
+    DevBuf<double> sum_tab;          // [4][SUMT] running sums of n copies of lo_free / lo_occ, and their means
     DevBuf<int> first_hit;
     ChunkCtr *cc = nullptr;
     DevBuf<DevStats> stats; DevStats *stats_host = nullptr; size_t stats_host_n = 0;
@@ -888,15 +1049,34 @@ int ensure_scratch(s3d_map *m, u64 want_cap, bool wipe)
     if (want_cap > (1ull << 31)) return fail(S3D_ENOMEM, "chunk dedupe table would exceed 2^31 entries");
     const bool realloc = want_cap > m->scratch_cap;
     if (realloc) {
-        int rc = m->skeys.ensure((size_t)want_cap); if (rc) return rc;
-        rc = m->scnt.ensure((size_t)want_cap * GF); if (rc) return rc;
+        const size_t cnt_bytes = sizeof(u64) * (size_t)want_cap * GF, key_bytes = sizeof(u64) * (size_t)want_cap;
+        const size_t pool = cnt_bytes + key_bytes + sizeof(u32) * (size_t)want_cap;
+        int rc = m->spool.ensure(pool); if (rc) return rc;
+        m->scnt = reinterpret_cast<u64 *>(m->spool.p);
+        m->skeys = reinterpret_cast<u64 *>(m->spool.p + cnt_bytes);
+        m->slist = reinterpret_cast<u32 *>(m->spool.p + cnt_bytes + key_bytes);
         m->scratch_cap = want_cap;
+        // The dedupe table is hit by every sample of a chunk and re-read by the apply kernel:
+        // ask L2 to keep it (persisting window) while images and voxel-table traffic stream by.
+        if (m->l2_persist_max > 0 && m->l2_window_max > 0) {
+            const size_t win = std::min(pool, m->l2_window_max);
+            const size_t carve = std::min(win, m->l2_persist_max);
+            CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+            cudaStreamAttrValue av{};
+            av.accessPolicyWindow.base_ptr = m->spool.p;
+            av.accessPolicyWindow.num_bytes = win;
+            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)win);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            CU(cudaStreamSetAttribute(m->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+            m->l2_window = win;
+        }
     }
     if (realloc || wipe) {
         const int blocks = (int)std::min<u64>((m->scratch_cap + 255) / 256, (u64)m->n_sm * 16);
-        k_fill_u64<<<blocks, 256, 0, m->stream>>>(m->skeys.p, m->scratch_cap, EMPTY_KEY);
+        k_fill_u64<<<blocks, 256, 0, m->stream>>>(m->skeys, m->scratch_cap, EMPTY_KEY);
         CU(cudaGetLastError());
-        CU(cudaMemsetAsync(m->scnt.p, 0, sizeof(u64) * (size_t)m->scratch_cap * GF, m->stream));
+        CU(cudaMemsetAsync(m->scnt, 0, sizeof(u64) * (size_t)m->scratch_cap * GF, m->stream));
     }
     return 0;
 }
@@ -907,8 +1087,8 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     const size_t img_stride = (size_t)tab.H * tab.W;
     const uint8_t *imgs = j.imgs + (size_t)base * img_stride;
     const bool vec16 = (tab.W % 16 == 0) && ((uintptr_t)imgs % 16 == 0) && (img_stride % 16 == 0);
-    const int max_c = (tab.H + tab.free_step - 1) / tab.free_step + tab.occ_window;
-    const size_t ex_smem = sizeof(int) * (size_t)(3 * max_c + 1);
+    const int max_f = (tab.H + tab.free_step - 1) / tab.free_step;
+    const size_t ex_smem = sizeof(int) * (size_t)EX_BEAMS * (size_t)(2 * max_f + 1 + 2 * tab.occ_window);
     const size_t fh_smem = sizeof(int) * (size_t)tab.n_beams;
     const size_t e0 = m->prof_on ? prof_mark(m) : 0;
     CU(cudaMemsetAsync(m->first_hit.p, 0x7f, sizeof(int) * (size_t)g * tab.n_beams, m->stream));
@@ -921,13 +1101,15 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     a.T = j.T + base * 16;
     a.tab = tab; a.p = m->p;
     a.first_hit = m->first_hit.p;
-    a.skeys = m->skeys.p; a.scnt = m->scnt.p; a.smask = (u32)(m->scratch_cap - 1);
+    a.skeys = m->skeys; a.scnt = m->scnt; a.smask = (u32)(m->scratch_cap - 1); a.slist = m->slist;
     a.cc = m->cc; a.stats = j.stats + base; a.mc = m->mc;
     a.seq = m->chunk_seq; a.table_limit = table_limit(m);
-    k_expand<<<dim3(tab.n_beams, g), EX_THREADS, ex_smem, m->stream>>>(a);
+    { const char *e = getenv("S3D_DEBUG_STAGE"); a.dbg = e ? atoi(e) : 0; }
+    k_expand<<<dim3((tab.n_beams + EX_BEAMS - 1) / EX_BEAMS, g), EX_THREADS, ex_smem, m->stream>>>(a);
     const size_t e2 = m->prof_on ? prof_mark(m) : 0;
-    const int ap_blocks = (int)std::min<u64>((m->scratch_cap + AP_TILE - 1) / AP_TILE, (u64)m->n_sm * 8);
-    k_apply_chunk<<<ap_blocks, AP_THREADS, 0, m->stream>>>(m->skeys.p, m->scnt.p, m->scratch_cap, g, m->cc,
+    // one thread per dedupe entry the chunk can have created; blocks past the live count exit at once
+    const int ap_blocks = (int)((m->scratch_cap + AP_THREADS - 1) / AP_THREADS);
+    k_apply_chunk<<<ap_blocks, AP_THREADS, 0, m->stream>>>(m->skeys, m->scnt, m->slist, g, m->cc,
                                                           j.stats + base, m->table, m->cap - 1, m->p,
                                                           m->sum_tab.p, m->mc);
     CU(cudaGetLastError());
@@ -1116,6 +1298,8 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     m->n_sm = prop.multiProcessorCount;
+    m->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    m->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&m->mc, sizeof(MapCtr)));
     CU(cudaMallocHost(&m->mc_host, sizeof(MapCtr)));
@@ -1152,7 +1336,7 @@ int s3d_destroy(s3d_map *m)
     if (m->stats_host) cudaFreeHost(m->stats_host);
     m->d_beam_col.release(); m->d_nv_free.release(); m->d_nv_occ.release();
     m->d_cos_b.release(); m->d_sin_b.release(); m->d_range.release(); m->d_cos_va.release(); m->d_sin_va.release();
-    m->d_col_to_beam.release(); m->skeys.release(); m->scnt.release(); m->sum_tab.release(); m->first_hit.release(); m->stats.release();
+    m->d_col_to_beam.release(); m->spool.release(); m->sum_tab.release(); m->first_hit.release(); m->stats.release();
     m->img_dev.release(); m->T_dev.release(); m->io_keys.release(); m->io_vals.release(); m->io_flags.release();
     m->ex_xyz.release(); m->ex_prob.release(); m->ex_L.release(); m->ex_cls.release(); m->ex_ijk.release(); m->ex_f32.release();
     for (cudaEvent_t e : m->ev_pool) cudaEventDestroy(e);
@@ -1172,15 +1356,20 @@ int s3d_set_params(s3d_map *m, const s3d_params *q)
     p.a_thr = q->adaptive_threshold; p.a_ratio = q->adaptive_max_ratio;
     p.zmin = q->z_filter_min;
     p.adaptive = q->adaptive_update; p.zfilter = q->z_filter_enabled;
+    p.l_skip = (p.a_thr > 1e-3 && p.a_thr < 1.0 - 1e-3) ? std::log(p.a_thr / (1.0 - p.a_thr)) + 1e-6
+                                                         : std::numeric_limits<double>::infinity();
     p.thr = std::max(-1, std::min(255, q->intensity_threshold));
     {
         // running sums, one addition at a time, exactly as `sum += log_odds` accumulates them
         int rc = set_device(m); if (rc) return rc;
         if ((rc = pump(m, true))) return rc;
-        double tab[2][SUMT];
-        tab[0][0] = tab[1][0] = 0.0;
-        for (int n = 1; n < SUMT; ++n) { tab[0][n] = tab[0][n - 1] + p.lo_free; tab[1][n] = tab[1][n - 1] + p.lo_occ; }
-        if ((rc = upload(m->sum_tab, &tab[0][0], (size_t)2 * SUMT, m->stream))) return rc;
+        double tab[4][SUMT];
+        tab[0][0] = tab[1][0] = tab[2][0] = tab[3][0] = 0.0;
+        for (int n = 1; n < SUMT; ++n) {
+            tab[0][n] = tab[0][n - 1] + p.lo_free; tab[1][n] = tab[1][n - 1] + p.lo_occ;
+            tab[2][n] = tab[0][n] / (double)n; tab[3][n] = tab[1][n] / (double)n;
+        }
+        if ((rc = upload(m->sum_tab, &tab[0][0], (size_t)4 * SUMT, m->stream))) return rc;
         CU(cudaStreamSynchronize(m->stream));
     }
     m->have_params = true;
@@ -1194,7 +1383,7 @@ int s3d_set_tables(s3d_map *m, const s3d_tables *t)
     if (t->H < 0 || t->W < 0 || t->n_beams < 0 || t->n_beams > t->W || t->nv_max < 0)
         return fail(S3D_EINVAL, "bad table shape");
     if (t->free_step < 1 || t->occ_window < 0) return fail(S3D_EINVAL, "bad free_step/occ_window");
-    if (t->H >= (1 << 30)) return fail(S3D_EINVAL, "H too large");
+    if (t->H >= (1 << 16) || t->nv_max >= (1 << 15)) return fail(S3D_EINVAL, "H or nv_max too large");
     int rc = set_device(m); if (rc) return rc;
     if ((rc = sync_counters(m))) return rc;
     const size_t nb = (size_t)t->n_beams, H = (size_t)t->H;
