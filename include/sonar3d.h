@@ -170,6 +170,32 @@ int s3d_export_read(s3d_map *map, double *xyz, double *prob, int8_t *cls, int32_
  * x, y, z, intensity=probability, 16-byte stride (scripts/3d_mapper_node.py:419-443). */
 int s3d_export_read_xyzi32(s3d_map *map, float *xyzi, uint64_t n);
 
+/* ---- sharded map (one process per GPU) ---------------------------------- */
+
+/* The map shards by a hash of the voxel key: owner = (mix64(packed key) >> 40) % world.  Each
+ * rank expands its slice of the processed beams of every frame, the per-(voxel, frame) integer
+ * counts travel to the owning rank by all-to-all (the caller moves the bytes, e.g. with NCCL
+ * through torch.distributed), and the owner merges and applies them.  Integer merges make the
+ * N-rank result identical to the 1-rank result.  A record is 17 uint64: the packed key and the
+ * (n_occ << 32 | n_free) counter of each of the up-to-16 frames of the chunk. */
+#define S3D_RECORD_WORDS 17
+#define S3D_CHUNK_FRAMES 16
+
+int s3d_shard_config(s3d_map *map, int rank, int world);
+/* owner rank of each key (host helper; same function the device uses) */
+int s3d_shard_owner(const int32_t *ijk, int64_t n, int world, int32_t *owner);
+/* Expand g <= 16 frames (device-resident images / transforms) on this rank's beam slice and
+ * pack the dedupe entries by owner.  *records_dev points at world runs of records laid out
+ * back to back (valid until the next shard call); counts[o] is the length of run o.
+ * stats_dev[g] receives this rank's num_samples.  Synchronous. */
+int s3d_shard_expand(s3d_map *map, const uint8_t *images_dev, const double *T_dev, int g,
+                     s3d_frame_stats *stats_dev, const void **records_dev, uint64_t *counts);
+/* Merge n_records received records (device memory) and apply the chunk's g frames in order to
+ * this rank's shard; stats_dev[g] receives the shard's num_occupied / num_free / num_voxels
+ * (sum over ranks = the reference's counters).  Synchronous. */
+int s3d_shard_apply(s3d_map *map, const void *records_dev, uint64_t n_records, int g,
+                    s3d_frame_stats *stats_dev);
+
 /* ---- measurement (bench.py) ----------------------------------------------------------------- */
 
 #define S3D_K_FIRST_HIT 0

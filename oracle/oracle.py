@@ -69,6 +69,7 @@ def lib():
         L.so_expand_frame.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, dp, dp, ip8, C.c_int64]
         L.so_bearing_table.argtypes = [C.c_void_p, dp]
         L.so_bearing_count.argtypes = [C.c_void_p]
+        L.so_set_beam_slice.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.so_sonar_to_base.argtypes = [C.c_void_p, dp]
         L.so_set_octree_params.argtypes = [C.c_void_p] + [C.c_double] * 4 + [C.c_int] + [C.c_double] * 2
         L.so_update_voxel.argtypes = [C.c_void_p, dp, C.c_double, C.c_int]
@@ -197,6 +198,10 @@ class OracleMapper:
         occ = np.empty(n, dtype=np.int8)
         lib().so_expand_frame(self._h, u8, H, W, _dptr(T), _dptr(xyz), occ.ctypes.data_as(C.POINTER(C.c_int8)), n)
         return xyz, occ
+
+    def set_beam_slice(self, lo: int, hi: int):
+        """Expand only processed beams [lo, hi) (not in the reference; used to test the sharded path)."""
+        lib().so_set_beam_slice(self._h, int(lo), int(hi))
 
     def world_to_key(self, xyz) -> np.ndarray:
         xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)

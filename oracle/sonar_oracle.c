@@ -254,6 +254,7 @@ typedef struct so_map {
     double *bearing; int32_t n_bearing;
     so_octree oct;
     int64_t frame_count, processed_frame_count;
+    int32_t beam_lo, beam_hi; /* processed-beam index range to expand (tests of the sharded path); default all */
     /* per-frame scratch */
     so_sample *samples; int64_t n_samples, cap_samples;
     so_dict fr;          /* key -> running sum (val) */
@@ -344,6 +345,7 @@ SO_API so_map *so_create(const so_config *cfg)
     o->adaptive_max_ratio = cfg->adaptive_max_ratio;
     so_dict_init(&o->voxels);
     for (int a = 0; a < 3; ++a) { o->min_bounds[a] = INFINITY; o->max_bounds[a] = -INFINITY; }
+    m->beam_lo = 0; m->beam_hi = INT32_MAX;
     m->n_bearing = cfg->image_width;
     m->bearing = malloc(sizeof(double) * (size_t)(m->n_bearing > 0 ? m->n_bearing : 1));
     so_linspace(-m->horizontal_fov / 2, m->horizontal_fov / 2, m->n_bearing, m->bearing); /* :295 */
@@ -446,6 +448,7 @@ static int so_expand(so_map *m, const uint8_t *img, int H, int W, const double *
     int nb = 0;
     for (int b = 0; b < W; b += step, ++nb) {            /* :530 */
         double ang = m->bearing[b];
+        if (nb < m->beam_lo || nb >= m->beam_hi) continue;   /* not in the reference: beam slicing for shard tests */
         if (fabs(ang) > m->horizontal_fov / 2) {         /* :382-385, :534 */
             if (first_hits) first_hits[nb] = -2;
             continue;
@@ -527,6 +530,7 @@ SO_API int64_t so_expand_frame(so_map *m, const uint8_t *img, int H, int W, cons
     return m->n_samples;
 }
 
+SO_API void so_set_beam_slice(so_map *m, int lo, int hi) { m->beam_lo = lo; m->beam_hi = hi; }
 SO_API int so_bearing_count(so_map *m) { return m->n_bearing; }
 SO_API void so_bearing_table(so_map *m, double *out) { memcpy(out, m->bearing, sizeof(double) * m->n_bearing); }
 SO_API void so_sonar_to_base(so_map *m, double *out) { memcpy(out, m->T_sonar_to_base, sizeof(double) * 16); }

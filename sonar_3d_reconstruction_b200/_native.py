@@ -18,6 +18,7 @@ SYMBOLS = (
     "s3d_apply_updates", "s3d_query", "s3d_count", "s3d_dump", "s3d_load", "s3d_clear", "s3d_bounds",
     "s3d_capacity", "s3d_export_begin", "s3d_export_read", "s3d_export_read_xyzi32",
     "s3d_profile_enable", "s3d_profile_read",
+    "s3d_shard_config", "s3d_shard_owner", "s3d_shard_expand", "s3d_shard_apply",
 )
 
 
@@ -99,10 +100,22 @@ def load_library():
     L.s3d_export_read_xyzi32.argtypes = [vp, C.POINTER(C.c_float), C.c_uint64]
     L.s3d_profile_enable.argtypes = [vp, C.c_int]
     L.s3d_profile_read.argtypes = [vp, C.POINTER(Profile)]
+    L.s3d_shard_config.argtypes = [vp, C.c_int, C.c_int]
+    L.s3d_shard_owner.argtypes = [i32p, C.c_int64, C.c_int, i32p]
+    L.s3d_shard_expand.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(vp), u64p]
+    L.s3d_shard_apply.argtypes = [vp, vp, C.c_uint64, C.c_int, vp]
     for name in SYMBOLS:
         getattr(L, name)          # AttributeError here = header / library mismatch
     _lib = L
     return L
+
+
+def shard_owner(ijk: np.ndarray, world: int) -> np.ndarray:
+    """Owner rank of each voxel key, evaluated by the library's host helper."""
+    ijk = np.ascontiguousarray(ijk, dtype=np.int32).reshape(-1, 3)
+    out = np.empty(len(ijk), dtype=np.int32)
+    _check(load_library().s3d_shard_owner(_ptr(ijk, C.c_int32), len(ijk), int(world), _ptr(out, C.c_int32)))
+    return out
 
 
 def _check(rc: int):
@@ -187,6 +200,24 @@ class NativeMap:
     @property
     def capacity(self) -> int:
         return int(self._lib.s3d_capacity(self._h))
+
+    # -- sharded map --------------------------------------------------------------------
+    RECORD_WORDS = 17
+    CHUNK_FRAMES = 16
+
+    def shard_config(self, rank: int, world: int):
+        _check(self._lib.s3d_shard_config(self._h, int(rank), int(world)))
+        self._world = int(world)
+
+    def shard_expand(self, images_ptr: int, T_ptr: int, g: int, stats_dev_ptr: int):
+        """-> (device pointer of the packed records, [count per owner])"""
+        rec = C.c_void_p()
+        counts = (C.c_uint64 * 64)()
+        _check(self._lib.s3d_shard_expand(self._h, images_ptr, T_ptr, int(g), stats_dev_ptr, C.byref(rec), counts))
+        return int(rec.value or 0), [int(counts[o]) for o in range(self._world)]
+
+    def shard_apply(self, records_ptr: int, n_records: int, g: int, stats_dev_ptr: int):
+        _check(self._lib.s3d_shard_apply(self._h, records_ptr or None, int(n_records), int(g), stats_dev_ptr))
 
     # -- measurement --------------------------------------------------------------------
     def profile_enable(self, on: bool = True):

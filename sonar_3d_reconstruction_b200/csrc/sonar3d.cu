@@ -199,6 +199,7 @@ struct ExpandArgs {
     ChunkCtr *cc;
     DevStats *stats;             // [g]
     MapCtr *mc;
+    int beam_lo, beam_hi;        // processed beams [beam_lo, beam_hi) are expanded (a rank's slice when sharded)
     int dbg;                     // S3D_DEBUG_STAGE (timing experiments only): 1 = no dedupe, 2 = probe only
     u64 seq;                     // chunk sequence number (for abort bookkeeping)
     u64 table_limit;             // gate: count + unique(chunk) must stay <= this
@@ -214,6 +215,11 @@ __device__ __forceinline__ void raise_abort(MapCtr *mc, u32 why, u64 seq)
 // already loaded from the home slot.  Returns the slot if this call created the entry, else ~0.
 __device__ __forceinline__ u32 scratch_resolve(const ExpandArgs &a, u64 key, u32 slot, u64 cur, int lane, u64 inc)
 {
+    if (a.dbg == 3) {      // timing experiment: reductions only, no key check
+        u32 *half = reinterpret_cast<u32 *>(&a.scnt[(size_t)slot * GF + lane]);
+        if (inc >> 32) atomicAdd(half + 1, (u32)(inc >> 32)); else atomicAdd(half, (u32)inc);
+        return ~0u;
+    }
     for (u32 probe = 0; probe < SCRATCH_PROBE_LIMIT; ++probe) {
         bool created = false;
         if (cur == EMPTY_KEY) {
@@ -223,6 +229,7 @@ __device__ __forceinline__ u32 scratch_resolve(const ExpandArgs &a, u64 key, u32
         if (cur == key) {
             // the counter lane is {n_free: low 32 bits, n_occ: high 32 bits}; bump the half that applies
             u32 *half = reinterpret_cast<u32 *>(&a.scnt[(size_t)slot * GF + lane]);
+            if (a.dbg == 4) return created ? slot : ~0u;       // timing experiment: keys only, no reductions
             if (inc >> 32) atomicAdd(half + 1, (u32)(inc >> 32)); else atomicAdd(half, (u32)inc);
             return created ? slot : ~0u;
         }
@@ -375,9 +382,9 @@ k_expand(ExpandArgs a)
     int *f_rn = f_off + (max_f + 1);           // [max_f] r | nv << 16 of free candidate c
     int *o_r = f_rn + max_f;                   // [occ_window] range bin of occupied column
     int *o_nv = o_r + tab.occ_window;          // [occ_window] its fan half-width
-    const int beam = blockIdx.x * EX_BEAMS + warp;
+    const int beam = a.beam_lo + blockIdx.x * EX_BEAMS + warp;
     int emitted = 0;
-    if (beam < tab.n_beams) {
+    if (beam < a.beam_hi) {
         const int col = tab.beam_col[beam];
         const double cb = tab.cos_b[beam], sb = tab.sin_b[beam];
         int fh = a.first_hit[g * tab.n_beams + beam];
@@ -421,6 +428,7 @@ k_expand(ExpandArgs a)
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) nvmax = max(nvmax, __shfl_xor_sync(0xffffffffu, nvmax, d));
         __syncwarp();
+        if (a.dbg == 5) total_free = ncol = 0;                     // timing experiment: listing only
         // ---- 2. free samples, EX_ILP x 32 consecutive samples per pass
         {
             int c[EX_ILP];
@@ -688,6 +696,84 @@ k_apply_chunk(u64 *__restrict__ skeys, u64 *__restrict__ scnt, const u32 *__rest
     }
 }
 
+// ------------------------------------------------------------------------------ sharded map
+// The map shards by a hash of the voxel key: owner = (mix64(key) >> 40) % world.  A rank expands
+// its slice of the beams into its local dedupe table, drains the table into per-owner runs of
+// 17-word records {key, counter lane of each of the 16 frames}, the runs travel by all-to-all,
+// and the owner merges what it receives (integer adds, so the result does not depend on how the
+// beams were split) before the ordinary apply kernel runs on its shard of the table.
+constexpr int REC_WORDS = 1 + GF;
+
+__device__ __forceinline__ u32 key_owner(u64 key, u32 world) { return (u32)((mix64(key) >> 40) % world); }
+
+// pass 1: how many of the chunk's dedupe entries go to each owner
+__global__ void k_shard_count(const u64 *__restrict__ skeys, const u32 *__restrict__ slist, const ChunkCtr *cc,
+                              u32 world, u32 *owner_count)
+{
+    __shared__ u32 s_cnt[64];
+    if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 n = cc->n_unique;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&s_cnt[key_owner(skeys[slist[i]], world)], 1u);
+    __syncthreads();
+    if (threadIdx.x < world && s_cnt[threadIdx.x]) atomicAdd(&owner_count[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+// pass 2: drain the dedupe table into the send buffer, records grouped by owner.
+// owner_base[o] = first record of owner o (exclusive prefix of the counts), owner_fill[o] = cursor.
+__global__ void k_shard_pack(u64 *__restrict__ skeys, u64 *__restrict__ scnt, const u32 *__restrict__ slist,
+                             ChunkCtr *cc, u32 world, const u32 *__restrict__ owner_base, u32 *owner_fill,
+                             u64 *__restrict__ send)
+{
+    const u32 n = cc->n_unique;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u32 s = slist[i];
+        const u64 key = skeys[s];
+        const u32 o = key_owner(key, world);
+        const u32 dst = owner_base[o] + atomicAdd(&owner_fill[o], 1u);
+        u64 *rec = send + (size_t)dst * REC_WORDS;
+        rec[0] = key;
+        u64 *cp = scnt + (size_t)s * GF;
+#pragma unroll
+        for (int f = 0; f < GF; ++f) { rec[1 + f] = cp[f]; cp[f] = 0ull; }
+        skeys[s] = EMPTY_KEY;
+    }
+}
+
+__global__ void k_shard_reset_cc(ChunkCtr *cc) { cc->n_unique = 0; cc->ticket = 0; }
+
+// owner side: merge received records into the (empty) dedupe table
+__global__ void k_shard_merge(const u64 *__restrict__ recv, u64 n_rec, u64 *skeys, u64 *scnt, u32 *slist, u32 smask,
+                              ChunkCtr *cc, MapCtr *mc)
+{
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n_rec; i += (u64)gridDim.x * blockDim.x) {
+        const u64 *rec = recv + i * REC_WORDS;
+        const u64 key = rec[0];
+        u32 slot = mix32(key) & smask;
+        bool done = false;
+        for (u32 probe = 0; probe <= smask && !done; ++probe) {
+            u64 cur = __ldcg(&skeys[slot]);
+            bool created = false;
+            if (cur == EMPTY_KEY) {
+                cur = atomicCAS(&skeys[slot], EMPTY_KEY, key);
+                if (cur == EMPTY_KEY) { cur = key; created = true; }
+            }
+            if (cur == key) {
+                if (created) slist[atomicAdd(&cc->n_unique, 1u) & smask] = slot;
+#pragma unroll
+                for (int f = 0; f < GF; ++f)
+                    if (rec[1 + f]) atomicAdd(&scnt[(size_t)slot * GF + f], rec[1 + f]);
+                done = true;
+            }
+            slot = (slot + 1) & smask;
+        }
+        if (!done) atomicOr(&mc->err, ERR_TABLEFULL);
+    }
+}
+
+__global__ void k_shard_count0(ChunkCtr *cc, const MapCtr *mc) { cc->count0 = mc->count; }
+
 // ------------------------------------------------------------------------------ store kernels
 __global__ void k_fill_slots(Slot *t, u64 n)
 {
@@ -904,6 +990,11 @@ struct s3d_map {
     u64 snap_floor = 0;              // snapshots older than this predate the last exact sync
     std::deque<Job> jobs; u64 job_seq = 0;
     u64 n_retries = 0, n_grows = 0;
+    // sharded map (multi-GPU): this rank's identity and beam slice, exchange staging
+    int shard_rank = 0, shard_world = 1, beam_lo = 0, beam_hi = -1;
+    DevBuf<u64> send_buf; DevBuf<u32> owner_ctr;      // owner_ctr: [3][64] count / base / fill
+    u32 *owner_host = nullptr;                        // pinned [64]
+    int dbg_stage = 0;               // S3D_DEBUG_STAGE: stage-ablation timing experiments (tools/dbg_stage.sh)
     // params / tables
     bool have_params = false, have_tables = false;
     DevParams p{};
@@ -1104,7 +1195,8 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     a.skeys = m->skeys; a.scnt = m->scnt; a.smask = (u32)(m->scratch_cap - 1); a.slist = m->slist;
     a.cc = m->cc; a.stats = j.stats + base; a.mc = m->mc;
     a.seq = m->chunk_seq; a.table_limit = table_limit(m);
-    { const char *e = getenv("S3D_DEBUG_STAGE"); a.dbg = e ? atoi(e) : 0; }
+    a.dbg = m->dbg_stage;
+    a.beam_lo = 0; a.beam_hi = tab.n_beams;
     k_expand<<<dim3((tab.n_beams + EX_BEAMS - 1) / EX_BEAMS, g), EX_THREADS, ex_smem, m->stream>>>(a);
     const size_t e2 = m->prof_on ? prof_mark(m) : 0;
     // one thread per dedupe entry the chunk can have created; blocks past the live count exit at once
@@ -1298,6 +1390,7 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     m->n_sm = prop.multiProcessorCount;
+    { const char *e = getenv("S3D_DEBUG_STAGE"); m->dbg_stage = e ? atoi(e) : 0; }
     m->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     m->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
@@ -1329,6 +1422,8 @@ int s3d_destroy(s3d_map *m)
     if (m->snap_host) cudaFreeHost(m->snap_host);
     for (int i = 0; i < s3d_map::RING; ++i) if (m->snap_ev[i]) cudaEventDestroy(m->snap_ev[i]);
     if (m->cc) cudaFree(m->cc);
+    if (m->owner_host) cudaFreeHost(m->owner_host);
+    m->send_buf.release(); m->owner_ctr.release();
     for (cudaEvent_t e : m->copy_ev) cudaEventDestroy(e);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->ex_counts) cudaFree(m->ex_counts);
@@ -1490,6 +1585,123 @@ int s3d_ingest_batch(s3d_map *m, const uint8_t *images, int64_t n, const double 
 int s3d_ingest(s3d_map *m, const uint8_t *image, const double T[16], s3d_frame_stats *out)
 {
     return s3d_ingest_batch(m, image, 1, T, out);
+}
+
+int s3d_shard_config(s3d_map *m, int rank, int world)
+{
+    if (!m) return fail(S3D_EINVAL, "null map");
+    if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(S3D_EINVAL, "bad rank/world");
+    int rc = set_device(m); if (rc) return rc;
+    if ((rc = sync_counters(m))) return rc;
+    m->shard_rank = rank; m->shard_world = world;
+    if (!m->owner_host) CU(cudaMallocHost(&m->owner_host, sizeof(u32) * 64));
+    return m->owner_ctr.ensure(3 * 64);
+}
+
+int s3d_shard_owner(const int32_t *ijk, int64_t n, int world, int32_t *owner)
+{
+    if (world < 1) return fail(S3D_EINVAL, "world < 1");
+    for (int64_t i = 0; i < n; ++i)
+        owner[i] = (int32_t)((mix64(pack_key(ijk[3 * i], ijk[3 * i + 1], ijk[3 * i + 2])) >> 40) % (u64)world);
+    return 0;
+}
+
+int s3d_shard_expand(s3d_map *m, const uint8_t *images_dev, const double *T_dev, int g, s3d_frame_stats *stats_dev,
+                     const void **records_dev, uint64_t *counts)
+{
+    int rc = check_ready(m); if (rc) return rc;
+    if (g < 1 || g > GF) return fail(S3D_EINVAL, "a sharded chunk holds 1..%d frames", GF);
+    if (!m->owner_host) return fail(S3D_EINVAL, "s3d_shard_config has not been called");
+    if ((rc = set_device(m))) return rc;
+    if ((rc = pump(m, true))) return rc;
+    const DevTables &tab = m->tab;
+    const u32 world = (u32)m->shard_world;
+    // this rank's contiguous slice of the processed beams
+    const int lo = (int)((int64_t)tab.n_beams * m->shard_rank / m->shard_world);
+    const int hi = (int)((int64_t)tab.n_beams * (m->shard_rank + 1) / m->shard_world);
+    const size_t img_stride = (size_t)tab.H * tab.W;
+    DevStats *st = reinterpret_cast<DevStats *>(stats_dev);
+    for (;;) {
+        CU(cudaMemsetAsync(st, 0, sizeof(DevStats) * (size_t)g, m->stream));
+        u32 n_unique = 0;
+        if (tab.n_beams > 0 && tab.H > 0 && hi > lo) {
+            const bool vec16 = (tab.W % 16 == 0) && ((uintptr_t)images_dev % 16 == 0) && (img_stride % 16 == 0);
+            const int max_f = (tab.H + tab.free_step - 1) / tab.free_step;
+            const size_t ex_smem = sizeof(int) * (size_t)EX_BEAMS * (size_t)(2 * max_f + 1 + 2 * tab.occ_window);
+            const size_t fh_smem = sizeof(int) * (size_t)tab.n_beams;
+            CU(cudaMemsetAsync(m->first_hit.p, 0x7f, sizeof(int) * (size_t)g * tab.n_beams, m->stream));
+            dim3 g1((tab.H + FH_ROWS - 1) / FH_ROWS, g);
+            if (vec16) k_first_hit<16><<<g1, FH_THREADS, fh_smem, m->stream>>>(images_dev, img_stride, tab, m->p.thr, m->first_hit.p);
+            else k_first_hit<1><<<g1, FH_THREADS, fh_smem, m->stream>>>(images_dev, img_stride, tab, m->p.thr, m->first_hit.p);
+            ExpandArgs a;
+            a.imgs = images_dev; a.img_stride = img_stride; a.T = T_dev;
+            a.tab = tab; a.p = m->p; a.first_hit = m->first_hit.p;
+            a.skeys = m->skeys; a.scnt = m->scnt; a.smask = (u32)(m->scratch_cap - 1); a.slist = m->slist;
+            a.cc = m->cc; a.stats = st; a.mc = m->mc;
+            a.seq = m->chunk_seq; a.table_limit = ~0ull;         // the owner gates growth, not the expander
+            a.dbg = 0; a.beam_lo = lo; a.beam_hi = hi;
+            k_expand<<<dim3((hi - lo + EX_BEAMS - 1) / EX_BEAMS, g), EX_THREADS, ex_smem, m->stream>>>(a);
+            m->launches += 2;
+        }
+        // counts per owner -> host (the all-to-all needs the split sizes), and the retry flag
+        CU(cudaMemsetAsync(m->owner_ctr.p, 0, sizeof(u32) * 3 * 64, m->stream));
+        k_shard_count<<<m->n_sm * 2, 256, 0, m->stream>>>(m->skeys, m->slist, m->cc, world, m->owner_ctr.p);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(m->owner_host, m->owner_ctr.p, sizeof(u32) * 64, cudaMemcpyDeviceToHost, m->stream));
+        CU(cudaMemcpyAsync(m->mc_host, m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, m->stream));
+        CU(cudaStreamSynchronize(m->stream));
+        ++m->chunk_seq; m->snap_floor = m->chunk_seq;
+        if (m->mc_host->abort) {             // dedupe table too small for this chunk: enlarge, wipe, redo
+            ++m->n_retries;
+            if ((rc = ensure_scratch(m, m->scratch_cap * 2, true))) return rc;
+            k_clear_abort<<<1, 1, 0, m->stream>>>(m->mc, m->cc);
+            CU(cudaGetLastError());
+            continue;
+        }
+        if ((rc = fatal_from_flags(m, m->mc_host->err))) return rc;
+        u32 base[64];
+        for (u32 o = 0; o < world; ++o) { base[o] = n_unique; n_unique += m->owner_host[o]; counts[o] = m->owner_host[o]; }
+        if ((rc = m->send_buf.ensure((size_t)std::max<u32>(n_unique, 1) * REC_WORDS))) return rc;
+        CU(cudaMemcpyAsync(m->owner_ctr.p + 64, base, sizeof(u32) * 64, cudaMemcpyHostToDevice, m->stream));
+        k_shard_pack<<<m->n_sm * 2, 256, 0, m->stream>>>(m->skeys, m->scnt, m->slist, m->cc, world,
+                                                        m->owner_ctr.p + 64, m->owner_ctr.p + 128, m->send_buf.p);
+        k_shard_reset_cc<<<1, 1, 0, m->stream>>>(m->cc);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(m->stream));
+        m->launches += 3;
+        if (2ull * n_unique > m->scratch_cap && (rc = ensure_scratch(m, m->scratch_cap * 2, false))) return rc;
+        *records_dev = m->send_buf.p;
+        return 0;
+    }
+}
+
+int s3d_shard_apply(s3d_map *m, const void *records_dev, uint64_t n_records, int g, s3d_frame_stats *stats_dev)
+{
+    int rc = check_ready(m); if (rc) return rc;
+    if (g < 1 || g > GF) return fail(S3D_EINVAL, "a sharded chunk holds 1..%d frames", GF);
+    if ((rc = set_device(m))) return rc;
+    if ((rc = pump(m, true))) return rc;
+    // every received record is at most one new voxel: exact room check on the host
+    CU(cudaMemcpyAsync(m->mc_host, m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    m->count_known = m->mc_host->count;
+    while (m->count_known + n_records > table_limit(m)) if ((rc = grow_table(m, m->cap * 2))) return rc;
+    if (2 * n_records > m->scratch_cap && (rc = ensure_scratch(m, 2 * n_records, false))) return rc;
+    DevStats *st = reinterpret_cast<DevStats *>(stats_dev);
+    CU(cudaMemsetAsync(st, 0, sizeof(DevStats) * (size_t)g, m->stream));
+    if (n_records) {
+        const int blocks = (int)std::min<u64>((n_records + 255) / 256, (u64)m->n_sm * 8);
+        k_shard_merge<<<blocks, 256, 0, m->stream>>>(reinterpret_cast<const u64 *>(records_dev), n_records, m->skeys,
+                                                    m->scnt, m->slist, (u32)(m->scratch_cap - 1), m->cc, m->mc);
+    }
+    k_shard_count0<<<1, 1, 0, m->stream>>>(m->cc, m->mc);
+    const int ap_blocks = (int)((m->scratch_cap + AP_THREADS - 1) / AP_THREADS);
+    k_apply_chunk<<<ap_blocks, AP_THREADS, 0, m->stream>>>(m->skeys, m->scnt, m->slist, g, m->cc, st, m->table,
+                                                          m->cap - 1, m->p, m->sum_tab.p, m->mc);
+    CU(cudaGetLastError());
+    m->launches += 3;
+    m->ex_valid = false;
+    return sync_counters(m);
 }
 
 int s3d_reserve(s3d_map *m, uint64_t n_voxels)

@@ -204,3 +204,23 @@ def test_dump_load_roundtrip_and_xyzi32(s3d):
     assert np.array_equal(blob[np.lexsort(blob.T[::-1])], want[np.lexsort(want.T[::-1])])
     m.reset_map()
     assert m.frame_count == 0 and m.get_point_cloud()["num_voxels"] == 0
+
+
+def test_sharded_single_rank_equals_plain(s3d):
+    """The sharded code path (expand -> pack by owner -> merge -> apply) with world = 1 must
+    reproduce the plain mapper exactly; the 2-rank exchange is covered on CPU (gloo) and by
+    tools/sharded_check.py under torchrun on 2+ GPUs."""
+    from sonar_3d_reconstruction_b200 import synthetic
+    from sonar_3d_reconstruction_b200.sharded import ShardedSonarMapper
+    spec = dict(H=160, W=200, config=dict(voxel_resolution=0.06, intensity_threshold=45, max_range=8.0), step_m=0.03)
+    images, pos, quat, cfg = synthetic.make_sequence(spec, 37, seed=4)
+    a = s3d.SonarTo3DMapper(cfg)
+    sa = [_stats3(s) for s in a.process_sonar_images(images, pos, quat)]
+    b = ShardedSonarMapper(dict(cfg, table_capacity=4096), group=None)
+    sb = [_stats3(s) for s in b.process_sonar_images(images, pos, quat)]
+    assert sa == sb
+    ka, va = a.octree.voxels.to_arrays()
+    kb, vb = b.gather_map()
+    assert_same_map(ka, va, kb, vb, 0.0, "sharded(world=1) vs plain")
+    assert b.get_point_cloud()["num_occupied"] == a.get_point_cloud()["num_occupied"]
+    assert b.num_voxels() == len(ka)

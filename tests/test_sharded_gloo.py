@@ -1,0 +1,222 @@
+"""Host-side logic of the sharded map on CPU: world_size-2 gloo, per-rank compute replaced by a
+test double built on the CPU oracle.  What is under test is the product's own exchange code
+(sonar_3d_reconstruction_b200/sharded.py): owner hash, record layout, the variable-size
+all-to-all, the stats reduction and the gathers.  The N-rank map must equal the 1-rank oracle map."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import assert_same_map, sort_by_key
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+class _HostMapper:
+    """Host side of the product mapper (config, pose -> 4x4, bearing table) without a GPU: the
+    methods are the product's own, borrowed unbound."""
+
+    def __init__(self, config):
+        from sonar_3d_reconstruction_b200.mapper import SonarTo3DMapper as M
+        self._M = M
+        c = dict(horizontal_fov=130.0, image_width=512, sonar_position=[0.0, 0.0, -0.5],
+                 sonar_orientation=[0.0, 1.5708, 0.0], min_probability=0.6)
+        c.update(config or {})
+        self.horizontal_fov = np.radians(c["horizontal_fov"])
+        self.image_width = c["image_width"]
+        self.min_probability = c["min_probability"]
+        self.bearing_angles = np.linspace(-self.horizontal_fov / 2, self.horizontal_fov / 2, self.image_width)
+        self.T_sonar_to_base = M.create_transform_matrix(self, np.array(c["sonar_position"]), np.array(c["sonar_orientation"]))
+
+    def quaternion_to_matrix(self, q):
+        return self._M.quaternion_to_matrix(self, q)
+
+    def create_odometry_transform(self, p, q):
+        return self._M.create_odometry_transform(self, p, q)
+
+    def compose_transforms(self, ps, qs):
+        return self._M.compose_transforms(self, ps, qs)
+
+    def _check_width(self, w):
+        return self._M._check_width(self, w)
+
+    def _sync_device_config(self, H, W):
+        pass
+
+
+class _OracleBackend:
+    """Test double of CudaShardBackend: same interface, CPU oracle inside."""
+
+    def __init__(self, config, rank, world):
+        from oracle.oracle import OracleMapper
+        self.o = OracleMapper(config)
+        self.cfg = dict(lo_occ=1.5, lo_free=-2.0)
+        self.cfg["lo_occ"] = (config or {}).get("log_odds_occupied", 1.5)
+        self.cfg["lo_free"] = (config or {}).get("log_odds_free", -2.0)
+        self.res = (config or {}).get("voxel_resolution", 0.05)
+        self.rank, self.world = rank, world
+
+    def upload(self, images, T):
+        return images, np.asarray(T, dtype=np.float64).reshape(-1, 16)
+
+    def expand(self, imgs, T, f0, g):
+        from sonar_3d_reconstruction_b200 import sharded as S
+        W = imgs.shape[2]
+        n_beams = len(range(0, W, max(1, W // 256)))
+        self.o.set_beam_slice(*S.beam_slice(n_beams, self.rank, self.world))
+        acc = {}
+        n_samp = []
+        for f in range(g):
+            xyz, occ = self.o.expand_frame(imgs[f0 + f], T[f0 + f])
+            n_samp.append(len(xyz))
+            if len(xyz) == 0:
+                continue
+            packed = S.pack_keys(self.o.world_to_key(xyz))
+            for typ, shift in ((0, 0), (1, 32)):
+                u, c = np.unique(packed[occ == typ], return_counts=True)
+                for k, n in zip(u.tolist(), c.tolist()):
+                    acc.setdefault(k, [0] * 16)[f] += n << shift
+        self.o.set_beam_slice(0, 2**31 - 1)
+        keys = np.array(sorted(acc), dtype=np.uint64)
+        owners = S.owner_of_packed(keys, self.world) if len(keys) else np.zeros(0, dtype=np.int64)
+        order = np.argsort(owners, kind="stable")
+        rec = np.zeros((len(keys), S.RECORD_WORDS), dtype=np.int64)
+        for row, i in enumerate(order):
+            rec[row, 0] = np.int64(np.uint64(keys[i]).view(np.int64)) if False else int(keys[i])
+            rec[row, 1:] = acc[int(keys[i])]
+        counts = [int((owners == o).sum()) for o in range(self.world)]
+        return torch.from_numpy(rec), counts, torch.tensor(n_samp, dtype=torch.int64)
+
+    def apply(self, recv, g):
+        from sonar_3d_reconstruction_b200 import sharded as S
+        rec = recv.numpy()
+        merged = {}
+        for row in rec:
+            a = merged.setdefault(int(row[0]), np.zeros(16, dtype=np.int64))
+            a += row[1:]
+        keys = np.array(sorted(merged), dtype=np.uint64)
+        ijk = S.unpack_keys(keys) if len(keys) else np.zeros((0, 3), dtype=np.int64)
+        st = np.zeros((g, 3), dtype=np.int64)
+        for f in range(g):
+            for k, c3 in zip(keys.tolist(), ijk):
+                c = int(merged[k][f])
+                if c == 0:
+                    continue
+                n_occ, n_free = c >> 32, c & 0xFFFFFFFF
+                s = 0.0
+                for _ in range(n_free):
+                    s += self.cfg["lo_free"]
+                for _ in range(n_occ):
+                    s += self.cfg["lo_occ"]
+                centre = (c3.astype(np.float64) + 0.5) * self.res
+                self.o.update_voxel(centre, s / (n_occ + n_free), adaptive=n_occ > 0)
+                st[f, 0 if n_occ > 0 else 1] += 1
+            st[f, 2] = self.o.num_voxels()
+        return torch.from_numpy(st)
+
+    def count(self):
+        return self.o.num_voxels()
+
+    def export_occupied(self, min_probability):
+        self.o.min_probability = min_probability
+        pc = self.o.get_point_cloud()
+        return pc["points"], pc["probabilities"]
+
+    def dump(self):
+        return self.o.dump()
+
+    def clear(self):
+        self.o.reset_map()
+
+    def tensor(self, a):
+        return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def _factory(config, rank, world):
+    return _HostMapper(config), _OracleBackend(config, rank, world)
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sonar_3d_reconstruction_b200 import synthetic
+    from sonar_3d_reconstruction_b200.sharded import ShardedSonarMapper
+    spec = dict(H=90, W=48, config=dict(voxel_resolution=0.12, intensity_threshold=40, max_range=6.0), step_m=0.04)
+    images, pos, quat, cfg = synthetic.make_sequence(spec, 19, seed=5)      # 19 frames: a full chunk + a ragged one
+    m = ShardedSonarMapper(cfg, group=dist.group.WORLD, backend_factory=_factory)
+    stats = m.process_sonar_images(images, pos, quat)
+    keys, L = m.gather_map()
+    pc = m.get_point_cloud()
+    nv = m.num_voxels()
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "sharded.npz"), keys=keys, L=L,
+                 stats=np.array([[s["num_occupied"], s["num_free"], s["num_voxels"], s["num_samples"]] for s in stats]),
+                 pc_points=pc["points"], pc_prob=pc["probabilities"], nv=nv, exch=m.last_exchange_bytes)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_equals_single_rank_oracle(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    z = np.load(tmp_path / "sharded.npz")
+    from oracle.oracle import OracleMapper
+    from sonar_3d_reconstruction_b200 import synthetic
+    spec = dict(H=90, W=48, config=dict(voxel_resolution=0.12, intensity_threshold=40, max_range=6.0), step_m=0.04)
+    images, pos, quat, cfg = synthetic.make_sequence(spec, 19, seed=5)
+    o = OracleMapper(cfg)
+    want = []
+    for f in range(len(images)):
+        s = o.process_sonar_image(images[f], pos[f], quat[f])
+        want.append([s["num_occupied"], s["num_free"], s["num_voxels"], s["num_samples"]])
+    assert z["stats"].tolist() == want
+    k, L = o.dump()
+    assert_same_map(z["keys"], z["L"], k, L, 0.0, "2-rank sharded vs 1-rank oracle")     # dyadic deltas: exact
+    assert int(z["nv"]) == len(k)
+    pc = o.get_point_cloud()
+    res = cfg["voxel_resolution"]
+    a = sort_by_key(np.floor(z["pc_points"] / res), z["pc_prob"])
+    b = sort_by_key(np.floor(pc["points"] / res), pc["probabilities"])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert int(z["exch"]) > 0
+
+
+def test_owner_hash_and_key_packing_match_the_library():
+    from sonar_3d_reconstruction_b200 import _native, sharded as S
+    rng = np.random.default_rng(0)
+    ijk = rng.integers(-(1 << 20), 1 << 20, size=(5000, 3))
+    ijk[:4] = [[0, 0, 0], [-(1 << 20), (1 << 20) - 1, 0], [1, -1, 1], [123456, -654321, 7]]
+    assert np.array_equal(S.unpack_keys(S.pack_keys(ijk)), ijk)
+    for world in (1, 2, 3, 4, 8):
+        mine = S.owner_of_keys(ijk, world)
+        lib = _native.shard_owner(ijk, world)            # host helper of libsonar3d.so, no GPU needed
+        assert np.array_equal(mine, lib)
+        assert mine.min() >= 0 and mine.max() < world
+        if world > 1:
+            share = np.bincount(mine, minlength=world) / len(ijk)
+            assert share.min() > 0.7 / world                # spatial hash spreads the load
+
+
+def test_beam_slices_cover_all_beams_once():
+    from sonar_3d_reconstruction_b200.sharded import beam_slice
+    for n in (1, 7, 256, 257):
+        for world in (1, 2, 3, 8):
+            cover = []
+            for r in range(world):
+                lo, hi = beam_slice(n, r, world)
+                cover += list(range(lo, hi))
+            assert cover == list(range(n))
