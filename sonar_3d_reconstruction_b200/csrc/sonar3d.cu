@@ -211,33 +211,59 @@ __device__ __forceinline__ void raise_abort(MapCtr *mc, u32 why, u64 seq)
     atomicMin(&mc->abort_seq, seq);
 }
 
-// Bump lane `lane` of the entry of `key`, creating the entry if needed.  `cur` is the key word
-// already loaded from the home slot.  Returns the slot if this call created the entry, else ~0.
-__device__ __forceinline__ u32 scratch_resolve(const ExpandArgs &a, u64 key, u32 slot, u64 cur, int lane, u64 inc)
+// The dedupe table is probed by 32-byte sector: a bucket is 4 consecutive keys, loaded with two
+// 16-byte ld.cg (one sector), so a lookup is one L2 round trip unless the bucket is full of other
+// keys.  Inside a warp the latency of a pass is the LONGEST probe chain of its lanes, which is
+// why single-slot linear probing was slow here (tools/dbg_stage.sh, profiles/).
+struct Bucket { ulonglong2 a, b; };
+
+__device__ __forceinline__ Bucket load_bucket(const u64 *skeys, u32 base)
+{
+    Bucket k;
+    k.a = __ldcg(reinterpret_cast<const ulonglong2 *>(skeys + base));
+    k.b = __ldcg(reinterpret_cast<const ulonglong2 *>(skeys + base + 2));
+    return k;
+}
+
+// find `key` in the dedupe table or create its entry; `k` holds the already loaded home bucket.
+// Returns the slot, or ~0u if the table is over-loaded.  `created` says this call made the entry.
+__device__ __forceinline__ u32 dedupe_slot(u64 *skeys, u32 smask, u64 key, u32 base, Bucket k, bool &created)
+{
+    created = false;
+    for (u32 probe = 0; probe < SCRATCH_PROBE_LIMIT; ++probe) {
+        const u64 w[4] = {k.a.x, k.a.y, k.b.x, k.b.y};
+        int hit = -1, hole = -1;
+#pragma unroll
+        for (int j = 3; j >= 0; --j) { if (w[j] == key) hit = j; if (w[j] == EMPTY_KEY) hole = j; }
+        if (hit >= 0) return base + (u32)hit;
+        if (hole >= 0) {
+            const u64 cur = atomicCAS(&skeys[base + hole], EMPTY_KEY, key);
+            if (cur == EMPTY_KEY) { created = true; return base + (u32)hole; }
+            if (cur == key) return base + (u32)hole;
+            k = load_bucket(skeys, base);            // another key took the hole: look at the bucket again
+            continue;
+        }
+        base = (base + 4) & smask;                   // bucket full of other keys
+        k = load_bucket(skeys, base);
+    }
+    return ~0u;
+}
+
+// Bump lane `lane` of the entry of `key`.  Returns the slot if this call created the entry, else ~0.
+__device__ __forceinline__ u32 scratch_resolve(const ExpandArgs &a, u64 key, u32 base, const Bucket &k, int lane, u64 inc)
 {
     if (a.dbg == 3) {      // timing experiment: reductions only, no key check
-        u32 *half = reinterpret_cast<u32 *>(&a.scnt[(size_t)slot * GF + lane]);
+        u32 *half = reinterpret_cast<u32 *>(&a.scnt[(size_t)base * GF + lane]);
         if (inc >> 32) atomicAdd(half + 1, (u32)(inc >> 32)); else atomicAdd(half, (u32)inc);
         return ~0u;
     }
-    for (u32 probe = 0; probe < SCRATCH_PROBE_LIMIT; ++probe) {
-        bool created = false;
-        if (cur == EMPTY_KEY) {
-            cur = atomicCAS(&a.skeys[slot], EMPTY_KEY, key);
-            if (cur == EMPTY_KEY) { cur = key; created = true; }
-        }
-        if (cur == key) {
-            // the counter lane is {n_free: low 32 bits, n_occ: high 32 bits}; bump the half that applies
-            u32 *half = reinterpret_cast<u32 *>(&a.scnt[(size_t)slot * GF + lane]);
-            if (a.dbg == 4) return created ? slot : ~0u;       // timing experiment: keys only, no reductions
-            if (inc >> 32) atomicAdd(half + 1, (u32)(inc >> 32)); else atomicAdd(half, (u32)inc);
-            return created ? slot : ~0u;
-        }
-        slot = (slot + 1) & a.smask;
-        cur = __ldcg(&a.skeys[slot]);
-    }
-    raise_abort(a.mc, ABORT_SCRATCH, a.seq);     // table too loaded: the host enlarges it and retries
-    return ~0u;
+    bool created;
+    const u32 slot = dedupe_slot(a.skeys, a.smask, key, base, k, created);
+    if (slot == ~0u) { raise_abort(a.mc, ABORT_SCRATCH, a.seq); return ~0u; }   // the host enlarges the table and retries
+    // the counter lane is {n_free: low 32 bits, n_occ: high 32 bits}; bump the half that applies
+    u32 *half = reinterpret_cast<u32 *>(&a.scnt[(size_t)slot * GF + lane]);
+    if (a.dbg != 4) { if (inc >> 32) atomicAdd(half + 1, (u32)(inc >> 32)); else atomicAdd(half, (u32)inc); }
+    return created ? slot : ~0u;
 }
 
 // One sample: sonar-frame point from the host trig tables, Sonar->Map transform, z filter, key.
@@ -311,18 +337,21 @@ __device__ __forceinline__ void commit_batch(const ExpandArgs &a, const bool (&o
             lead[j] = (lane == __ffs(peers) - 1);
             const u64 n = (u64)__popc(peers);
             inc[j] = occupied ? (n << 32) : n;
-            slot[j] = mix32(key[j]) & a.smask;
+            slot[j] = mix32(key[j]) & a.smask & ~3u;          // home bucket
         }
     }
-    u64 cur[EX_ILP];
+    Bucket cur[EX_ILP];
 #pragma unroll
-    for (int j = 0; j < EX_ILP; ++j) cur[j] = lead[j] ? __ldcg(&a.skeys[slot[j]]) : 0ull;
+    for (int j = 0; j < EX_ILP; ++j) {
+        cur[j].a = cur[j].b = make_ulonglong2(0ull, 0ull);
+        if (lead[j]) cur[j] = load_bucket(a.skeys, slot[j]);
+    }
     u32 made[EX_ILP];
     int n_mine = 0;
     if (a.dbg == 2) {
         u64 x = 0;
 #pragma unroll
-        for (int j = 0; j < EX_ILP; ++j) x ^= cur[j];
+        for (int j = 0; j < EX_ILP; ++j) x ^= cur[j].a.x ^ cur[j].b.y;
         if (x == 0x123456789ull) a.slist[0] = 1;
         return;
     }
@@ -515,20 +544,27 @@ __device__ __forceinline__ double apply_one(double L, double upd, bool adaptive,
 }
 
 // find-or-insert; returns slot index or ~0 on failure.  `fresh` says the key was inserted.
+// Probing goes by 32-byte sector = 2 slots (one L2 round trip sees both), starting at the even
+// slot of the home pair; every reader of the table (k_query) walks the same sequence.
+__device__ __forceinline__ u64 table_home(u64 key, u64 mask) { return (mix64(key) >> 8) & mask & ~1ull; }
+
 __device__ __forceinline__ u64 table_find_or_insert(Slot *table, u64 mask, u64 key, bool &fresh, double &val)
 {
-    u64 slot = (mix64(key) >> 8) & mask;
+    u64 pair = table_home(key, mask);
     fresh = false;
     for (u32 probe = 0; probe < (1u << 20); ++probe) {
-        const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2 *>(&table[slot]));
-        u64 cur = raw.x;
-        if (cur == key) { val = __longlong_as_double((long long)raw.y); return slot; }
-        if (cur == EMPTY_KEY) {
-            cur = atomicCAS(&table[slot].key, EMPTY_KEY, key);
+        const ulonglong2 s0 = __ldcg(reinterpret_cast<const ulonglong2 *>(&table[pair]));
+        const ulonglong2 s1 = __ldcg(reinterpret_cast<const ulonglong2 *>(&table[pair + 1]));
+        if (s0.x == key) { val = __longlong_as_double((long long)s0.y); return pair; }
+        if (s1.x == key) { val = __longlong_as_double((long long)s1.y); return pair + 1; }
+        if (s0.x == EMPTY_KEY || s1.x == EMPTY_KEY) {
+            const u64 slot = s0.x == EMPTY_KEY ? pair : pair + 1;
+            const u64 cur = atomicCAS(&table[slot].key, EMPTY_KEY, key);
             if (cur == EMPTY_KEY) { fresh = true; val = 0.0; return slot; }     // :105-106
             if (cur == key) { val = __ldcg(&table[slot].val); return slot; }
+            continue;                                   // lost the hole to another key: same pair again
         }
-        slot = (slot + 1) & mask;
+        pair = (pair + 2) & mask;
     }
     return ~0ull;
 }
@@ -750,23 +786,15 @@ __global__ void k_shard_merge(const u64 *__restrict__ recv, u64 n_rec, u64 *skey
     for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n_rec; i += (u64)gridDim.x * blockDim.x) {
         const u64 *rec = recv + i * REC_WORDS;
         const u64 key = rec[0];
-        u32 slot = mix32(key) & smask;
-        bool done = false;
-        for (u32 probe = 0; probe <= smask && !done; ++probe) {
-            u64 cur = __ldcg(&skeys[slot]);
-            bool created = false;
-            if (cur == EMPTY_KEY) {
-                cur = atomicCAS(&skeys[slot], EMPTY_KEY, key);
-                if (cur == EMPTY_KEY) { cur = key; created = true; }
-            }
-            if (cur == key) {
-                if (created) slist[atomicAdd(&cc->n_unique, 1u) & smask] = slot;
+        const u32 base = mix32(key) & smask & ~3u;
+        bool created;
+        const u32 slot = dedupe_slot(skeys, smask, key, base, load_bucket(skeys, base), created);
+        const bool done = slot != ~0u;
+        if (done) {
+            if (created) slist[atomicAdd(&cc->n_unique, 1u) & smask] = slot;
 #pragma unroll
-                for (int f = 0; f < GF; ++f)
-                    if (rec[1 + f]) atomicAdd(&scnt[(size_t)slot * GF + f], rec[1 + f]);
-                done = true;
-            }
-            slot = (slot + 1) & smask;
+            for (int f = 0; f < GF; ++f)
+                if (rec[1 + f]) atomicAdd(&scnt[(size_t)slot * GF + f], rec[1 + f]);
         }
         if (!done) atomicOr(&mc->err, ERR_TABLEFULL);
     }
@@ -851,7 +879,7 @@ __global__ void k_query(const u64 *__restrict__ keys, u64 n, const Slot *__restr
     const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const u64 key = keys[i];
-    u64 slot = (mix64(key) >> 8) & tmask;
+    u64 slot = table_home(key, tmask);
     double v = 0.0; uint8_t f = 0;
     for (u64 probe = 0; probe <= tmask; ++probe) {
         const ulonglong2 raw = *reinterpret_cast<const ulonglong2 *>(&table[slot]);
@@ -1116,7 +1144,7 @@ int grow_table(s3d_map *m, u64 new_cap)
 }
 
 // the device gate: a chunk is applied only if count + unique(chunk) stays within this
-u64 table_limit(const s3d_map *m) { return m->cap / 4 * 3; }
+u64 table_limit(const s3d_map *m) { return m->cap / 2; }
 
 // room for `extra` more voxels on top of the last known count (stream must be idle)
 int ensure_room(s3d_map *m, u64 extra)
