@@ -202,7 +202,6 @@ struct ExpandArgs {
     int beam_lo, beam_hi;        // processed beams [beam_lo, beam_hi) are expanded (a rank's slice when sharded)
     int dbg;                     // S3D_DEBUG_STAGE (timing experiments only): 1 = no dedupe, 2 = probe only
     u64 seq;                     // chunk sequence number (for abort bookkeeping)
-    u64 table_limit;             // gate: count + unique(chunk) must stay <= this
 };
 
 __device__ __forceinline__ void raise_abort(MapCtr *mc, u32 why, u64 seq)
@@ -394,7 +393,6 @@ k_expand(ExpandArgs a)
     const int max_f = (H + tab.free_step - 1) / tab.free_step;        // free candidates per beam
     const int per_warp = (max_f + 1) + max_f + 2 * tab.occ_window;
     __shared__ double s_T[12];
-    __shared__ bool s_last;
     __shared__ u32 s_abort;
     __shared__ u32 s_wbuf[EX_BEAMS][EX_WBUF];
 
@@ -507,23 +505,19 @@ k_expand(ExpandArgs a)
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
     if (lane == 0 && emitted) atomicAdd(&a.stats[g].n_samples, (u64)emitted);
-    // last block out: the gate.  The chunk may be applied only if the table keeps its load bound
-    // even when every voxel of the chunk is new; otherwise the host grows the table and retries.
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const u32 t = atomicAdd(&a.cc->ticket, 1u);
-        s_last = (t == gridDim.x * gridDim.y - 1);
-    }
-    __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-        __threadfence();
-        const u32 nu = atomicAdd(&a.cc->n_unique, 0u);
-        const u64 cnt = atomicAdd(&a.mc->count, 0ull);
-        a.cc->count0 = cnt;
-        a.cc->ticket = 0;
-        if (cnt + nu > a.table_limit) raise_abort(a.mc, ABORT_TABLE, a.seq);
-    }
+}
+
+// The gate, one thread, on the apply stream between k_expand and k_apply_chunk of a chunk (the
+// previous chunk's apply has finished there, so `count` is final).  The chunk may be applied only
+// if the table keeps its load bound even when every voxel of the chunk is new; otherwise the
+// host grows the table and re-runs the chunk.
+__global__ void k_gate(ChunkCtr *cc, MapCtr *mc, u64 table_limit, u64 seq)
+{
+    if (mc->abort) return;
+    const u64 cnt = mc->count;
+    cc->count0 = cnt;
+    cc->ticket = 0;
+    if (cnt + cc->n_unique > table_limit) raise_abort(mc, ABORT_TABLE, seq);
 }
 
 // ------------------------------------------------------------------------------------ K4
@@ -817,8 +811,10 @@ __global__ void k_fill_u64(u64 *t, u64 n, u64 v)
 __global__ void k_clear_abort(MapCtr *mc, ChunkCtr *cc)
 {
     mc->abort = 0; mc->abort_seq = ~0ull;
-    cc->count0 = 0; cc->n_unique = 0; cc->ticket = 0;
-    for (int f = 0; f < GF; ++f) cc->neu[f] = 0;
+    for (int b = 0; b < 2; ++b) {
+        cc[b].count0 = 0; cc[b].n_unique = 0; cc[b].ticket = 0;
+        for (int f = 0; f < GF; ++f) cc[b].neu[f] = 0;
+    }
 }
 
 __global__ void k_rehash(const Slot *__restrict__ old_t, u64 old_n, Slot *new_t, u64 new_mask, MapCtr *mc)
@@ -1035,7 +1031,12 @@ struct s3d_map {
     // chunk dedupe table: one allocation {counters[C][GF], keys[C], list[C]} so that a single L2
     // access-policy window can keep it resident between the kernels of a chunk
     DevBuf<uint8_t> spool; u64 scratch_cap = 0;
-    u64 *skeys = nullptr, *scnt = nullptr; u32 *slist = nullptr;
+    u64 *skeys = nullptr, *scnt = nullptr; u32 *slist = nullptr;     // buffer 0 (also the sharded path's)
+    // two chunk buffers: k_expand of chunk c+1 (expand stream) overlaps k_apply_chunk of chunk c
+    struct ChunkBuf { u64 *skeys = nullptr, *scnt = nullptr; u32 *slist = nullptr; ChunkCtr *cc = nullptr;
+                      int *first_hit = nullptr; cudaEvent_t expanded = nullptr, freed = nullptr; bool used = false; };
+    ChunkBuf buf[2];
+    cudaStream_t xstream = nullptr;  // expand stream
     size_t l2_persist_max = 0, l2_window_max = 0, l2_window = 0;
     DevBuf<double> sum_tab;          // [4][SUMT] running sums of n copies of lo_free / lo_occ, and their means
     DevBuf<int> first_hit;
@@ -1063,19 +1064,20 @@ namespace {
 int set_device(s3d_map *m) { CU(cudaSetDevice(m->device)); return 0; }
 
 // CUDA-event bracket around one kernel group, on the launching stream
-size_t prof_mark(s3d_map *m)
+size_t prof_mark(s3d_map *m, cudaStream_t st)
 {
     if (m->ev_used == m->ev_pool.size()) {
         cudaEvent_t e; cudaEventCreate(&e);
         m->ev_pool.push_back(e);
     }
-    cudaEventRecord(m->ev_pool[m->ev_used], m->stream);
+    cudaEventRecord(m->ev_pool[m->ev_used], st);
     return m->ev_used++;
 }
 
 int prof_collect(s3d_map *m)
 {
     if (m->spans.empty()) { m->ev_used = 0; return 0; }
+    CU(cudaStreamSynchronize(m->xstream));
     CU(cudaStreamSynchronize(m->stream));
     for (const auto &sp : m->spans) {
         float ms = 0.f;
@@ -1169,11 +1171,18 @@ int ensure_scratch(s3d_map *m, u64 want_cap, bool wipe)
     const bool realloc = want_cap > m->scratch_cap;
     if (realloc) {
         const size_t cnt_bytes = sizeof(u64) * (size_t)want_cap * GF, key_bytes = sizeof(u64) * (size_t)want_cap;
-        const size_t pool = cnt_bytes + key_bytes + sizeof(u32) * (size_t)want_cap;
+        const size_t one = cnt_bytes + key_bytes + sizeof(u32) * (size_t)want_cap;
+        const size_t pool = 2 * one;
+        CU(cudaStreamSynchronize(m->xstream));
         int rc = m->spool.ensure(pool); if (rc) return rc;
-        m->scnt = reinterpret_cast<u64 *>(m->spool.p);
-        m->skeys = reinterpret_cast<u64 *>(m->spool.p + cnt_bytes);
-        m->slist = reinterpret_cast<u32 *>(m->spool.p + cnt_bytes + key_bytes);
+        for (int b = 0; b < 2; ++b) {
+            uint8_t *base = m->spool.p + (size_t)b * one;
+            m->buf[b].scnt = reinterpret_cast<u64 *>(base);
+            m->buf[b].skeys = reinterpret_cast<u64 *>(base + cnt_bytes);
+            m->buf[b].slist = reinterpret_cast<u32 *>(base + cnt_bytes + key_bytes);
+            m->buf[b].used = false;
+        }
+        m->scnt = m->buf[0].scnt; m->skeys = m->buf[0].skeys; m->slist = m->buf[0].slist;
         m->scratch_cap = want_cap;
         // The dedupe table is hit by every sample of a chunk and re-read by the apply kernel:
         // ask L2 to keep it (persisting window) while images and voxel-table traffic stream by.
@@ -1188,14 +1197,20 @@ int ensure_scratch(s3d_map *m, u64 want_cap, bool wipe)
             av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             CU(cudaStreamSetAttribute(m->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+            CU(cudaStreamSetAttribute(m->xstream, cudaStreamAttributeAccessPolicyWindow, &av));
             m->l2_window = win;
         }
     }
     if (realloc || wipe) {
         const int blocks = (int)std::min<u64>((m->scratch_cap + 255) / 256, (u64)m->n_sm * 16);
-        k_fill_u64<<<blocks, 256, 0, m->stream>>>(m->skeys, m->scratch_cap, EMPTY_KEY);
-        CU(cudaGetLastError());
-        CU(cudaMemsetAsync(m->scnt, 0, sizeof(u64) * (size_t)m->scratch_cap * GF, m->stream));
+        CU(cudaStreamSynchronize(m->xstream));
+        for (int b = 0; b < 2; ++b) {
+            k_fill_u64<<<blocks, 256, 0, m->stream>>>(m->buf[b].skeys, m->scratch_cap, EMPTY_KEY);
+            CU(cudaGetLastError());
+            CU(cudaMemsetAsync(m->buf[b].scnt, 0, sizeof(u64) * (size_t)m->scratch_cap * GF, m->stream));
+            m->buf[b].used = false;
+        }
+        CU(cudaStreamSynchronize(m->stream));
     }
     return 0;
 }
@@ -1209,42 +1224,53 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     const int max_f = (tab.H + tab.free_step - 1) / tab.free_step;
     const size_t ex_smem = sizeof(int) * (size_t)EX_BEAMS * (size_t)(2 * max_f + 1 + 2 * tab.occ_window);
     const size_t fh_smem = sizeof(int) * (size_t)tab.n_beams;
-    const size_t e0 = m->prof_on ? prof_mark(m) : 0;
-    CU(cudaMemsetAsync(m->first_hit.p, 0x7f, sizeof(int) * (size_t)g * tab.n_beams, m->stream));
+    s3d_map::ChunkBuf &cb = m->buf[m->chunk_seq & 1];
+    cudaStream_t xs = m->xstream, as = m->stream;
+    // ---- expand stream: first hits + expansion into this chunk's dedupe buffer.  It may run while
+    // the previous chunk is still being applied; it only waits for its own buffer to be drained.
+    if (cb.used) CU(cudaStreamWaitEvent(xs, cb.freed, 0));
+    const size_t e0 = m->prof_on ? prof_mark(m, xs) : 0;
+    CU(cudaMemsetAsync(cb.first_hit, 0x7f, sizeof(int) * (size_t)g * tab.n_beams, xs));
     dim3 g1((tab.H + FH_ROWS - 1) / FH_ROWS, g);
-    if (vec16) k_first_hit<16><<<g1, FH_THREADS, fh_smem, m->stream>>>(imgs, img_stride, tab, m->p.thr, m->first_hit.p);
-    else k_first_hit<1><<<g1, FH_THREADS, fh_smem, m->stream>>>(imgs, img_stride, tab, m->p.thr, m->first_hit.p);
-    const size_t e1 = m->prof_on ? prof_mark(m) : 0;
+    if (vec16) k_first_hit<16><<<g1, FH_THREADS, fh_smem, xs>>>(imgs, img_stride, tab, m->p.thr, cb.first_hit);
+    else k_first_hit<1><<<g1, FH_THREADS, fh_smem, xs>>>(imgs, img_stride, tab, m->p.thr, cb.first_hit);
+    const size_t e1 = m->prof_on ? prof_mark(m, xs) : 0;
     ExpandArgs a;
     a.imgs = imgs; a.img_stride = img_stride;
     a.T = j.T + base * 16;
     a.tab = tab; a.p = m->p;
-    a.first_hit = m->first_hit.p;
-    a.skeys = m->skeys; a.scnt = m->scnt; a.smask = (u32)(m->scratch_cap - 1); a.slist = m->slist;
-    a.cc = m->cc; a.stats = j.stats + base; a.mc = m->mc;
-    a.seq = m->chunk_seq; a.table_limit = table_limit(m);
+    a.first_hit = cb.first_hit;
+    a.skeys = cb.skeys; a.scnt = cb.scnt; a.smask = (u32)(m->scratch_cap - 1); a.slist = cb.slist;
+    a.cc = cb.cc; a.stats = j.stats + base; a.mc = m->mc;
+    a.seq = m->chunk_seq;
     a.dbg = m->dbg_stage;
     a.beam_lo = 0; a.beam_hi = tab.n_beams;
-    k_expand<<<dim3((tab.n_beams + EX_BEAMS - 1) / EX_BEAMS, g), EX_THREADS, ex_smem, m->stream>>>(a);
-    const size_t e2 = m->prof_on ? prof_mark(m) : 0;
+    k_expand<<<dim3((tab.n_beams + EX_BEAMS - 1) / EX_BEAMS, g), EX_THREADS, ex_smem, xs>>>(a);
+    const size_t e2 = m->prof_on ? prof_mark(m, xs) : 0;
+    CU(cudaEventRecord(cb.expanded, xs));
+    // ---- apply stream: gate, then the chunk's frames in order into the voxel table
+    CU(cudaStreamWaitEvent(as, cb.expanded, 0));
+    const size_t e3 = m->prof_on ? prof_mark(m, as) : 0;
+    k_gate<<<1, 1, 0, as>>>(cb.cc, m->mc, table_limit(m), m->chunk_seq);
     // one thread per dedupe entry the chunk can have created; blocks past the live count exit at once
     const int ap_blocks = (int)((m->scratch_cap + AP_THREADS - 1) / AP_THREADS);
-    k_apply_chunk<<<ap_blocks, AP_THREADS, 0, m->stream>>>(m->skeys, m->scnt, m->slist, g, m->cc,
-                                                          j.stats + base, m->table, m->cap - 1, m->p,
-                                                          m->sum_tab.p, m->mc);
+    k_apply_chunk<<<ap_blocks, AP_THREADS, 0, as>>>(cb.skeys, cb.scnt, cb.slist, g, cb.cc, j.stats + base, m->table,
+                                                  m->cap - 1, m->p, m->sum_tab.p, m->mc);
     CU(cudaGetLastError());
-    m->launches += 3;
+    CU(cudaEventRecord(cb.freed, as));
+    cb.used = true;
+    m->launches += 4;
     if (m->prof_on) {
-        const size_t e3 = prof_mark(m);
+        const size_t e4 = prof_mark(m, as);
         m->spans.push_back({e0, e1, S3D_K_FIRST_HIT});
         m->spans.push_back({e1, e2, S3D_K_EXPAND});
-        m->spans.push_back({e2, e3, S3D_K_APPLY});
+        m->spans.push_back({e3, e4, S3D_K_APPLY});
         for (int k = 0; k < S3D_K_COUNT; ++k) m->prof.launches[k] += 1;
         m->prof.frames += (u64)g;
     }
     const int ri = (int)(m->chunk_seq % s3d_map::RING);
-    CU(cudaMemcpyAsync(&m->snap_host[ri], m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, m->stream));
-    CU(cudaEventRecord(m->snap_ev[ri], m->stream));
+    CU(cudaMemcpyAsync(&m->snap_host[ri], m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, as));
+    CU(cudaEventRecord(m->snap_ev[ri], as));
     m->inflight[ri] = InFlight{m->chunk_seq, j.id, base, g};
     ++m->chunk_seq;
     m->ex_valid = false;
@@ -1256,6 +1282,7 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
 // was short, wipe the chunk working set and rewind the job queue to the chunk's first frame.
 int recover(s3d_map *m)
 {
+    CU(cudaStreamSynchronize(m->xstream));          // later chunks may still be expanding
     CU(cudaMemcpyAsync(m->mc_host, m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, m->stream));
     CU(cudaStreamSynchronize(m->stream));
     const MapCtr mc = *m->mc_host;
@@ -1339,10 +1366,12 @@ int pump(s3d_map *m, bool drain)
 // queue n frames whose images / transforms sit in device memory
 int submit_frames(s3d_map *m, const uint8_t *imgs_dev, int64_t n, const double *T_dev, DevStats *stats_dev)
 {
-    CU(cudaMemsetAsync(stats_dev, 0, sizeof(DevStats) * (size_t)n, m->stream));
+    // zeroed on the expand stream: k_expand is the first writer (num_samples)
+    CU(cudaMemsetAsync(stats_dev, 0, sizeof(DevStats) * (size_t)n, m->xstream));
     if (m->tab.n_beams == 0 || m->tab.H == 0) {
         // nothing to expand; len(voxels) still has to be reported
         int rc = pump(m, true); if (rc) return rc;
+        CU(cudaStreamSynchronize(m->xstream));
         for (int64_t f = 0; f < n; ++f)
             CU(cudaMemcpyAsync(&stats_dev[f].n_voxels, &m->mc->count, sizeof(u64), cudaMemcpyDeviceToDevice, m->stream));
         return 0;
@@ -1427,8 +1456,14 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
     CU(cudaMallocHost(&m->snap_host, sizeof(MapCtr) * s3d_map::RING));
     for (int i = 0; i < s3d_map::RING; ++i) CU(cudaEventCreateWithFlags(&m->snap_ev[i], cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
-    CU(cudaMalloc(&m->cc, sizeof(ChunkCtr)));
-    CU(cudaMemsetAsync(m->cc, 0, sizeof(ChunkCtr), m->stream));
+    CU(cudaStreamCreateWithFlags(&m->xstream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&m->cc, sizeof(ChunkCtr) * 2));
+    CU(cudaMemsetAsync(m->cc, 0, sizeof(ChunkCtr) * 2, m->stream));
+    for (int b = 0; b < 2; ++b) {
+        m->buf[b].cc = m->cc + b;
+        CU(cudaEventCreateWithFlags(&m->buf[b].expanded, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&m->buf[b].freed, cudaEventDisableTiming));
+    }
     CU(cudaMalloc(&m->ex_counts, sizeof(u64) * 4));
     CU(cudaMallocHost(&m->ex_counts_host, sizeof(u64) * 4));
     k_reset_ctr<<<1, 1, 0, m->stream>>>(m->mc);
@@ -1450,6 +1485,11 @@ int s3d_destroy(s3d_map *m)
     if (m->snap_host) cudaFreeHost(m->snap_host);
     for (int i = 0; i < s3d_map::RING; ++i) if (m->snap_ev[i]) cudaEventDestroy(m->snap_ev[i]);
     if (m->cc) cudaFree(m->cc);
+    for (int b = 0; b < 2; ++b) {
+        if (m->buf[b].expanded) cudaEventDestroy(m->buf[b].expanded);
+        if (m->buf[b].freed) cudaEventDestroy(m->buf[b].freed);
+    }
+    if (m->xstream) { cudaStreamSynchronize(m->xstream); cudaStreamDestroy(m->xstream); }
     if (m->owner_host) cudaFreeHost(m->owner_host);
     m->send_buf.release(); m->owner_ctr.release();
     for (cudaEvent_t e : m->copy_ev) cudaEventDestroy(e);
@@ -1548,7 +1588,8 @@ int s3d_set_tables(s3d_map *m, const s3d_tables *t)
     d.nv_free = m->d_nv_free.p; d.nv_occ = m->d_nv_occ.p; d.cos_va = m->d_cos_va.p; d.sin_va = m->d_sin_va.p;
     d.col_to_beam = m->d_col_to_beam.p;
     m->have_tables = true;
-    if ((rc = m->first_hit.ensure((size_t)GF * std::max(1, t->n_beams)))) return rc;
+    if ((rc = m->first_hit.ensure((size_t)2 * GF * std::max(1, t->n_beams)))) return rc;
+    for (int b = 0; b < 2; ++b) m->buf[b].first_hit = m->first_hit.p + (size_t)b * GF * std::max(1, t->n_beams);
     // first guess for the chunk dedupe table; it doubles on demand (retry) from here
     return ensure_scratch(m, std::min<u64>(1u << 20, std::max<u64>(1u << 14, m->samples_max / 4)), false);
 }
@@ -1591,7 +1632,7 @@ int s3d_ingest_batch(s3d_map *m, const uint8_t *images, int64_t n, const double 
     for (int64_t base = 0; base < n; base += stage) {
         const int64_t k = std::min<int64_t>(stage, n - base);
         if (base > 0 && (rc = pump(m, true))) return rc;
-        CU(cudaMemcpyAsync(m->T_dev.p, T + base * 16, sizeof(double) * 16 * (size_t)k, cudaMemcpyHostToDevice, m->stream));
+        CU(cudaMemcpyAsync(m->T_dev.p, T + base * 16, sizeof(double) * 16 * (size_t)k, cudaMemcpyHostToDevice, m->copy_stream));
         size_t ei = 0;
         for (int64_t s0 = 0; s0 < k; s0 += sub, ++ei) {
             const int64_t kk = std::min<int64_t>(sub, k - s0);
@@ -1603,7 +1644,7 @@ int s3d_ingest_batch(s3d_map *m, const uint8_t *images, int64_t n, const double 
                 CU(cudaMemcpyAsync(m->img_dev.p + (size_t)s0 * img_bytes, images + (size_t)(base + s0) * img_bytes,
                                    img_bytes * (size_t)kk, cudaMemcpyHostToDevice, m->copy_stream));
             CU(cudaEventRecord(m->copy_ev[ei], m->copy_stream));
-            CU(cudaStreamWaitEvent(m->stream, m->copy_ev[ei], 0));
+            CU(cudaStreamWaitEvent(m->xstream, m->copy_ev[ei], 0));
             if ((rc = submit_frames(m, m->img_dev.p + (size_t)s0 * img_bytes, kk, m->T_dev.p + s0 * 16, m->stats.p + base + s0))) return rc;
         }
     }
@@ -1666,7 +1707,7 @@ int s3d_shard_expand(s3d_map *m, const uint8_t *images_dev, const double *T_dev,
             a.tab = tab; a.p = m->p; a.first_hit = m->first_hit.p;
             a.skeys = m->skeys; a.scnt = m->scnt; a.smask = (u32)(m->scratch_cap - 1); a.slist = m->slist;
             a.cc = m->cc; a.stats = st; a.mc = m->mc;
-            a.seq = m->chunk_seq; a.table_limit = ~0ull;         // the owner gates growth, not the expander
+            a.seq = m->chunk_seq;                                // the owner gates growth, not the expander
             a.dbg = 0; a.beam_lo = lo; a.beam_hi = hi;
             k_expand<<<dim3((hi - lo + EX_BEAMS - 1) / EX_BEAMS, g), EX_THREADS, ex_smem, m->stream>>>(a);
             m->launches += 2;
