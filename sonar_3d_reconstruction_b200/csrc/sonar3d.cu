@@ -1,8 +1,8 @@
 // sonar3d.cu -- sm_100a kernels + C-ABI (include/sonar3d.h) of the sonar -> voxel hot path.
 //
 // Reference behaviour: luckkim123/sonar_3d_reconstruction scripts/3d_mapper.py
-//   :387-483 process_sonar_ray   -> k_first_hit + k_expand   (K1, K2+K3 of SURVEY 2.2)
-//   :485-567 process_sonar_image -> per-frame dedupe scratch + k_apply (K3, K4)
+//   :387-483 process_sonar_ray   -> k_expand (first-hit scan fused in; K1+K2+K3 of SURVEY 2.2)
+//   :485-567 process_sonar_image -> chunk dedupe table + k_apply_chunk (K3, K4)
 //   :83-115  update_voxel        -> apply_one()
 //   :117-188 queries / export    -> k_query, k_export (K5, K6)
 //
@@ -122,62 +122,7 @@ __device__ __forceinline__ u32 mix32(u64 key)
     return h;
 }
 
-// ------------------------------------------------------------------------------------ K1
-// First above-threshold range bin per processed beam (3d_mapper.py:406-409).  The image is
-// read once, row-major and coalesced (16 B per thread); per-beam minima are kept in shared
-// memory per row strip and merged with one atomicMin per (strip, beam) that found a hit.
-constexpr int FH_ROWS = 16;
-constexpr int FH_THREADS = 256;
-
-template <int VEC>
-__global__ void __launch_bounds__(FH_THREADS)
-k_first_hit(const uint8_t *__restrict__ imgs, size_t img_stride, DevTables tab, int thr,
-            int *__restrict__ first_hit)
-{
-    extern __shared__ int s_min[];   // [n_beams]
-    const int g = blockIdx.y;
-    const uint8_t *img = imgs + (size_t)g * img_stride;
-    const int H = tab.H, W = tab.W;
-    const int r0 = blockIdx.x * FH_ROWS;
-    const int r1 = min(r0 + FH_ROWS, H);
-    for (int b = threadIdx.x; b < tab.n_beams; b += FH_THREADS) s_min[b] = 0x7f7f7f7f;
-    __syncthreads();
-    const int vec_per_row = (W + VEC - 1) / VEC;
-    const int n_items = (r1 - r0) * vec_per_row;
-    for (int it = threadIdx.x; it < n_items; it += FH_THREADS) {
-        const int r = r0 + it / vec_per_row;
-        const int c0 = (it % vec_per_row) * VEC;
-        const uint8_t *p = img + (size_t)r * W + c0;
-        if (VEC == 16) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
-            const u32 w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-#pragma unroll
-                for (int bb = 0; bb < 4; ++bb) {
-                    const int px = (int)((w[q] >> (8 * bb)) & 0xffu);
-                    if (px > thr) {
-                        const int beam = tab.col_to_beam[c0 + 4 * q + bb];
-                        if (beam >= 0) atomicMin(&s_min[beam], r);
-                    }
-                }
-            }
-        } else {
-            const int px = (int)__ldg(p);
-            if (px > thr) {
-                const int beam = tab.col_to_beam[c0];
-                if (beam >= 0) atomicMin(&s_min[beam], r);
-            }
-        }
-    }
-    __syncthreads();
-    for (int b = threadIdx.x; b < tab.n_beams; b += FH_THREADS) {
-        const int m = s_min[b];
-        if (m < H) atomicMin(&first_hit[g * tab.n_beams + b], m);
-    }
-}
-
-// ------------------------------------------------------------------------------------ K2+K3
+// ------------------------------------------------------------------------------------ K1+K2+K3
 // One block per (processed beam, frame of the chunk).  The block lists the beam's range samples
 // (free: every free_step-th bin before the first hit; occupied: above-threshold bins in the
 // occ_window bins from the first hit), prefix-sums their fan sizes (2*nv+1), and its threads
@@ -193,7 +138,6 @@ struct ExpandArgs {
     const uint8_t *imgs; size_t img_stride;
     const double *T;             // [g][16]
     DevTables tab; DevParams p;
-    const int *first_hit;        // [g][n_beams]
     u64 *skeys; u64 *scnt; u32 smask;   // chunk dedupe table: keys[C], counters[C][GF]
     u32 *slist;                         // [C] slots of the entries created by this chunk, dense
     ChunkCtr *cc;
@@ -297,7 +241,7 @@ __device__ __forceinline__ bool sample_key(const ExpandArgs &a, const double *s_
     return false;
 }
 
-constexpr int EX_WBUF = 128;      // per-warp staging of created dedupe slots (flushed in bulk)
+constexpr int EX_WBUF = 64 * EX_ILP + 32;   // per-warp staging of created dedupe slots (flushed in bulk)
 
 // move the warp's staged slots to the chunk's dense list: one atomic per flush
 __device__ __forceinline__ void flush_created(const ExpandArgs &a, u32 *wbuf, int &wn, int lane)
@@ -414,8 +358,21 @@ k_expand(ExpandArgs a)
     if (beam < a.beam_hi) {
         const int col = tab.beam_col[beam];
         const double cb = tab.cos_b[beam], sb = tab.sin_b[beam];
-        int fh = a.first_hit[g * tab.n_beams + beam];
-        fh = fh < H ? fh : H;                                          // no hit -> whole ray is free (:412-413)
+        // ---- 0. first above-threshold range bin of this beam (:406-409): 128 rows per step, lanes = rows
+        int fh = H;                                                    // no hit -> whole ray is free (:412-413)
+        for (int r0 = 0; r0 < H && fh == H; r0 += 128) {
+            bool hit[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = r0 + q * 32 + lane;
+                hit[q] = r < H && (int)__ldg(&img[(size_t)r * W + col]) > a.p.thr;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const u32 mk = __ballot_sync(0xffffffffu, hit[q]);
+                if (mk && fh == H) fh = r0 + q * 32 + __ffs(mk) - 1;
+            }
+        }
         const int nfc = (fh + tab.free_step - 1) / tab.free_step;      // range(0, fh, free_step) (:420)
         const int noc = fh < H ? min(tab.occ_window, H - fh) : 0;      // range(fh, min(fh+50, H)) (:451)
         // ---- 1a. free candidates and the prefix sum of their fan sizes
@@ -1220,26 +1177,18 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     const DevTables &tab = m->tab;
     const size_t img_stride = (size_t)tab.H * tab.W;
     const uint8_t *imgs = j.imgs + (size_t)base * img_stride;
-    const bool vec16 = (tab.W % 16 == 0) && ((uintptr_t)imgs % 16 == 0) && (img_stride % 16 == 0);
     const int max_f = (tab.H + tab.free_step - 1) / tab.free_step;
     const size_t ex_smem = sizeof(int) * (size_t)EX_BEAMS * (size_t)(2 * max_f + 1 + 2 * tab.occ_window);
-    const size_t fh_smem = sizeof(int) * (size_t)tab.n_beams;
     s3d_map::ChunkBuf &cb = m->buf[m->chunk_seq & 1];
     cudaStream_t xs = m->xstream, as = m->stream;
     // ---- expand stream: first hits + expansion into this chunk's dedupe buffer.  It may run while
     // the previous chunk is still being applied; it only waits for its own buffer to be drained.
     if (cb.used) CU(cudaStreamWaitEvent(xs, cb.freed, 0));
-    const size_t e0 = m->prof_on ? prof_mark(m, xs) : 0;
-    CU(cudaMemsetAsync(cb.first_hit, 0x7f, sizeof(int) * (size_t)g * tab.n_beams, xs));
-    dim3 g1((tab.H + FH_ROWS - 1) / FH_ROWS, g);
-    if (vec16) k_first_hit<16><<<g1, FH_THREADS, fh_smem, xs>>>(imgs, img_stride, tab, m->p.thr, cb.first_hit);
-    else k_first_hit<1><<<g1, FH_THREADS, fh_smem, xs>>>(imgs, img_stride, tab, m->p.thr, cb.first_hit);
     const size_t e1 = m->prof_on ? prof_mark(m, xs) : 0;
     ExpandArgs a;
     a.imgs = imgs; a.img_stride = img_stride;
     a.T = j.T + base * 16;
     a.tab = tab; a.p = m->p;
-    a.first_hit = cb.first_hit;
     a.skeys = cb.skeys; a.scnt = cb.scnt; a.smask = (u32)(m->scratch_cap - 1); a.slist = cb.slist;
     a.cc = cb.cc; a.stats = j.stats + base; a.mc = m->mc;
     a.seq = m->chunk_seq;
@@ -1259,13 +1208,12 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     CU(cudaGetLastError());
     CU(cudaEventRecord(cb.freed, as));
     cb.used = true;
-    m->launches += 4;
+    m->launches += 3;
     if (m->prof_on) {
         const size_t e4 = prof_mark(m, as);
-        m->spans.push_back({e0, e1, S3D_K_FIRST_HIT});
         m->spans.push_back({e1, e2, S3D_K_EXPAND});
         m->spans.push_back({e3, e4, S3D_K_APPLY});
-        for (int k = 0; k < S3D_K_COUNT; ++k) m->prof.launches[k] += 1;
+        m->prof.launches[S3D_K_EXPAND] += 1; m->prof.launches[S3D_K_APPLY] += 1;
         m->prof.frames += (u64)g;
     }
     const int ri = (int)(m->chunk_seq % s3d_map::RING);
@@ -1694,23 +1642,17 @@ int s3d_shard_expand(s3d_map *m, const uint8_t *images_dev, const double *T_dev,
         CU(cudaMemsetAsync(st, 0, sizeof(DevStats) * (size_t)g, m->stream));
         u32 n_unique = 0;
         if (tab.n_beams > 0 && tab.H > 0 && hi > lo) {
-            const bool vec16 = (tab.W % 16 == 0) && ((uintptr_t)images_dev % 16 == 0) && (img_stride % 16 == 0);
             const int max_f = (tab.H + tab.free_step - 1) / tab.free_step;
             const size_t ex_smem = sizeof(int) * (size_t)EX_BEAMS * (size_t)(2 * max_f + 1 + 2 * tab.occ_window);
-            const size_t fh_smem = sizeof(int) * (size_t)tab.n_beams;
-            CU(cudaMemsetAsync(m->first_hit.p, 0x7f, sizeof(int) * (size_t)g * tab.n_beams, m->stream));
-            dim3 g1((tab.H + FH_ROWS - 1) / FH_ROWS, g);
-            if (vec16) k_first_hit<16><<<g1, FH_THREADS, fh_smem, m->stream>>>(images_dev, img_stride, tab, m->p.thr, m->first_hit.p);
-            else k_first_hit<1><<<g1, FH_THREADS, fh_smem, m->stream>>>(images_dev, img_stride, tab, m->p.thr, m->first_hit.p);
             ExpandArgs a;
             a.imgs = images_dev; a.img_stride = img_stride; a.T = T_dev;
-            a.tab = tab; a.p = m->p; a.first_hit = m->first_hit.p;
+            a.tab = tab; a.p = m->p;
             a.skeys = m->skeys; a.scnt = m->scnt; a.smask = (u32)(m->scratch_cap - 1); a.slist = m->slist;
             a.cc = m->cc; a.stats = st; a.mc = m->mc;
             a.seq = m->chunk_seq;                                // the owner gates growth, not the expander
             a.dbg = 0; a.beam_lo = lo; a.beam_hi = hi;
             k_expand<<<dim3((hi - lo + EX_BEAMS - 1) / EX_BEAMS, g), EX_THREADS, ex_smem, m->stream>>>(a);
-            m->launches += 2;
+            m->launches += 1;
         }
         // counts per owner -> host (the all-to-all needs the split sizes), and the retry flag
         CU(cudaMemsetAsync(m->owner_ctr.p, 0, sizeof(u32) * 3 * 64, m->stream));
