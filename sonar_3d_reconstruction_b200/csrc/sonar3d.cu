@@ -596,35 +596,36 @@ k_apply_chunk(u64 *__restrict__ skeys, u64 *__restrict__ scnt, const u32 *__rest
     const u32 abort = __ldcg(&mc->abort);
     const u32 n_live = __ldcg(&cc->n_unique);
     if (abort) return;
-    const u32 i = blockIdx.x * AP_THREADS + threadIdx.x;
-    const bool live = i < n_live;
+    // blocks past the live entries leave at once; the rest stride over the list
+    const u32 live_blocks = max(1u, min((u32)gridDim.x, (n_live + AP_THREADS - 1) / AP_THREADS));
+    if (blockIdx.x >= live_blocks) return;
     const u32 lane = threadIdx.x & 31;
-    // entry -> registers; the loads are issued before anything waits on them
-    u64 key = 0; u32 s = 0;
-    ulonglong2 c2[GF / 2];
-#pragma unroll
-    for (int q = 0; q < GF / 2; ++q) c2[q] = make_ulonglong2(0ull, 0ull);
-    if (live) {
-        s = __ldcs(&slist[i]);
-        key = __ldcg(&skeys[s]);
-        const ulonglong2 *cp = reinterpret_cast<const ulonglong2 *>(scnt + (size_t)s * GF);
-#pragma unroll
-        for (int q = 0; q < GF / 2; ++q) c2[q] = __ldcg(cp + q);
-    }
     if (threadIdx.x < GF) { s_occ[threadIdx.x] = 0; s_free[threadIdx.x] = 0; s_new[threadIdx.x] = 0; }
     for (int q = threadIdx.x; q < 4 * SUMT; q += AP_THREADS) (&s_sum[0][0])[q] = sum_tab[q];
     __syncthreads();
-    if (blockIdx.x * AP_THREADS < n_live) {             // block-uniform
+    u32 w_occ = 0, w_free = 0, w_new = 0;          // lane f of each warp accumulates frame f
+    LocalAcc acc; acc_init(acc);
+    for (u32 base = blockIdx.x * AP_THREADS; base < n_live; base += live_blocks * AP_THREADS) {   // block-uniform
+        const u32 i = base + threadIdx.x;
+        const bool live = i < n_live;
+        // entry -> registers; the loads are issued before anything waits on them
+        u64 key = 0; u32 s = 0;
+        ulonglong2 c2[GF / 2];
+#pragma unroll
+        for (int q = 0; q < GF / 2; ++q) c2[q] = make_ulonglong2(0ull, 0ull);
         u64 slot = ~0ull; bool fresh = false; double L = 0.0;
         if (live) {
+            s = __ldcs(&slist[i]);
+            key = __ldcg(&skeys[s]);
+            ulonglong2 *cp = reinterpret_cast<ulonglong2 *>(scnt + (size_t)s * GF);
+#pragma unroll
+            for (int q = 0; q < GF / 2; ++q) c2[q] = __ldcg(cp + q);
             slot = table_find_or_insert(table, tmask, key, fresh, L);
             if (slot == ~0ull) atomicOr(&mc->err, ERR_TABLEFULL);
             skeys[s] = EMPTY_KEY;                                   // entry is ready for the next chunk
-            ulonglong2 *cp = reinterpret_cast<ulonglong2 *>(scnt + (size_t)s * GF);
 #pragma unroll
             for (int q = 0; q < GF / 2; ++q) cp[q] = make_ulonglong2(0ull, 0ull);
         }
-        u32 w_occ = 0, w_free = 0, w_new = 0;          // lane f of each warp accumulates frame f
         bool pending_new = fresh;
 #pragma unroll
         for (int f = 0; f < GF; ++f) {
@@ -638,34 +639,33 @@ k_apply_chunk(u64 *__restrict__ skeys, u64 *__restrict__ scnt, const u32 *__rest
                 const u32 b_free = __ballot_sync(0xffffffffu, hit && !occ_typed);
                 const u32 b_new = __ballot_sync(0xffffffffu, hit && pending_new);
                 if (hit) pending_new = false;
-                if (lane == (u32)f) { w_occ = __popc(b_occ); w_free = __popc(b_free); w_new = __popc(b_new); }
+                if (lane == (u32)f) { w_occ += __popc(b_occ); w_free += __popc(b_free); w_new += __popc(b_new); }
             }
         }
-        LocalAcc acc; acc_init(acc);
         if (live && slot != ~0ull) {
             table[slot].val = L;
             acc_key(acc, key);
         }
-        acc_publish(acc, mc, false);
-        if (lane < GF) {
-            if (w_occ) atomicAdd(&s_occ[lane], w_occ);
-            if (w_free) atomicAdd(&s_free[lane], w_free);
-            if (w_new) atomicAdd(&s_new[lane], w_new);
-        }
-        __syncthreads();
-        if (threadIdx.x < g) {
-            const int f = threadIdx.x;
-            if (s_occ[f]) atomicAdd(&st[f].n_occ, (u64)s_occ[f]);
-            if (s_free[f]) atomicAdd(&st[f].n_free, (u64)s_free[f]);
-            if (s_new[f]) atomicAdd(&cc->neu[f], s_new[f]);
-        }
     }
-    // last block out: len(voxels) after each frame (:592), publish the new count, re-arm the chunk
+    acc_publish(acc, mc, false);
+    if (lane < GF) {
+        if (w_occ) atomicAdd(&s_occ[lane], w_occ);
+        if (w_free) atomicAdd(&s_free[lane], w_free);
+        if (w_new) atomicAdd(&s_new[lane], w_new);
+    }
+    __syncthreads();
+    if (threadIdx.x < g) {
+        const int f = threadIdx.x;
+        if (s_occ[f]) atomicAdd(&st[f].n_occ, (u64)s_occ[f]);
+        if (s_free[f]) atomicAdd(&st[f].n_free, (u64)s_free[f]);
+        if (s_new[f]) atomicAdd(&cc->neu[f], s_new[f]);
+    }
+    // last live block out: len(voxels) after each frame (:592), publish the new count, re-arm the chunk
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         const u32 t = atomicAdd(&cc->ticket, 1u);
-        s_last = (t == gridDim.x - 1);
+        s_last = (t == live_blocks - 1);
     }
     __syncthreads();
     if (s_last && threadIdx.x == 0) {
@@ -975,6 +975,7 @@ struct s3d_map {
     int shard_rank = 0, shard_world = 1, beam_lo = 0, beam_hi = -1;
     DevBuf<u64> send_buf; DevBuf<u32> owner_ctr;      // owner_ctr: [3][64] count / base / fill
     u32 *owner_host = nullptr;                        // pinned [64]
+    int l2_policy = 0;               // S3D_L2_POLICY: 0 = no window, 1 = persisting + streaming misses, 2 = persisting + normal
     int dbg_stage = 0;               // S3D_DEBUG_STAGE: stage-ablation timing experiments (tools/dbg_stage.sh)
     // params / tables
     bool have_params = false, have_tables = false;
@@ -1143,7 +1144,7 @@ int ensure_scratch(s3d_map *m, u64 want_cap, bool wipe)
         m->scratch_cap = want_cap;
         // The dedupe table is hit by every sample of a chunk and re-read by the apply kernel:
         // ask L2 to keep it (persisting window) while images and voxel-table traffic stream by.
-        if (m->l2_persist_max > 0 && m->l2_window_max > 0) {
+        if (m->l2_persist_max > 0 && m->l2_window_max > 0 && m->l2_policy > 0) {
             const size_t win = std::min(pool, m->l2_window_max);
             const size_t carve = std::min(win, m->l2_persist_max);
             CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
@@ -1152,7 +1153,7 @@ int ensure_scratch(s3d_map *m, u64 want_cap, bool wipe)
             av.accessPolicyWindow.num_bytes = win;
             av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)win);
             av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            av.accessPolicyWindow.missProp = m->l2_policy == 1 ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
             CU(cudaStreamSetAttribute(m->stream, cudaStreamAttributeAccessPolicyWindow, &av));
             CU(cudaStreamSetAttribute(m->xstream, cudaStreamAttributeAccessPolicyWindow, &av));
             m->l2_window = win;
@@ -1202,7 +1203,8 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     const size_t e3 = m->prof_on ? prof_mark(m, as) : 0;
     k_gate<<<1, 1, 0, as>>>(cb.cc, m->mc, table_limit(m), m->chunk_seq);
     // one thread per dedupe entry the chunk can have created; blocks past the live count exit at once
-    const int ap_blocks = (int)((m->scratch_cap + AP_THREADS - 1) / AP_THREADS);
+    const u64 ap_want = std::max<u64>((u64)m->n_sm * 4, (m->unique_est + m->unique_est / 4) / AP_THREADS + 1);
+    const int ap_blocks = (int)std::min<u64>((m->scratch_cap + AP_THREADS - 1) / AP_THREADS, ap_want);
     k_apply_chunk<<<ap_blocks, AP_THREADS, 0, as>>>(cb.skeys, cb.scnt, cb.slist, g, cb.cc, j.stats + base, m->table,
                                                   m->cap - 1, m->p, m->sum_tab.p, m->mc);
     CU(cudaGetLastError());
@@ -1281,7 +1283,7 @@ int pump(s3d_map *m, bool drain)
             }
             // grow ahead of the gate when the chunks in flight could reach it (saves a retry)
             if (m->count_known + (u64)(LOOKAHEAD + 2) * m->unique_est > table_limit(m) ||
-                2 * m->unique_est > m->scratch_cap) {
+                3 * m->unique_est > 2 * m->scratch_cap) {
                 CU(cudaMemcpyAsync(m->mc_host, m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, m->stream));
                 CU(cudaStreamSynchronize(m->stream));
                 if (m->mc_host->abort) { int rc = recover(m); if (rc) return rc; continue; }
@@ -1290,7 +1292,7 @@ int pump(s3d_map *m, bool drain)
                 int rc;
                 if (m->count_known + (u64)(LOOKAHEAD + 2) * m->unique_est > table_limit(m) &&
                     (rc = grow_table(m, m->cap * 2))) return rc;
-                if (2 * m->unique_est > m->scratch_cap && (rc = ensure_scratch(m, m->scratch_cap * 2, false))) return rc;
+                if (3 * m->unique_est > 2 * m->scratch_cap && (rc = ensure_scratch(m, m->scratch_cap * 2, false))) return rc;
             }
             const int g = (int)std::min<int64_t>(GF, job->n - job->next);
             if (m->prof_on && m->ev_used > 4096) { int rc = prof_collect(m); if (rc) return rc; }
@@ -1396,6 +1398,7 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
     CU(cudaGetDeviceProperties(&prop, device));
     m->n_sm = prop.multiProcessorCount;
     { const char *e = getenv("S3D_DEBUG_STAGE"); m->dbg_stage = e ? atoi(e) : 0; }
+    { const char *e = getenv("S3D_L2_POLICY"); if (e) m->l2_policy = atoi(e); }
     m->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     m->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
@@ -1581,6 +1584,8 @@ int s3d_ingest_batch(s3d_map *m, const uint8_t *images, int64_t n, const double 
         const int64_t k = std::min<int64_t>(stage, n - base);
         if (base > 0 && (rc = pump(m, true))) return rc;
         CU(cudaMemcpyAsync(m->T_dev.p, T + base * 16, sizeof(double) * 16 * (size_t)k, cudaMemcpyHostToDevice, m->copy_stream));
+        // all copies of this stage are queued first (they run back to back on the copy stream),
+        // then the frames are submitted piece by piece, each behind the event of its own copy
         size_t ei = 0;
         for (int64_t s0 = 0; s0 < k; s0 += sub, ++ei) {
             const int64_t kk = std::min<int64_t>(sub, k - s0);
@@ -1592,6 +1597,10 @@ int s3d_ingest_batch(s3d_map *m, const uint8_t *images, int64_t n, const double 
                 CU(cudaMemcpyAsync(m->img_dev.p + (size_t)s0 * img_bytes, images + (size_t)(base + s0) * img_bytes,
                                    img_bytes * (size_t)kk, cudaMemcpyHostToDevice, m->copy_stream));
             CU(cudaEventRecord(m->copy_ev[ei], m->copy_stream));
+        }
+        ei = 0;
+        for (int64_t s0 = 0; s0 < k; s0 += sub, ++ei) {
+            const int64_t kk = std::min<int64_t>(sub, k - s0);
             CU(cudaStreamWaitEvent(m->xstream, m->copy_ev[ei], 0));
             if ((rc = submit_frames(m, m->img_dev.p + (size_t)s0 * img_bytes, kk, m->T_dev.p + s0 * 16, m->stats.p + base + s0))) return rc;
         }

@@ -407,12 +407,42 @@ class SonarTo3DMapper:
             'avg_processing_time': self.total_processing_time / max(1, self.processed_frame_count),
         }
 
-    def compose_transforms(self, positions, orientations) -> np.ndarray:
-        """T_sonar_to_world for each pose, float64[n,4,4], evaluated as the per-frame path does."""
+    def _compose_scalar(self, positions, orientations) -> np.ndarray:
         out = np.empty((len(positions), 4, 4))
         for f in range(len(positions)):
             out[f] = self.create_odometry_transform(positions[f], orientations[f]) @ self.T_sonar_to_base
         return out
+
+    def _compose_vector(self, positions, orientations) -> np.ndarray:
+        """The same expressions as quaternion_to_matrix / create_odometry_transform (:346-380) and
+        the :521 product, evaluated for all poses at once."""
+        p = np.asarray(positions, dtype=np.float64).reshape(-1, 3)
+        q = np.asarray(orientations, dtype=np.float64).reshape(-1, 4)
+        x, y, z, w = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        Tb = np.zeros((len(p), 4, 4))
+        Tb[:, 0, 0] = 1 - 2 * (y**2 + z**2); Tb[:, 0, 1] = 2 * (x * y - w * z); Tb[:, 0, 2] = 2 * (x * z + w * y)
+        Tb[:, 1, 0] = 2 * (x * y + w * z); Tb[:, 1, 1] = 1 - 2 * (x**2 + z**2); Tb[:, 1, 2] = 2 * (y * z - w * x)
+        Tb[:, 2, 0] = 2 * (x * z - w * y); Tb[:, 2, 1] = 2 * (y * z + w * x); Tb[:, 2, 2] = 1 - 2 * (x**2 + y**2)
+        Tb[:, :3, 3] = p
+        Tb[:, 3, 3] = 1.0
+        return np.matmul(Tb, self.T_sonar_to_base)
+
+    def compose_transforms(self, positions, orientations) -> np.ndarray:
+        """T_sonar_to_world for each pose, float64[n,4,4], bit-identical to what the per-frame path
+        computes.  The all-at-once evaluation is used only after it has been checked, on this
+        host and for this mount transform, to reproduce the pose-by-pose evaluation bit for bit
+        (numpy hands the 4x4 products to BLAS, whose rounding is build- and CPU-specific)."""
+        key = self.T_sonar_to_base.tobytes()
+        if getattr(self, "_vector_ok_for", None) != key:
+            rng = np.random.default_rng(12345)
+            tp = rng.normal(size=(64, 3)) * 7.0
+            tq = rng.normal(size=(64, 4))
+            tq[:32] /= np.linalg.norm(tq[:32], axis=1, keepdims=True)
+            self._vector_ok = bool(np.array_equal(self._compose_vector(tp, tq), self._compose_scalar(tp, tq)))
+            self._vector_ok_for = key
+        if self._vector_ok and len(positions) > 1:
+            return self._compose_vector(positions, orientations)
+        return self._compose_scalar(positions, orientations)
 
     def process_sonar_images(self, polar_images: np.ndarray, robot_positions, robot_orientations
                              ) -> List[Dict[str, Any]]:

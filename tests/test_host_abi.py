@@ -138,3 +138,26 @@ def test_synthetic_generator_shapes_and_determinism():
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert np.allclose(np.linalg.norm(a[2], axis=1), 1.0)
     assert (a[0] > a[3]["intensity_threshold"]).any()
+
+
+def test_vectorised_pose_composition_is_bit_identical_or_disabled():
+    """compose_transforms may evaluate all poses at once only where that reproduces the
+    pose-by-pose evaluation (scripts/3d_mapper.py:346-380, :521) bit for bit."""
+    from sonar_3d_reconstruction_b200 import synthetic
+    from sonar_3d_reconstruction_b200.mapper import SonarTo3DMapper as M
+
+    class Host:
+        quaternion_to_matrix = M.quaternion_to_matrix
+        create_odometry_transform = M.create_odometry_transform
+        _compose_scalar = M._compose_scalar
+        _compose_vector = M._compose_vector
+        compose_transforms = M.compose_transforms
+
+    h = Host()
+    h.T_sonar_to_base = M.create_transform_matrix(h, np.array([0.0, 0.0, -0.1]), np.array([0.0, np.radians(60.0), 0.0]))
+    pos, quat = synthetic.make_poses(np.random.default_rng(3), 700)
+    want = h._compose_scalar(pos, quat)
+    got = h.compose_transforms(pos, quat)
+    assert np.array_equal(got, want)                 # whichever path was chosen, the result is the scalar one
+    one = h.compose_transforms(pos[:1], quat[:1])
+    assert np.array_equal(one[0], want[0])

@@ -48,6 +48,12 @@ class _HostMapper:
     def compose_transforms(self, ps, qs):
         return self._M.compose_transforms(self, ps, qs)
 
+    def _compose_scalar(self, ps, qs):
+        return self._M._compose_scalar(self, ps, qs)
+
+    def _compose_vector(self, ps, qs):
+        return self._M._compose_vector(self, ps, qs)
+
     def _check_width(self, w):
         return self._M._check_width(self, w)
 
