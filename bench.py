@@ -228,7 +228,8 @@ def run_gpu(args, rank, world, local_rank):
     del mapper, native
     if args.no_e2e:
         e2e_s, e2e_steps = float("nan"), 0
-    mapper2 = SonarTo3DMapper(cfg) if not args.no_e2e else None
+    # same table pre-sizing as the device-resident arm (`table_capacity` is a constructor option)
+    mapper2 = SonarTo3DMapper(dict(cfg, table_capacity=cap)) if not args.no_e2e else None
     if not args.no_e2e:
         pin = torch.from_numpy(images).pin_memory()
         images_pinned = pin.numpy()
