@@ -182,6 +182,12 @@ int s3d_export_read_xyzi32(s3d_map *map, float *xyzi, uint64_t n);
 #define S3D_CHUNK_FRAMES 16
 
 int s3d_shard_config(s3d_map *map, int rank, int world);
+/* Replicated expansion (the alternative to routing): with the filter on, s3d_ingest* on every rank
+ * expands ALL beams of every frame but keeps only the samples whose voxel this rank owns.  No
+ * exchange is needed -- each rank ends up with exactly the per-voxel counts of its shard -- at
+ * the price of repeating the (cheap) expansion arithmetic on every rank.  Counters returned by
+ * s3d_ingest* are then per-shard partials (sum over ranks = the reference's counters). */
+int s3d_shard_filter(s3d_map *map, int on);
 /* owner rank of each key (host helper; same function the device uses) */
 int s3d_shard_owner(const int32_t *ijk, int64_t n, int world, int32_t *owner);
 /* Expand g <= 16 frames (device-resident images / transforms) on this rank's beam slice and

@@ -18,7 +18,7 @@ SYMBOLS = (
     "s3d_apply_updates", "s3d_query", "s3d_count", "s3d_dump", "s3d_load", "s3d_clear", "s3d_bounds",
     "s3d_capacity", "s3d_export_begin", "s3d_export_read", "s3d_export_read_xyzi32",
     "s3d_profile_enable", "s3d_profile_read",
-    "s3d_shard_config", "s3d_shard_owner", "s3d_shard_expand", "s3d_shard_apply",
+    "s3d_shard_config", "s3d_shard_filter", "s3d_shard_owner", "s3d_shard_expand", "s3d_shard_apply",
 )
 
 
@@ -101,6 +101,7 @@ def load_library():
     L.s3d_profile_enable.argtypes = [vp, C.c_int]
     L.s3d_profile_read.argtypes = [vp, C.POINTER(Profile)]
     L.s3d_shard_config.argtypes = [vp, C.c_int, C.c_int]
+    L.s3d_shard_filter.argtypes = [vp, C.c_int]
     L.s3d_shard_owner.argtypes = [i32p, C.c_int64, C.c_int, i32p]
     L.s3d_shard_expand.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(vp), u64p]
     L.s3d_shard_apply.argtypes = [vp, vp, C.c_uint64, C.c_int, vp]
@@ -208,6 +209,9 @@ class NativeMap:
     def shard_config(self, rank: int, world: int):
         _check(self._lib.s3d_shard_config(self._h, int(rank), int(world)))
         self._world = int(world)
+
+    def shard_filter(self, on: bool):
+        _check(self._lib.s3d_shard_filter(self._h, int(bool(on))))
 
     def shard_expand(self, images_ptr: int, T_ptr: int, g: int, stats_dev_ptr: int):
         """-> (device pointer of the packed records, [count per owner])"""

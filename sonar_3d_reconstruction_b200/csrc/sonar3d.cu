@@ -112,6 +112,9 @@ __device__ __forceinline__ bool voxel_index(double w, double res, double inv_res
     return true;
 }
 
+// owning rank of a voxel when the map is sharded over `world` GPUs
+__device__ __forceinline__ u32 key_owner(u64 key, u32 world) { return (u32)((mix64(key) >> 40) % world); }
+
 // cheap 32-bit mix for the chunk dedupe table (the voxel table keeps the stronger mix64)
 __device__ __forceinline__ u32 mix32(u64 key)
 {
@@ -144,6 +147,7 @@ struct ExpandArgs {
     DevStats *stats;             // [g]
     MapCtr *mc;
     int beam_lo, beam_hi;        // processed beams [beam_lo, beam_hi) are expanded (a rank's slice when sharded)
+    u32 own_rank, own_world;     // own_world > 1: keep only samples whose voxel this rank owns (replicated expansion)
     int dbg;                     // S3D_DEBUG_STAGE (timing experiments only): 1 = no dedupe, 2 = probe only
     u64 seq;                     // chunk sequence number (for abort bookkeeping)
 };
@@ -230,13 +234,16 @@ __device__ __forceinline__ bool sample_key(const ExpandArgs &a, const double *s_
         wv[q] = __dadd_rn(__dadd_rn(__dmul_rn(s_T[4 * q], xs), __dmul_rn(s_T[4 * q + 2], zs)),
                           __dadd_rn(__dmul_rn(s_T[4 * q + 1], ys), s_T[4 * q + 3]));
     if (a.p.zfilter && wv[2] < a.p.zmin) return false;      // :443, :478
-    ++emitted;
     int ki, kj, kk;
     if (voxel_index(wv[0], a.p.res, a.p.inv_res, ki) && voxel_index(wv[1], a.p.res, a.p.inv_res, kj) &&
         voxel_index(wv[2], a.p.res, a.p.inv_res, kk)) {
         key = pack_key(ki, kj, kk);
+        // replicated expansion: every rank computes every sample and keeps the voxels it owns
+        if (a.own_world > 1 && key_owner(key, a.own_world) != a.own_rank) return false;
+        ++emitted;
         return true;
     }
+    ++emitted;
     atomicOr(&a.mc->err, ERR_KEYRANGE);
     return false;
 }
@@ -691,8 +698,6 @@ k_apply_chunk(u64 *__restrict__ skeys, u64 *__restrict__ scnt, const u32 *__rest
 // beams were split) before the ordinary apply kernel runs on its shard of the table.
 constexpr int REC_WORDS = 1 + GF;
 
-__device__ __forceinline__ u32 key_owner(u64 key, u32 world) { return (u32)((mix64(key) >> 40) % world); }
-
 // pass 1: how many of the chunk's dedupe entries go to each owner
 __global__ void k_shard_count(const u64 *__restrict__ skeys, const u32 *__restrict__ slist, const ChunkCtr *cc,
                               u32 world, u32 *owner_count)
@@ -973,6 +978,7 @@ struct s3d_map {
     u64 n_retries = 0, n_grows = 0;
     // sharded map (multi-GPU): this rank's identity and beam slice, exchange staging
     int shard_rank = 0, shard_world = 1, beam_lo = 0, beam_hi = -1;
+    bool shard_filter = false;       // replicated expansion: s3d_ingest* keeps only the voxels this rank owns
     DevBuf<u64> send_buf; DevBuf<u32> owner_ctr;      // owner_ctr: [3][64] count / base / fill
     u32 *owner_host = nullptr;                        // pinned [64]
     int l2_policy = 0;               // S3D_L2_POLICY: 0 = no window, 1 = persisting + streaming misses, 2 = persisting + normal
@@ -1195,6 +1201,7 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     a.seq = m->chunk_seq;
     a.dbg = m->dbg_stage;
     a.beam_lo = 0; a.beam_hi = tab.n_beams;
+    a.own_rank = (u32)m->shard_rank; a.own_world = m->shard_filter ? (u32)m->shard_world : 1u;
     k_expand<<<dim3((tab.n_beams + EX_BEAMS - 1) / EX_BEAMS, g), EX_THREADS, ex_smem, xs>>>(a);
     const size_t e2 = m->prof_on ? prof_mark(m, xs) : 0;
     CU(cudaEventRecord(cb.expanded, xs));
@@ -1624,6 +1631,15 @@ int s3d_shard_config(s3d_map *m, int rank, int world)
     return m->owner_ctr.ensure(3 * 64);
 }
 
+int s3d_shard_filter(s3d_map *m, int on)
+{
+    if (!m) return fail(S3D_EINVAL, "null map");
+    int rc = set_device(m); if (rc) return rc;
+    if ((rc = sync_counters(m))) return rc;
+    m->shard_filter = on != 0;
+    return 0;
+}
+
 int s3d_shard_owner(const int32_t *ijk, int64_t n, int world, int32_t *owner)
 {
     if (world < 1) return fail(S3D_EINVAL, "world < 1");
@@ -1660,6 +1676,7 @@ int s3d_shard_expand(s3d_map *m, const uint8_t *images_dev, const double *T_dev,
             a.cc = m->cc; a.stats = st; a.mc = m->mc;
             a.seq = m->chunk_seq;                                // the owner gates growth, not the expander
             a.dbg = 0; a.beam_lo = lo; a.beam_hi = hi;
+            a.own_rank = 0; a.own_world = 1;
             k_expand<<<dim3((hi - lo + EX_BEAMS - 1) / EX_BEAMS, g), EX_THREADS, ex_smem, m->stream>>>(a);
             m->launches += 1;
         }

@@ -1,12 +1,19 @@
 """Voxel map sharded across the GPUs of one node (one process per GPU).
 
 The reference has no distributed code; this is the B200-native scaling of its hot path.  The
-map shards by a hash of the voxel key (`owner_of_keys`).  Every rank sees every frame, expands
-its slice of the processed beams into per-(voxel, frame) integer counts, the counts travel to
-the owning rank in one variable-size all-to-all per chunk of 16 frames (NCCL over
-NVLink/NVSwitch through torch.distributed; gloo works for CPU tests), and the owner merges them
-by integer addition and applies the chunk's frames in order to its shard.  Because the merge is
-an integer sum, the N-rank map is identical to the 1-rank map, voxel for voxel.
+map shards by a hash of the voxel key (`owner_of_keys`); every rank sees every frame.  Two modes:
+
+* ``mode="route"`` -- each rank expands its slice of the processed beams into per-(voxel, frame)
+  integer counts, the counts travel to the owning rank in one variable-size all-to-all per chunk
+  of 16 frames (NCCL over NVLink/NVSwitch through torch.distributed; gloo works for CPU tests),
+  and the owner merges them by integer addition and applies the chunk's frames in order.
+* ``mode="replicate"`` (default) -- each rank expands ALL beams but keeps only the samples whose
+  voxel it owns, so its dedupe table already holds exactly its shard's counts and no exchange is
+  needed; the cheap expansion arithmetic is repeated on every rank, the hash-table work (the
+  expensive part, see profiles/README.md) and the voxel table are split N ways, and the rank-local
+  pipeline stays fully asynchronous.  Only the per-frame counters are all-reduced, once per call.
+
+Either way the merge is an integer sum, so the N-rank map is identical to the 1-rank map.
 
 `ShardedSonarMapper` keeps the reference's method names (process_sonar_image,
 get_point_cloud, reset_map); every rank must call them collectively with the same arguments.
@@ -174,6 +181,24 @@ class CudaShardBackend:
         self.native.shard_config(rank, world)
         self.world = world
 
+    def set_mode(self, mode: str):
+        self.native.shard_filter(mode == "replicate" and self.world > 1)
+
+    def ingest_owned_dev(self, d_img, d_T):
+        """replicate mode, inputs on the device: per-shard counters int64[n, 4] (device tensor)."""
+        t = self.torch
+        n = int(d_img.shape[0])
+        st = t.empty((n, 4), dtype=t.int64, device=self.device)
+        self.native.ingest_batch_dev(d_img.data_ptr(), n, d_T.data_ptr(), want_stats=False, stats_dev_ptr=st.data_ptr())
+        self.native.sync()
+        return st
+
+    def ingest_owned_host(self, images: np.ndarray, T: np.ndarray):
+        """replicate mode, host inputs (copies overlap the kernels inside the library)."""
+        st = self.native.ingest_batch(np.ascontiguousarray(images), T)
+        arr = np.stack([st["num_occupied"], st["num_free"], st["num_voxels"], st["num_samples"]], axis=1)
+        return self.torch.from_numpy(arr.astype(np.int64)).to(self.device)
+
     def upload(self, images: np.ndarray, T: np.ndarray):
         t = self.torch
         return (t.from_numpy(np.ascontiguousarray(images)).to(self.device, non_blocking=False),
@@ -222,7 +247,11 @@ class ShardedSonarMapper:
     Collective: every rank constructs it with the same config and calls every method with the
     same arguments.  `group=None` means a single rank (no torch.distributed needed)."""
 
-    def __init__(self, config: Optional[Dict[str, Any]] = None, group=None, backend_factory=None):
+    def __init__(self, config: Optional[Dict[str, Any]] = None, group=None, backend_factory=None,
+                 mode: str = "replicate"):
+        if mode not in ("replicate", "route"):
+            raise ValueError("mode must be 'replicate' or 'route'")
+        self.mode = mode
         self.ex = Exchange(group)
         self.rank, self.world = self.ex.rank, self.ex.world
         if backend_factory is None:
@@ -231,6 +260,7 @@ class ShardedSonarMapper:
             self.backend = CudaShardBackend(self.mapper, self.rank, self.world)
         else:
             self.mapper, self.backend = backend_factory(config, self.rank, self.world)
+        self.backend.set_mode(mode)
         self.frame_count = 0
         self.processed_frame_count = 0
         self.total_processing_time = 0.0
@@ -251,6 +281,10 @@ class ShardedSonarMapper:
         m._check_width(W)
         T = m.compose_transforms(robot_positions, robot_orientations)
         m._sync_device_config(H, W)
+        if self.mode == "replicate":
+            stats = self.ex.all_reduce_sum(self.backend.ingest_owned_host(polar_images, T))
+            self.last_exchange_bytes = 0
+            return self._finish(stats, n, t0)
         d_img, d_T = self.backend.upload(polar_images, T)
         return self._finish(self.process_device_batch(d_img, d_T), n, t0)
 
@@ -260,6 +294,9 @@ class ShardedSonarMapper:
         num_occupied, num_free, num_voxels, num_samples."""
         import torch
         n = int(d_img.shape[0])
+        if self.mode == "replicate":
+            self.last_exchange_bytes = 0
+            return self.ex.all_reduce_sum(self.backend.ingest_owned_dev(d_img, d_T))
         samples, applied = [], []
         self.last_exchange_bytes = 0
         for f0 in range(0, n, CHUNK_FRAMES):

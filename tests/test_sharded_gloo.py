@@ -76,6 +76,30 @@ class _OracleBackend:
     def upload(self, images, T):
         return images, np.asarray(T, dtype=np.float64).reshape(-1, 16)
 
+    def set_mode(self, mode):
+        self.mode = mode
+
+    def ingest_owned_dev(self, imgs, T):
+        """replicate mode: expand every beam, keep the records this rank owns, apply them."""
+        from sonar_3d_reconstruction_b200 import sharded as S
+        rank, world = self.rank, self.world
+        out = []
+        for f0 in range(0, len(imgs), S.CHUNK_FRAMES):
+            g = min(S.CHUNK_FRAMES, len(imgs) - f0)
+            self.rank, self.world = 0, 1                      # expand all beams, all owners
+            rec, _, _ = self.expand(imgs, T, f0, g)
+            self.rank, self.world = rank, world
+            r = rec.numpy()
+            mine = S.owner_of_packed(r[:, 0].astype(np.uint64), world) == rank if len(r) else np.zeros(0, bool)
+            own = r[mine]
+            st = self.apply(torch.from_numpy(own), g)
+            n_samp = np.array([int(((own[:, 1 + f] >> 32) + (own[:, 1 + f] & 0xFFFFFFFF)).sum()) for f in range(g)])
+            out.append(torch.cat([st, torch.from_numpy(n_samp)[:, None]], dim=1))
+        return torch.cat(out, dim=0)
+
+    def ingest_owned_host(self, images, T):
+        return self.ingest_owned_dev(images, np.asarray(T, dtype=np.float64).reshape(-1, 16))
+
     def expand(self, imgs, T, f0, g):
         from sonar_3d_reconstruction_b200 import sharded as S
         W = imgs.shape[2]
@@ -153,7 +177,7 @@ def _factory(config, rank, world):
     return _HostMapper(config), _OracleBackend(config, rank, world)
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, mode):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -163,7 +187,7 @@ def _worker(rank, world, port, out_dir):
     from sonar_3d_reconstruction_b200.sharded import ShardedSonarMapper
     spec = dict(H=90, W=48, config=dict(voxel_resolution=0.12, intensity_threshold=40, max_range=6.0), step_m=0.04)
     images, pos, quat, cfg = synthetic.make_sequence(spec, 19, seed=5)      # 19 frames: a full chunk + a ragged one
-    m = ShardedSonarMapper(cfg, group=dist.group.WORLD, backend_factory=_factory)
+    m = ShardedSonarMapper(cfg, group=dist.group.WORLD, backend_factory=_factory, mode=mode)
     stats = m.process_sonar_images(images, pos, quat)
     keys, L = m.gather_map()
     pc = m.get_point_cloud()
@@ -176,9 +200,10 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_gloo_equals_single_rank_oracle(tmp_path):
+@pytest.mark.parametrize("mode", ["route", "replicate"])
+def test_two_rank_gloo_equals_single_rank_oracle(tmp_path, mode):
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), mode), nprocs=world, join=True)
     z = np.load(tmp_path / "sharded.npz")
     from oracle.oracle import OracleMapper
     from sonar_3d_reconstruction_b200 import synthetic
@@ -198,7 +223,7 @@ def test_two_rank_gloo_equals_single_rank_oracle(tmp_path):
     a = sort_by_key(np.floor(z["pc_points"] / res), z["pc_prob"])
     b = sort_by_key(np.floor(pc["points"] / res), pc["probabilities"])
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
-    assert int(z["exch"]) > 0
+    assert (int(z["exch"]) > 0) == (mode == "route")
 
 
 def test_owner_hash_and_key_packing_match_the_library():

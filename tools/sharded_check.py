@@ -29,21 +29,26 @@ def main():
     n = int(os.environ.get("S3D_CHECK_FRAMES", "70"))
     images, pos, quat, cfg = synthetic.make_sequence("cfg2", n, seed=2)
     cfg = dict(cfg, device=local)
-    sh = ShardedSonarMapper(cfg, group=dist.group.WORLD)
-    stats = sh.process_sonar_images(images, pos, quat)
-    keys, L = sh.gather_map()
-    pc = sh.get_point_cloud()
-    if rank == 0:
-        plain = SonarTo3DMapper(cfg)
-        ps = plain.process_sonar_images(images, pos, quat)
-        for a, b in zip(stats, ps):
-            assert (a["num_occupied"], a["num_free"], a["num_voxels"]) == (b["num_occupied"], b["num_free"], b["num_voxels"])
-        k1, L1 = plain.octree.voxels.to_arrays()
-        err = assert_same_map(keys, L, k1, L1, 0.0, f"{world}-GPU sharded vs 1-GPU")
-        assert pc["num_occupied"] == plain.get_point_cloud()["num_occupied"]
-        print(f"sharded_check ok: world={world} frames={n} voxels={len(k1)} max|dL|={err} "
-              f"exchange={sh.last_exchange_bytes / 1e6:.1f} MB sent by rank 0")
-    dist.barrier()
+    plain_ref = None
+    for mode in ("replicate", "route"):
+        sh = ShardedSonarMapper(cfg, group=dist.group.WORLD, mode=mode)
+        stats = sh.process_sonar_images(images, pos, quat)
+        keys, L = sh.gather_map()
+        pc = sh.get_point_cloud()
+        if rank == 0:
+            if plain_ref is None:
+                plain = SonarTo3DMapper(cfg)
+                ps = plain.process_sonar_images(images, pos, quat)
+                plain_ref = (ps, *plain.octree.voxels.to_arrays(), plain.get_point_cloud()["num_occupied"])
+            ps, k1, L1, n_occ = plain_ref
+            for a, b in zip(stats, ps):
+                assert (a["num_occupied"], a["num_free"], a["num_voxels"]) == (b["num_occupied"], b["num_free"], b["num_voxels"])
+            err = assert_same_map(keys, L, k1, L1, 0.0, f"{world}-GPU sharded ({mode}) vs 1-GPU")
+            assert pc["num_occupied"] == n_occ
+            print(f"sharded_check ok: mode={mode} world={world} frames={n} voxels={len(k1)} max|dL|={err} "
+                  f"exchange={sh.last_exchange_bytes / 1e6:.1f} MB sent by rank 0")
+        del sh
+        dist.barrier()
     dist.destroy_process_group()
 
 
