@@ -36,8 +36,31 @@ constexpr u64 EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
 constexpr int KEY_BITS = 21;
 constexpr int KEY_BIAS = 1 << 20;
 constexpr int GF = 16;                                      // frames per chunk = counter lanes per dedupe entry
+constexpr int N_CHUNK_BUF = 4;                              // chunk dedupe buffers in flight
 constexpr u32 ERR_KEYRANGE = 1u, ERR_TABLEFULL = 2u;        // fatal
 constexpr u32 ABORT_SCRATCH = 1u, ABORT_TABLE = 2u;         // retryable: the host enlarges and re-runs the chunk
+constexpr u32 ABORT_NARROW = 4u;                            // retryable: a 16-bit sample count overflowed -> wide lanes
+
+// A dedupe entry holds one counter lane per frame of the chunk: {n_occ, n_free} of the voxel in
+// that frame.  Narrow lanes (u32 = 16 + 16 bits) are the normal format -- half the bytes of the
+// wide ones; a voxel that collects more than 65535 samples of one kind in one frame (voxels far
+// larger than the range resolution) makes the chunk re-run with wide lanes (u64 = 32 + 32 bits).
+template <typename CT> struct Lane;
+template <> struct Lane<u32> {
+    static constexpr bool narrow = true;
+    static __device__ __forceinline__ u32 n_occ(u32 c) { return c >> 16; }
+    static __device__ __forceinline__ u32 n_free(u32 c) { return c & 0xffffu; }
+    static __device__ __forceinline__ u32 make(u32 n_occ, u32 n_free) { return (n_occ << 16) | n_free; }
+    static __device__ __forceinline__ bool overflows(u32 old, u32 inc)
+    { return (((old & 0xffffu) + (inc & 0xffffu)) | ((old >> 16) + (inc >> 16))) > 0xffffu; }
+};
+template <> struct Lane<u64> {
+    static constexpr bool narrow = false;
+    static __device__ __forceinline__ u32 n_occ(u64 c) { return (u32)(c >> 32); }
+    static __device__ __forceinline__ u32 n_free(u64 c) { return (u32)(c & 0xffffffffu); }
+    static __device__ __forceinline__ u64 make(u32 n_occ, u32 n_free) { return ((u64)n_occ << 32) | (u64)n_free; }
+    static __device__ __forceinline__ bool overflows(u64, u64) { return false; }
+};
 
 struct __align__(16) Slot { u64 key; double val; };
 
@@ -45,6 +68,7 @@ struct DevParams {
     double res, inv_res, lo_occ, lo_free, lo_min, lo_max, a_thr, a_ratio, zmin;
     double l_skip;   // log-odds above which prob > a_thr for sure (+inf = never skip the exp)
     int adaptive, zfilter, thr;
+    u32 fr_hi_lo, fr_hi_span;   // high words bounding the fractional parts the fast quantiser accepts
 };
 
 struct DevTables {
@@ -68,7 +92,7 @@ struct MapCtr {       // device-resident map counters
 
 struct ChunkCtr {     // working counters of the chunk in flight (chunks are serialised on the stream)
     u64 count0;       // live voxels before the chunk
-    u32 n_unique;     // dedupe entries created by k_expand
+    u32 n_unique;     // dedupe entries created for the chunk (k_expand, k_shard_merge)
     u32 ticket;       // last-block-out election
     u32 neu[GF];      // voxels first inserted at frame f of the chunk
 };
@@ -126,29 +150,43 @@ __device__ __forceinline__ u32 mix32(u64 key)
 }
 
 // ------------------------------------------------------------------------------------ K1+K2+K3
-// One block per (processed beam, frame of the chunk).  The block lists the beam's range samples
-// (free: every free_step-th bin before the first hit; occupied: above-threshold bins in the
-// occ_window bins from the first hit), prefix-sums their fan sizes (2*nv+1), and its threads
-// then walk the flattened (range sample, vertical step) space: sonar-frame point from the
-// host trig tables, Sonar->Map transform, z filter, voxel key, and a count bump in the
-// chunk's dedupe table: one entry per voxel touched by the chunk, one counter lane per frame.
-constexpr int EX_THREADS = 128;
-constexpr int EX_BEAMS = EX_THREADS / 32;   // beams per block: warp b lists beam b
-constexpr int EX_ILP = 2;                   // samples per lane per pass
+// One block per (group of EX_WARPS adjacent processed beams, frame of the chunk); warp w lists
+// and walks beam w.  Samples are merged twice before they reach HBM-side structures:
+//   1. in a block-local combiner in shared memory (open addressing, 32-bit voxel key relative
+//      to the voxel of the sonar origin, 16+16-bit occupied/free counts): adjacent range bins,
+//      vertical steps and beams fall into the same voxels, so a block's ~5 k samples collapse
+//      to ~1 k entries at shared-memory atomic cost;
+//   2. the combiner is flushed, entry by entry, into the chunk's dedupe table in global memory
+//      (one entry per voxel touched by the chunk, one counter lane per frame).
+constexpr int EX_WARPS = 8;                  // beams per block
+constexpr int EX_THREADS = EX_WARPS * 32;
+constexpr int EX_ILP = 2;                    // samples per lane per pass
+constexpr int EX_PASS = 32 * EX_ILP;         // samples per warp per pass
+constexpr int EX_ROUND = 6;                  // passes between two block-wide flush votes
+constexpr int EX_ROUND_SAMPLES = EX_WARPS * EX_PASS * EX_ROUND;
+constexpr int LT_BITS = 12;
+constexpr int LT_CAP = 1 << LT_BITS;         // combiner entries
+constexpr int LT_LIMIT = LT_CAP * 3 / 4;     // load bound
+constexpr int LT_MAX_SAMPLES = 0xFFFF;       // 16-bit counts cannot overflow between two flushes
+constexpr u32 LT_EMPTY = 0xFFFFFFFFu;
+constexpr int LK_BITS = 10;                  // local key: 3 x 10 bits around the sonar-origin voxel
+constexpr int LK_HALF = 1 << (LK_BITS - 1);
+constexpr int FL_ILP = 2;                    // combiner entries per thread per flush batch
 constexpr u32 SCRATCH_PROBE_LIMIT = 512;
+static_assert(EX_ROUND_SAMPLES <= LT_LIMIT, "a round must fit the combiner");
+
+struct __align__(16) Fan { int off; u32 code; double range; };   // code = r | nv << 16 | occupied << 31
 
 struct ExpandArgs {
     const uint8_t *imgs; size_t img_stride;
     const double *T;             // [g][16]
     DevTables tab; DevParams p;
-    u64 *skeys; u64 *scnt; u32 smask;   // chunk dedupe table: keys[C], counters[C][GF]
-    u32 *slist;                         // [C] slots of the entries created by this chunk, dense
+    u64 *skeys; void *scnt; u32 smask;  // chunk dedupe table: keys[C], counter lanes[C][GF] (u32 or u64 lanes)
     ChunkCtr *cc;
     DevStats *stats;             // [g]
     MapCtr *mc;
     int beam_lo, beam_hi;        // processed beams [beam_lo, beam_hi) are expanded (a rank's slice when sharded)
-    u32 own_rank, own_world;     // own_world > 1: keep only samples whose voxel this rank owns (replicated expansion)
-    int dbg;                     // S3D_DEBUG_STAGE (timing experiments only): 1 = no dedupe, 2 = probe only
+    u32 own_rank, own_world;     // own_world > 1: keep only the voxels this rank owns (replicated expansion)
     u64 seq;                     // chunk sequence number (for abort bookkeeping)
 };
 
@@ -160,8 +198,7 @@ __device__ __forceinline__ void raise_abort(MapCtr *mc, u32 why, u64 seq)
 
 // The dedupe table is probed by 32-byte sector: a bucket is 4 consecutive keys, loaded with two
 // 16-byte ld.cg (one sector), so a lookup is one L2 round trip unless the bucket is full of other
-// keys.  Inside a warp the latency of a pass is the LONGEST probe chain of its lanes, which is
-// why single-slot linear probing was slow here (tools/dbg_stage.sh, profiles/).
+// keys.
 struct Bucket { ulonglong2 a, b; };
 
 __device__ __forceinline__ Bucket load_bucket(const u64 *skeys, u32 base)
@@ -179,10 +216,13 @@ __device__ __forceinline__ u32 dedupe_slot(u64 *skeys, u32 smask, u64 key, u32 b
     created = false;
     for (u32 probe = 0; probe < SCRATCH_PROBE_LIMIT; ++probe) {
         const u64 w[4] = {k.a.x, k.a.y, k.b.x, k.b.y};
-        int hit = -1, hole = -1;
+        int hit = -1;
 #pragma unroll
-        for (int j = 3; j >= 0; --j) { if (w[j] == key) hit = j; if (w[j] == EMPTY_KEY) hole = j; }
+        for (int j = 3; j >= 0; --j) if (w[j] == key) hit = j;
         if (hit >= 0) return base + (u32)hit;
+        int hole = -1;
+#pragma unroll
+        for (int j = 3; j >= 0; --j) if (w[j] == EMPTY_KEY) hole = j;
         if (hole >= 0) {
             const u64 cur = atomicCAS(&skeys[base + hole], EMPTY_KEY, key);
             if (cur == EMPTY_KEY) { created = true; return base + (u32)hole; }
@@ -196,176 +236,189 @@ __device__ __forceinline__ u32 dedupe_slot(u64 *skeys, u32 smask, u64 key, u32 b
     return ~0u;
 }
 
-// Bump lane `lane` of the entry of `key`.  Returns the slot if this call created the entry, else ~0.
-__device__ __forceinline__ u32 scratch_resolve(const ExpandArgs &a, u64 key, u32 base, const Bucket &k, int lane, u64 inc)
+__device__ __forceinline__ u32 dedupe_home(u64 key, u32 smask) { return mix32(key) & smask & ~3u; }
+
+// add n_occ / n_free samples to lane g of the entry of `key`; returns 1 if this call created the entry
+template <typename CT>
+__device__ __forceinline__ u32 dedupe_add(u64 *skeys, CT *scnt, u32 smask, MapCtr *mc, u64 seq, u64 key, u32 home,
+                                          const Bucket &k, int g, u32 n_occ, u32 n_free)
 {
-    if (a.dbg == 3) {      // timing experiment: reductions only, no key check
-        u32 *half = reinterpret_cast<u32 *>(&a.scnt[(size_t)base * GF + lane]);
-        if (inc >> 32) atomicAdd(half + 1, (u32)(inc >> 32)); else atomicAdd(half, (u32)inc);
-        return ~0u;
-    }
     bool created;
-    const u32 slot = dedupe_slot(a.skeys, a.smask, key, base, k, created);
-    if (slot == ~0u) { raise_abort(a.mc, ABORT_SCRATCH, a.seq); return ~0u; }   // the host enlarges the table and retries
-    // the counter lane is {n_free: low 32 bits, n_occ: high 32 bits}; bump the half that applies
-    u32 *half = reinterpret_cast<u32 *>(&a.scnt[(size_t)slot * GF + lane]);
-    if (a.dbg != 4) { if (inc >> 32) atomicAdd(half + 1, (u32)(inc >> 32)); else atomicAdd(half, (u32)inc); }
-    return created ? slot : ~0u;
-}
-
-// One sample: sonar-frame point from the host trig tables, Sonar->Map transform, z filter, key.
-// Returns false if the sample is filtered out or its key is unusable.
-__device__ __forceinline__ bool sample_key(const ExpandArgs &a, const double *s_T, int r, int nv, int vi,
-                                           double cb, double sb, int &emitted, u64 &key)
-{
-    const DevTables &tab = a.tab;
-    const int ti = nv * nv - 1 + vi;                        // row nv, entry v_step + nv
-    const double cv = __ldg(&tab.cos_va[ti]), sv = __ldg(&tab.sin_va[ti]);
-    const double range = __ldg(&tab.range_m[r]);
-    // sonar frame, X fwd / Y right / Z down, products rounded left to right (:434-436)
-    const double rc = __dmul_rn(range, cv);
-    const double xs = __dmul_rn(rc, cb);
-    const double ys = -__dmul_rn(rc, sb);
-    const double zs = __dmul_rn(range, sv);
-    // T @ [x,y,z,1] as numpy evaluates it: (t0*x + t2*z) + (t1*y + t3) (:440)
-    double wv[3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q)
-        wv[q] = __dadd_rn(__dadd_rn(__dmul_rn(s_T[4 * q], xs), __dmul_rn(s_T[4 * q + 2], zs)),
-                          __dadd_rn(__dmul_rn(s_T[4 * q + 1], ys), s_T[4 * q + 3]));
-    if (a.p.zfilter && wv[2] < a.p.zmin) return false;      // :443, :478
-    int ki, kj, kk;
-    if (voxel_index(wv[0], a.p.res, a.p.inv_res, ki) && voxel_index(wv[1], a.p.res, a.p.inv_res, kj) &&
-        voxel_index(wv[2], a.p.res, a.p.inv_res, kk)) {
-        key = pack_key(ki, kj, kk);
-        // replicated expansion: every rank computes every sample and keeps the voxels it owns
-        if (a.own_world > 1 && key_owner(key, a.own_world) != a.own_rank) return false;
-        ++emitted;
-        return true;
+    const u32 slot = dedupe_slot(skeys, smask, key, home, k, created);
+    if (slot == ~0u) { raise_abort(mc, ABORT_SCRATCH, seq); return 0u; }   // the host enlarges the table and retries
+    const CT inc = Lane<CT>::make(n_occ, n_free);
+    if (Lane<CT>::narrow) {
+        const CT old = atomicAdd(&scnt[(size_t)slot * GF + g], inc);
+        if (Lane<CT>::overflows(old, inc)) raise_abort(mc, ABORT_NARROW, seq);   // re-run with wide lanes
+    } else {
+        atomicAdd(&scnt[(size_t)slot * GF + g], inc);
     }
-    ++emitted;
-    atomicOr(&a.mc->err, ERR_KEYRANGE);
-    return false;
+    return created ? 1u : 0u;
 }
 
-constexpr int EX_WBUF = 64 * EX_ILP + 32;   // per-warp staging of created dedupe slots (flushed in bulk)
-
-// move the warp's staged slots to the chunk's dense list: one atomic per flush
-__device__ __forceinline__ void flush_created(const ExpandArgs &a, u32 *wbuf, int &wn, int lane)
+// a sample that does not fit the block combiner (more than 2^9 voxels from the sonar origin, or
+// a transform too large for the fast quantiser) goes to the dedupe table on its own
+template <typename CT>
+__device__ __noinline__ void commit_direct(u64 *skeys, CT *scnt, u32 smask, ChunkCtr *cc, MapCtr *mc, u64 seq, u64 key,
+                                           int g, bool occ)
 {
-    if (wn == 0) return;
-    u32 base = 0;
-    if (lane == 0) base = atomicAdd(&a.cc->n_unique, (u32)wn);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    __syncwarp();
-    for (int q = lane; q < wn; q += 32) a.slist[(base + q) & a.smask] = wbuf[q];
-    __syncwarp();
-    wn = 0;
+    const u32 home = dedupe_home(key, smask);
+    if (dedupe_add<CT>(skeys, scnt, smask, mc, seq, key, home, load_bucket(skeys, home), g, occ ? 1u : 0u, occ ? 0u : 1u))
+        atomicAdd(&cc->n_unique, 1u);
 }
 
-// Warp-wide commit of up to EX_ILP samples per lane into the chunk dedupe table.  Lanes that
-// hold the same voxel are merged first (adjacent range bins usually do), so only one lane per
-// distinct voxel touches the table; the home-slot probes of all samples are issued together.
-// Slots of entries created here are staged per warp and reach the chunk's dense list in bulk.
-__device__ __forceinline__ void commit_batch(const ExpandArgs &a, const bool (&ok)[EX_ILP], const u64 (&key)[EX_ILP],
-                                             bool occupied, int g, int lane, u32 *wbuf, int &wn)
+// floor(w / res) for samples of a block whose transform is known to keep |w / res| < 2^30:
+// the reciprocal product, floored by a round-down add of 1.5 * 2^52 (the integer lands in the
+// low word), decides unless it is within 1e-6 of an integer; then the IEEE division does.
+__device__ __forceinline__ bool quantise(const DevParams &p, double w, bool fast, int &k)
 {
-    u32 slot[EX_ILP]; u64 inc[EX_ILP]; bool lead[EX_ILP];
-    if (a.dbg == 1) {
-        u64 x = 0;
-#pragma unroll
-        for (int j = 0; j < EX_ILP; ++j) x ^= ok[j] ? key[j] : 0ull;
-        if (x == 0x123456789ull) a.slist[0] = 1;
-        return;
+    if (fast) {
+        const double MAGIC = 6755399441055744.0;
+        const double q = __dmul_rn(w, p.inv_res);
+        const double t = __dadd_rd(q, MAGIC);
+        const double fr = __dadd_rn(q, -__dadd_rn(t, -MAGIC));        // q - floor(q), exact
+        k = __double2loint(t);
+        if ((u32)(__double2hiint(fr) - p.fr_hi_lo) < p.fr_hi_span) return true;
     }
-#pragma unroll
-    for (int j = 0; j < EX_ILP; ++j) {
-        const u32 m_ok = __ballot_sync(0xffffffffu, ok[j]);
-        lead[j] = false; slot[j] = 0; inc[j] = 0;
-        if (ok[j]) {
-            const u32 peers = __match_any_sync(m_ok, key[j]);
-            lead[j] = (lane == __ffs(peers) - 1);
-            const u64 n = (u64)__popc(peers);
-            inc[j] = occupied ? (n << 32) : n;
-            slot[j] = mix32(key[j]) & a.smask & ~3u;          // home bucket
+    return voxel_index(w, p.res, p.inv_res, k);
+}
+
+// the key range voxel_index accepts: -2^20 < k < 2^20 - 1 on every axis
+__device__ __forceinline__ bool key_in_range(int ki, int kj, int kk)
+{
+    const u32 span = 2u * KEY_BIAS - 2u;
+    return (u32)(ki + KEY_BIAS - 1) < span && (u32)(kj + KEY_BIAS - 1) < span && (u32)(kk + KEY_BIAS - 1) < span;
+}
+
+// Block-wide: move every combiner entry into the chunk dedupe table and leave the combiner
+// empty.  All threads of the block call it after a barrier that follows the last insert.
+template <typename CT>
+__device__ __forceinline__ void flush_combiner(const ExpandArgs &a, u32 *tkey, u32 *tcnt, unsigned short *live,
+                                               u32 *s_nlive, volatile u32 *s_count, const int (&o)[3], int g,
+                                               u32 &emitted)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    const u32 lt_mask = (1u << lane) - 1;
+    if (tid == 0) *s_nlive = 0;
+    __syncthreads();
+    // 1. dense list of the live entries
+#pragma unroll 4
+    for (int i = tid; i < LT_CAP; i += EX_THREADS) {
+        const bool lv = tkey[i] != LT_EMPTY;
+        const u32 m = __ballot_sync(0xffffffffu, lv);
+        if (m) {
+            u32 base = 0;
+            if (lane == 0) base = atomicAdd(s_nlive, (u32)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (lv) live[base + __popc(m & lt_mask)] = (unsigned short)i;
         }
     }
-    Bucket cur[EX_ILP];
+    __syncthreads();
+    const int n = (int)*s_nlive;
+    // 2. FL_ILP entries per thread at a time: home buckets are fetched together, then resolved
+    for (int base = 0; base < n; base += EX_THREADS * FL_ILP) {
+        u64 key[FL_ILP]; u32 inc[FL_ILP], home[FL_ILP]; bool ok[FL_ILP]; Bucket bk[FL_ILP];
+        u32 made = 0;
 #pragma unroll
-    for (int j = 0; j < EX_ILP; ++j) {
-        cur[j].a = cur[j].b = make_ulonglong2(0ull, 0ull);
-        if (lead[j]) cur[j] = load_bucket(a.skeys, slot[j]);
-    }
-    u32 made[EX_ILP];
-    int n_mine = 0;
-    if (a.dbg == 2) {
-        u64 x = 0;
-#pragma unroll
-        for (int j = 0; j < EX_ILP; ++j) x ^= cur[j].a.x ^ cur[j].b.y;
-        if (x == 0x123456789ull) a.slist[0] = 1;
-        return;
-    }
-#pragma unroll
-    for (int j = 0; j < EX_ILP; ++j) {
-        made[j] = lead[j] ? scratch_resolve(a, key[j], slot[j], cur[j], g, inc[j]) : ~0u;
-        n_mine += made[j] != ~0u;
-    }
-    __syncwarp();
-    if (__any_sync(0xffffffffu, n_mine > 0)) {
-        int incl = n_mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
+        for (int j = 0; j < FL_ILP; ++j) {
+            const int e = base + j * EX_THREADS + tid;
+            ok[j] = false; key[j] = 0; inc[j] = 0; home[j] = 0;
+            bk[j].a = bk[j].b = make_ulonglong2(0ull, 0ull);
+            if (e < n) {
+                const int idx = live[e];
+                const u32 lk = tkey[idx], c = tcnt[idx];
+                tkey[idx] = LT_EMPTY; tcnt[idx] = 0;
+                const int ki = (int)(lk & (2 * LK_HALF - 1)) - LK_HALF + o[0];
+                const int kj = (int)((lk >> LK_BITS) & (2 * LK_HALF - 1)) - LK_HALF + o[1];
+                const int kk = (int)(lk >> (2 * LK_BITS)) - LK_HALF + o[2];
+                if (!key_in_range(ki, kj, kk)) atomicOr(&a.mc->err, ERR_KEYRANGE);
+                else {
+                    key[j] = pack_key(ki, kj, kk);
+                    // replicated expansion: every rank computes every sample and keeps the voxels it owns
+                    if (a.own_world <= 1 || key_owner(key[j], a.own_world) == a.own_rank) {
+                        ok[j] = true;
+                        inc[j] = c;
+                        emitted += (c >> 16) + (c & 0xffffu);
+                        home[j] = dedupe_home(key[j], a.smask);
+                        bk[j] = load_bucket(a.skeys, home[j]);
+                    }
+                }
+            }
         }
-        int dst = wn + incl - n_mine;
 #pragma unroll
-        for (int j = 0; j < EX_ILP; ++j)
-            if (made[j] != ~0u) wbuf[dst++] = made[j];
-        wn += __shfl_sync(0xffffffffu, incl, 31);
-        if (wn > EX_WBUF - 32 * EX_ILP) flush_created(a, wbuf, wn, lane);
+        for (int j = 0; j < FL_ILP; ++j)
+            if (ok[j]) made += dedupe_add<CT>(a.skeys, static_cast<CT *>(a.scnt), a.smask, a.mc, a.seq, key[j], home[j], bk[j],
+                                              g, inc[j] >> 16, inc[j] & 0xffffu);
+        // entries created for the chunk: one reduction per warp per batch (nobody waits for it)
+        made = __reduce_add_sync(0xffffffffu, made);
+        if (lane == 0 && made) atomicAdd(&a.cc->n_unique, made);
     }
+    if (tid == 0) *s_count = 0;
+    __syncthreads();
 }
 
-// One warp per (processed beam, frame of the chunk); EX_BEAMS beams per block.
-//  1. list the beam's range samples: free = every free_step-th bin before the first hit (:420),
-//     occupied = above-threshold bins in the occ_window bins from the first hit (:451-452);
-//  2. free samples: the flattened (range sample, vertical step) space, 32 consecutive samples
-//     per pass (consecutive vertical steps => coalesced trig-table reads);
-//  3. occupied samples: a (vertical step, range bin) grid walked range-bin-fastest, so that
-//     the lanes of a pass are adjacent range bins at one vertical step -- they mostly fall into
-//     the same few voxels and are merged before touching the dedupe table.
-__global__ void __launch_bounds__(EX_THREADS)
+__host__ __device__ inline size_t expand_smem_bytes(int H, int free_step, int occ_window)
+{
+    const int max_f = (H + free_step - 1) / free_step;
+    return sizeof(u32) * 2 * LT_CAP + sizeof(unsigned short) * LT_CAP +
+           sizeof(Fan) * (size_t)EX_WARPS * (size_t)(max_f + occ_window + 1);
+}
+
+template <typename CT>
+__global__ void __launch_bounds__(EX_THREADS, 4)
 k_expand(ExpandArgs a)
 {
-    extern __shared__ int s_dyn[];
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    u32 *tkey = reinterpret_cast<u32 *>(s_raw);
+    u32 *tcnt = tkey + LT_CAP;
+    unsigned short *live = reinterpret_cast<unsigned short *>(tcnt + LT_CAP);
+    Fan *fans_all = reinterpret_cast<Fan *>(live + LT_CAP);
     const DevTables &tab = a.tab;
     const int H = tab.H, W = tab.W;
     const int max_f = (H + tab.free_step - 1) / tab.free_step;        // free candidates per beam
-    const int per_warp = (max_f + 1) + max_f + 2 * tab.occ_window;
+    const int nf_max = max_f + tab.occ_window;                        // fans per beam
     __shared__ double s_T[12];
-    __shared__ u32 s_abort;
-    __shared__ u32 s_wbuf[EX_BEAMS][EX_WBUF];
+    __shared__ int s_o[3], s_fast, s_tot[EX_WARPS];
+    __shared__ u32 s_count, s_nlive, s_abort;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    u32 *wbuf = s_wbuf[warp];
-    int wn = 0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const u32 lt_mask = (1u << lane) - 1;
     const int g = blockIdx.y;
     const uint8_t *img = a.imgs + (size_t)g * a.img_stride;
-    if (threadIdx.x == 0) s_abort = __ldcg(&a.mc->abort);
-    if (threadIdx.x < 12) s_T[threadIdx.x] = a.T[g * 16 + threadIdx.x];
+    if (tid == 0) { s_abort = __ldcg(&a.mc->abort); s_count = 0; }
+    if (tid < 12) s_T[tid] = a.T[g * 16 + tid];
+    if (tid == 32) {
+        // voxel of the sonar origin (the combiner's key origin), and whether every sample of this
+        // frame is certain to stay below 2^30 voxels from zero (then the fast quantiser is exact)
+        const double *T = a.T + g * 16;
+        const double reach = H > 0 ? tab.range_m[H - 1] : 0.0;
+        bool fast = true;
+        int o[3] = {0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const double bound = (fabs(T[4 * q]) + fabs(T[4 * q + 1]) + fabs(T[4 * q + 2])) * reach + fabs(T[4 * q + 3]);
+            if (!(bound * a.p.inv_res < 1073741824.0)) fast = false;
+            if (!voxel_index(T[4 * q + 3], a.p.res, a.p.inv_res, o[q])) fast = false;
+        }
+        s_o[0] = o[0]; s_o[1] = o[1]; s_o[2] = o[2];
+        s_fast = fast;
+    }
+    for (int i = tid; i < LT_CAP / 4; i += EX_THREADS) {
+        reinterpret_cast<uint4 *>(tkey)[i] = make_uint4(LT_EMPTY, LT_EMPTY, LT_EMPTY, LT_EMPTY);
+        reinterpret_cast<uint4 *>(tcnt)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     __syncthreads();
     if (s_abort) return;                // a chunk must be retried first: stay side-effect free (block-uniform)
-    int *f_off = s_dyn + warp * per_warp;      // [max_f + 1] exclusive prefix of free fan sizes
-    int *f_rn = f_off + (max_f + 1);           // [max_f] r | nv << 16 of free candidate c
-    int *o_r = f_rn + max_f;                   // [occ_window] range bin of occupied column
-    int *o_nv = o_r + tab.occ_window;          // [occ_window] its fan half-width
-    const int beam = a.beam_lo + blockIdx.x * EX_BEAMS + warp;
-    int emitted = 0;
+
+    // ---- per warp: first hit and fan list of its beam
+    Fan *fans = fans_all + (size_t)warp * (nf_max + 1);
+    const int beam = a.beam_lo + blockIdx.x * EX_WARPS + warp;
+    int total = 0, nfan = 0;
+    double cb = 0.0, sb = 0.0;
     if (beam < a.beam_hi) {
         const int col = tab.beam_col[beam];
-        const double cb = tab.cos_b[beam], sb = tab.sin_b[beam];
-        // ---- 0. first above-threshold range bin of this beam (:406-409): 128 rows per step, lanes = rows
+        cb = tab.cos_b[beam]; sb = tab.sin_b[beam];
+        // first above-threshold range bin of this beam (:406-409): 128 rows per step, lanes = rows
         int fh = H;                                                    // no hit -> whole ray is free (:412-413)
         for (int r0 = 0; r0 < H && fh == H; r0 += 128) {
             bool hit[4];
@@ -382,12 +435,26 @@ k_expand(ExpandArgs a)
         }
         const int nfc = (fh + tab.free_step - 1) / tab.free_step;      // range(0, fh, free_step) (:420)
         const int noc = fh < H ? min(tab.occ_window, H - fh) : 0;      // range(fh, min(fh+50, H)) (:451)
-        // ---- 1a. free candidates and the prefix sum of their fan sizes
-        int total_free = 0;
-        for (int base = 0; base < nfc; base += 32) {
-            const int c = base + lane;
+        // fans in walking order, empty ones dropped: free = every free_step-th bin before the first
+        // hit (:420; bins below min_range have nv == 0), then occupied = above-threshold bins in
+        // the window from the first hit (:451-452)
+        int run = 0;
+        const int nfc32 = (nfc + 31) & ~31;
+        for (int base = 0; base < nfc32 + noc; base += 32) {
             int r = 0, nv = 0;
-            if (c < nfc) { r = c * tab.free_step; nv = tab.nv_free[r]; }
+            u32 occ_bit = 0u;
+            if (base < nfc32) {                                         // warp-uniform
+                const int c = base + lane;
+                if (c < nfc) { r = c * tab.free_step; nv = tab.nv_free[r]; }
+            } else {
+                const int c = base - nfc32 + lane;
+                if (c < noc) {
+                    r = fh + c;
+                    nv = ((int)__ldg(&img[(size_t)r * W + col]) > a.p.thr) ? tab.nv_occ[r] : 0;   // :452, :456
+                }
+                occ_bit = 0x80000000u;
+            }
+            const u32 m = __ballot_sync(0xffffffffu, nv > 0);
             const int v = nv > 0 ? 2 * nv + 1 : 0;
             int incl = v;
 #pragma unroll
@@ -395,77 +462,116 @@ k_expand(ExpandArgs a)
                 const int t = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= d) incl += t;
             }
-            if (c < nfc) { f_off[c] = total_free + incl - v; f_rn[c] = r | (nv << 16); }
-            total_free += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (lane == 0) f_off[nfc] = total_free;
-        // ---- 1b. occupied columns, compacted
-        int ncol = 0, nvmax = 0;
-        for (int base = 0; base < noc; base += 32) {
-            const int c = base + lane;
-            int r = 0, nv = 0;
-            if (c < noc) {
-                r = fh + c;
-                nv = ((int)img[(size_t)r * W + col] > a.p.thr) ? tab.nv_occ[r] : 0;       // :452, :456
-            }
-            const u32 m = __ballot_sync(0xffffffffu, nv > 0);
             if (nv > 0) {
-                const int dst = ncol + __popc(m & ((1u << lane) - 1));
-                o_r[dst] = r; o_nv[dst] = nv;
+                Fan f; f.off = run + incl - v; f.code = (u32)r | ((u32)nv << 16) | occ_bit; f.range = tab.range_m[r];
+                fans[nfan + __popc(m & lt_mask)] = f;
             }
-            ncol += __popc(m);
-            nvmax = max(nvmax, nv);
+            nfan += __popc(m);
+            run += __shfl_sync(0xffffffffu, incl, 31);
         }
+        if (lane == 0) fans[nfan].off = run;
+        total = run;
+    }
+    if (lane == 0) s_tot[warp] = total;
+    __syncthreads();
+    const bool fast = s_fast != 0;
+    const int o[3] = {s_o[0], s_o[1], s_o[2]};
+    volatile u32 *v_count = &s_count;
+    volatile u32 *v_tkey = tkey;
+
+    // ---- the flattened (fan, vertical step) space of the beam, EX_PASS consecutive samples per pass.
+    // The block walks in rounds of EX_ROUND passes per warp; between rounds it votes on flushing the
+    // combiner, until what is left certainly fits (then the warps run free to the end).
+    u32 emitted = 0;
+    int c0 = 0;                      // fan that holds the first sample of the next pass
+    int base = 0;                    // first sample of the next pass of this warp
+    int since = 0;                   // samples the block has walked since the last flush (>= combiner entries)
+    int rem = 0;                     // samples the block still has to walk
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) nvmax = max(nvmax, __shfl_xor_sync(0xffffffffu, nvmax, d));
-        __syncwarp();
-        if (a.dbg == 5) total_free = ncol = 0;                     // timing experiment: listing only
-        // ---- 2. free samples, EX_ILP x 32 consecutive samples per pass
-        {
-            int c[EX_ILP];
+    for (int b = 0; b < EX_WARPS; ++b) rem += s_tot[b];
+    for (int round = 0; rem > 0; ++round) {
+        const bool free_run = since + rem <= LT_LIMIT;                  // block-uniform
+        const int last = free_run ? total : min(total, (round + 1) * (EX_PASS * EX_ROUND));
+        for (; base < last; base += EX_PASS) {
+            // fans that start inside this pass: bit (start - base) of a 64-bit mask (a fan has >= 3 samples)
+            const int kf = c0 + 1 + lane;
+            const int rel = (kf <= nfan ? fans[kf].off : INT_MAX) - base;
+            const u32 m_lo = __reduce_or_sync(0xffffffffu, (rel > 0 && rel < 32) ? 1u << rel : 0u);
+            const u32 m_hi = __reduce_or_sync(0xffffffffu, (rel >= 32 && rel < 64) ? 1u << (rel - 32) : 0u);
+            const int adv = __popc(__ballot_sync(0xffffffffu, rel > 0 && rel <= EX_PASS));
+            const u32 upto = 0xffffffffu >> (31 - lane);                // bits 0..lane
+            int n_new = 0;
 #pragma unroll
-            for (int j = 0; j < EX_ILP; ++j) c[j] = 0;
-            for (int base = 0; base < total_free; base += 32 * EX_ILP) {
-                bool ok[EX_ILP]; u64 key[EX_ILP];
+            for (int j = 0; j < EX_ILP; ++j) {
+                const int w = base + j * 32 + lane;
+                if (w >= total) continue;
+                const Fan f = fans[c0 + (j == 0 ? __popc(m_lo & upto) : __popc(m_lo) + __popc(m_hi & upto))];
+                const int nv = (int)((f.code >> 16) & 0x7fffu);
+                const bool occ = (f.code >> 31) != 0u;
+                const int ti = nv * nv - 1 + (w - f.off);               // row nv, entry v_step + nv
+                const double cv = __ldg(&tab.cos_va[ti]), sv = __ldg(&tab.sin_va[ti]);
+                // sonar frame, X fwd / Y right / Z down, products rounded left to right (:434-436)
+                const double rc = __dmul_rn(f.range, cv);
+                const double xs = __dmul_rn(rc, cb);
+                const double ys = -__dmul_rn(rc, sb);
+                const double zs = __dmul_rn(f.range, sv);
+                // T @ [x,y,z,1] as numpy evaluates it: (t0*x + t2*z) + (t1*y + t3) (:440)
+                double wv[3];
 #pragma unroll
-                for (int j = 0; j < EX_ILP; ++j) {
-                    const int w = base + j * 32 + lane;
-                    ok[j] = false; key[j] = 0;
-                    if (w < total_free) {
-                        while (f_off[c[j] + 1] <= w) ++c[j];          // zero-size fans are skipped here
-                        const int rn = f_rn[c[j]];
-                        ok[j] = sample_key(a, s_T, rn & 0xffff, rn >> 16, w - f_off[c[j]], cb, sb, emitted, key[j]);
-                    }
+                for (int q = 0; q < 3; ++q)
+                    wv[q] = __dadd_rn(__dadd_rn(__dmul_rn(s_T[4 * q], xs), __dmul_rn(s_T[4 * q + 2], zs)),
+                                      __dadd_rn(__dmul_rn(s_T[4 * q + 1], ys), s_T[4 * q + 3]));
+                if (a.p.zfilter && wv[2] < a.p.zmin) continue;          // :443, :478
+                int ki, kj, kk;
+                if (!(quantise(a.p, wv[0], fast, ki) && quantise(a.p, wv[1], fast, kj) && quantise(a.p, wv[2], fast, kk))) {
+                    atomicOr(&a.mc->err, ERR_KEYRANGE);
+                    continue;
                 }
-                commit_batch(a, ok, key, false, g, lane, wbuf, wn);
-            }
-        }
-        // ---- 3. occupied samples, range-bin-fastest
-        {
-            const int n_v = ncol > 0 ? 2 * nvmax + 1 : 0;
-            const int col_passes = (ncol + 31) / 32;
-            const int n_cells = n_v * col_passes;                   // one cell = (v slot, 32 columns)
-            for (int cell0 = 0; cell0 < n_cells; cell0 += EX_ILP) {
-                bool ok[EX_ILP]; u64 key[EX_ILP];
-#pragma unroll
-                for (int j = 0; j < EX_ILP; ++j) {
-                    const int cell = cell0 + j;
-                    ok[j] = false; key[j] = 0;
-                    if (cell < n_cells) {
-                        const int vs = cell / col_passes, cc = (cell - vs * col_passes) * 32 + lane;
-                        if (cc < ncol) {
-                            const int nv = o_nv[cc];
-                            const int v_step = vs - nvmax;            // fans are centred on the same slot
-                            if (v_step >= -nv && v_step <= nv)
-                                ok[j] = sample_key(a, s_T, o_r[cc], nv, v_step + nv, cb, sb, emitted, key[j]);
+                const u32 d0 = (u32)(ki - o[0] + LK_HALF), d1 = (u32)(kj - o[1] + LK_HALF), d2 = (u32)(kk - o[2] + LK_HALF);
+                if (fast && (d0 | d1 | d2) < (u32)(2 * LK_HALF)) {
+                    // block combiner: find-or-insert the 30-bit local key, bump its 16+16-bit counts
+                    const u32 lk = d0 | (d1 << LK_BITS) | (d2 << (2 * LK_BITS));
+                    u32 h = (lk * 0x9E3779B1u) >> (32 - LT_BITS);
+                    for (;;) {
+                        u32 cur = v_tkey[h];
+                        if (cur == lk) break;
+                        if (cur == LT_EMPTY) {
+                            cur = atomicCAS(&tkey[h], LT_EMPTY, lk);
+                            if (cur == LT_EMPTY) { ++n_new; break; }
+                            if (cur == lk) break;
                         }
+                        h = (h + 1) & (LT_CAP - 1);
                     }
+                    atomicAdd(&tcnt[h], occ ? 0x10000u : 1u);
+                } else {
+                    if (!key_in_range(ki, kj, kk)) { atomicOr(&a.mc->err, ERR_KEYRANGE); continue; }
+                    const u64 key = pack_key(ki, kj, kk);
+                    if (a.own_world > 1 && key_owner(key, a.own_world) != a.own_rank) continue;
+                    ++emitted;
+                    commit_direct<CT>(a.skeys, static_cast<CT *>(a.scnt), a.smask, a.cc, a.mc, a.seq, key, g, occ);
                 }
-                commit_batch(a, ok, key, true, g, lane, wbuf, wn);
             }
+            c0 += adv;
+            n_new = __reduce_add_sync(0xffffffffu, n_new);
+            if (lane == 0 && n_new) atomicAdd(&s_count, (u32)n_new);
+        }
+        if (free_run) break;
+        int rem_next = 0;
+#pragma unroll
+        for (int b = 0; b < EX_WARPS; ++b) rem_next += max(0, s_tot[b] - (round + 1) * (EX_PASS * EX_ROUND));
+        since += rem - rem_next;
+        rem = rem_next;
+        // flush if the next round could overflow the combiner's entries or its 16-bit counts.  Every
+        // thread votes with the entry count it sees on arrival; the last one to arrive sees the final one.
+        const int next = min(rem, EX_ROUND_SAMPLES);
+        const int want = (*v_count + (u32)next > (u32)LT_LIMIT) || (since + next > LT_MAX_SAMPLES);
+        if (__syncthreads_or(want)) {
+            flush_combiner<CT>(a, tkey, tcnt, live, &s_nlive, v_count, o, g, emitted);
+            since = 0;
         }
     }
-    flush_created(a, wbuf, wn, lane);
+    __syncthreads();
+    if (*v_count > 0u) flush_combiner<CT>(a, tkey, tcnt, live, &s_nlive, v_count, o, g, emitted);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
     if (lane == 0 && emitted) atomicAdd(&a.stats[g].n_samples, (u64)emitted);
@@ -566,7 +672,7 @@ __device__ __forceinline__ void acc_publish(LocalAcc &a, MapCtr *mc, bool add_co
     }
 }
 
-constexpr int AP_THREADS = 128;
+constexpr int AP_THREADS = 256;    // = dedupe slots per tile
 constexpr int SUMT = 64;           // entries of the sequential-sum tables
 
 // sum of n_free copies of lo_free followed by n_occ copies of lo_occ, added one by one as the
@@ -587,95 +693,146 @@ __device__ __forceinline__ double seq_avg(u32 n_free, u32 n_occ, const double (*
     return sum / (double)(n_occ + n_free);                       // :559
 }
 
-// One thread per voxel touched by the chunk (k_expand left a dense list of the dedupe entries
-// it created).  The thread consumes and resets its entry, reads the voxel's table slot once,
-// walks the chunk's frames in order -- for each frame that touched the voxel: per-voxel mean of
-// the sample deltas (3d_mapper.py:557-559), then update_voxel (:562-567) -- and writes the slot
-// back once.  Frames stay strictly ordered per voxel, which is all the reference's sequential
-// semantics require (voxels are independent of each other).
+// The chunk's dedupe table is walked in tiles of AP_THREADS slots.  Per tile:
+//   1. one thread per slot: a live entry is read into registers and wiped, its voxel is found or
+//      inserted in the table (one probe per voxel per chunk), the per-frame num_occupied /
+//      num_free / new-voxel counts are taken from the counter lanes (they do not depend on L),
+//      and lanes + L are staged in shared memory;
+//   2. the live entries are listed, those that can take the adaptive path (some frame saw the
+//      voxel occupied) first, so that warps are homogeneous;
+//   3. one thread per listed entry walks only the frames that touched the voxel, in order:
+//      per-voxel mean of the sample deltas (3d_mapper.py:557-559), then update_voxel (:562-567);
+//      L goes back to the table with one 8-byte store.
+// Frames stay strictly ordered per voxel, which is all the reference's sequential semantics
+// require (voxels are independent of each other).
+template <typename CT>
 __global__ void __launch_bounds__(AP_THREADS)
-k_apply_chunk(u64 *__restrict__ skeys, u64 *__restrict__ scnt, const u32 *__restrict__ slist, int g, ChunkCtr *cc,
-              DevStats *st, Slot *table, u64 tmask, DevParams p, const double *__restrict__ sum_tab, MapCtr *mc)
+k_apply_chunk(u64 *__restrict__ skeys, CT *__restrict__ scnt, u32 n_slots, int g, ChunkCtr *cc, DevStats *st,
+              Slot *table, u64 tmask, DevParams p, const double *__restrict__ sum_tab, MapCtr *mc)
 {
-    __shared__ u32 s_occ[GF], s_free[GF], s_new[GF];
+    constexpr int ROW = GF + 1;                 // padded row: conflict-free column access
+    __shared__ CT s_lane[AP_THREADS * ROW];
+    __shared__ double s_L[AP_THREADS];
+    __shared__ u64 s_slot[AP_THREADS];
+    __shared__ unsigned short s_mask[AP_THREADS], s_ordA[AP_THREADS], s_ordB[AP_THREADS];
+    __shared__ u32 s_occ[GF], s_free[GF], s_new[GF], s_nA, s_nB;
     __shared__ double s_sum[4][SUMT];
     __shared__ bool s_last;
-    const u32 abort = __ldcg(&mc->abort);
-    const u32 n_live = __ldcg(&cc->n_unique);
-    if (abort) return;
-    // blocks past the live entries leave at once; the rest stride over the list
-    const u32 live_blocks = max(1u, min((u32)gridDim.x, (n_live + AP_THREADS - 1) / AP_THREADS));
-    if (blockIdx.x >= live_blocks) return;
-    const u32 lane = threadIdx.x & 31;
-    if (threadIdx.x < GF) { s_occ[threadIdx.x] = 0; s_free[threadIdx.x] = 0; s_new[threadIdx.x] = 0; }
-    for (int q = threadIdx.x; q < 4 * SUMT; q += AP_THREADS) (&s_sum[0][0])[q] = sum_tab[q];
-    __syncthreads();
-    u32 w_occ = 0, w_free = 0, w_new = 0;          // lane f of each warp accumulates frame f
+    static_assert(GF <= 16, "s_mask holds one bit per frame");
+    if (__ldcg(&mc->abort)) return;
+    const u32 tid = threadIdx.x, lane = tid & 31;
+    const u32 lt_mask = (1u << lane) - 1;
+    if (tid < GF) { s_occ[tid] = 0; s_free[tid] = 0; s_new[tid] = 0; }
+    for (int q = tid; q < 4 * SUMT; q += AP_THREADS) (&s_sum[0][0])[q] = sum_tab[q];
+    u32 w_occ = 0, w_free = 0;                  // lane f of each warp accumulates frame f
     LocalAcc acc; acc_init(acc);
-    for (u32 base = blockIdx.x * AP_THREADS; base < n_live; base += live_blocks * AP_THREADS) {   // block-uniform
-        const u32 i = base + threadIdx.x;
-        const bool live = i < n_live;
-        // entry -> registers; the loads are issued before anything waits on them
-        u64 key = 0; u32 s = 0;
-        ulonglong2 c2[GF / 2];
+    const u32 n_tiles = n_slots / AP_THREADS;
+    for (u32 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const u32 s = tile * AP_THREADS + tid;
+        const u64 key = __ldcg(&skeys[s]);
+        bool live = key != EMPTY_KEY;
+        // also the barrier that lets the previous tile's readers of the staging arrays finish
+        if (!__syncthreads_or(live)) continue;
+        if (tid == 0) { s_nA = 0; s_nB = 0; }
+        // ---- 1. entry -> registers, wipe, probe, per-frame counts, stage
+        CT c[GF];
 #pragma unroll
-        for (int q = 0; q < GF / 2; ++q) c2[q] = make_ulonglong2(0ull, 0ull);
+        for (int f = 0; f < GF; ++f) c[f] = 0;
         u64 slot = ~0ull; bool fresh = false; double L = 0.0;
         if (live) {
-            s = __ldcs(&slist[i]);
-            key = __ldcg(&skeys[s]);
-            ulonglong2 *cp = reinterpret_cast<ulonglong2 *>(scnt + (size_t)s * GF);
+            uint4 *cp = reinterpret_cast<uint4 *>(scnt + (size_t)s * GF);
+            constexpr int NV = (int)(sizeof(CT) * GF / 16);
+            uint4 raw[NV];
 #pragma unroll
-            for (int q = 0; q < GF / 2; ++q) c2[q] = __ldcg(cp + q);
+            for (int q = 0; q < NV; ++q) raw[q] = __ldcg(cp + q);
             slot = table_find_or_insert(table, tmask, key, fresh, L);
-            if (slot == ~0ull) atomicOr(&mc->err, ERR_TABLEFULL);
+            if (slot == ~0ull) { atomicOr(&mc->err, ERR_TABLEFULL); live = false; }
             skeys[s] = EMPTY_KEY;                                   // entry is ready for the next chunk
 #pragma unroll
-            for (int q = 0; q < GF / 2; ++q) cp[q] = make_ulonglong2(0ull, 0ull);
+            for (int q = 0; q < NV; ++q) cp[q] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                if (sizeof(CT) == 4) {
+                    c[4 * q] = (CT)raw[q].x; c[4 * q + 1] = (CT)raw[q].y; c[4 * q + 2] = (CT)raw[q].z; c[4 * q + 3] = (CT)raw[q].w;
+                } else {
+                    c[2 * q] = (CT)(((u64)raw[q].y << 32) | raw[q].x); c[2 * q + 1] = (CT)(((u64)raw[q].w << 32) | raw[q].z);
+                }
+            }
         }
-        bool pending_new = fresh;
+        u32 mask = 0; bool any_occ = false;
 #pragma unroll
         for (int f = 0; f < GF; ++f) {
             if (f < g) {                                            // uniform
-                const u64 c = (f & 1) ? c2[f >> 1].y : c2[f >> 1].x;
-                const bool hit = c != 0ull;
-                const u32 n_occ = (u32)(c >> 32), n_free = (u32)(c & 0xffffffffu);
-                const bool occ_typed = n_occ > 0;                   // occupied has priority (:544-545)
-                if (hit) L = apply_one(L, seq_avg(n_free, n_occ, s_sum, p), occ_typed, p);
-                const u32 b_occ = __ballot_sync(0xffffffffu, hit && occ_typed);
-                const u32 b_free = __ballot_sync(0xffffffffu, hit && !occ_typed);
-                const u32 b_new = __ballot_sync(0xffffffffu, hit && pending_new);
-                if (hit) pending_new = false;
-                if (lane == (u32)f) { w_occ += __popc(b_occ); w_free += __popc(b_free); w_new += __popc(b_new); }
+                const bool hit = live && c[f] != 0;
+                const bool occ = hit && Lane<CT>::n_occ(c[f]) > 0;  // occupied has priority (:544-545)
+                const u32 b_occ = __ballot_sync(0xffffffffu, occ);
+                const u32 b_free = __ballot_sync(0xffffffffu, hit && !occ);
+                if (lane == (u32)f) { w_occ += __popc(b_occ); w_free += __popc(b_free); }
+                if (hit) mask |= 1u << f;
+                any_occ |= occ;
             }
         }
-        if (live && slot != ~0ull) {
-            table[slot].val = L;
+        live = live && mask != 0;
+        if (live) {
+#pragma unroll
+            for (int f = 0; f < GF; ++f) s_lane[tid * ROW + f] = c[f];
+            s_L[tid] = L; s_slot[tid] = slot; s_mask[tid] = (unsigned short)mask;
+            if (fresh) atomicAdd(&s_new[__ffs(mask) - 1], 1u);       // len(voxels) grows at the first frame that touched it
             acc_key(acc, key);
+        }
+        __syncthreads();
+        // ---- 2. list the live entries, adaptive candidates first
+        {
+            const bool isA = live && any_occ && p.adaptive;
+            const u32 mA = __ballot_sync(0xffffffffu, isA), mB = __ballot_sync(0xffffffffu, live && !isA);
+            u32 bA = 0, bB = 0;
+            if (lane == 0) { if (mA) bA = atomicAdd(&s_nA, (u32)__popc(mA)); if (mB) bB = atomicAdd(&s_nB, (u32)__popc(mB)); }
+            bA = __shfl_sync(0xffffffffu, bA, 0); bB = __shfl_sync(0xffffffffu, bB, 0);
+            if (isA) s_ordA[bA + __popc(mA & lt_mask)] = (unsigned short)tid;
+            else if (live) s_ordB[bB + __popc(mB & lt_mask)] = (unsigned short)tid;
+        }
+        __syncthreads();
+        // ---- 3. one thread per listed entry: the frames that touched the voxel, in order
+        {
+            const u32 nA = s_nA, nB = s_nB;
+            if (tid < nA + nB) {
+                const u32 e = tid < nA ? s_ordA[tid] : s_ordB[tid - nA];
+                u32 todo = s_mask[e];
+                double Lv = s_L[e];
+                const CT *row = s_lane + e * ROW;
+                while (todo) {
+                    const int f = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const CT cf = row[f];
+                    const u32 n_occ = Lane<CT>::n_occ(cf), n_free = Lane<CT>::n_free(cf);
+                    Lv = apply_one(Lv, seq_avg(n_free, n_occ, s_sum, p), n_occ > 0, p);
+                }
+                table[s_slot[e]].val = Lv;
+            }
         }
     }
     acc_publish(acc, mc, false);
+    __syncthreads();
     if (lane < GF) {
         if (w_occ) atomicAdd(&s_occ[lane], w_occ);
         if (w_free) atomicAdd(&s_free[lane], w_free);
-        if (w_new) atomicAdd(&s_new[lane], w_new);
     }
     __syncthreads();
-    if (threadIdx.x < g) {
-        const int f = threadIdx.x;
+    if (tid < (u32)g) {
+        const int f = tid;
         if (s_occ[f]) atomicAdd(&st[f].n_occ, (u64)s_occ[f]);
         if (s_free[f]) atomicAdd(&st[f].n_free, (u64)s_free[f]);
         if (s_new[f]) atomicAdd(&cc->neu[f], s_new[f]);
     }
-    // last live block out: len(voxels) after each frame (:592), publish the new count, re-arm the chunk
+    // last block out: len(voxels) after each frame (:592), publish the new count, re-arm the chunk
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         __threadfence();
         const u32 t = atomicAdd(&cc->ticket, 1u);
-        s_last = (t == live_blocks - 1);
+        s_last = (t == gridDim.x - 1);
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
+    if (s_last && tid == 0) {
         __threadfence();
         u64 run = cc->count0;
         for (int f = 0; f < g; ++f) {
@@ -684,7 +841,7 @@ k_apply_chunk(u64 *__restrict__ skeys, u64 *__restrict__ scnt, const u32 *__rest
             cc->neu[f] = 0;
         }
         mc->last_new = (u32)(run - cc->count0);
-        mc->last_unique = n_live;
+        mc->last_unique = atomicAdd(&cc->n_unique, 0u);
         atomicExch(&mc->count, run);
         cc->n_unique = 0; cc->ticket = 0;
     }
@@ -699,36 +856,40 @@ k_apply_chunk(u64 *__restrict__ skeys, u64 *__restrict__ scnt, const u32 *__rest
 constexpr int REC_WORDS = 1 + GF;
 
 // pass 1: how many of the chunk's dedupe entries go to each owner
-__global__ void k_shard_count(const u64 *__restrict__ skeys, const u32 *__restrict__ slist, const ChunkCtr *cc,
-                              u32 world, u32 *owner_count)
+__global__ void k_shard_count(const u64 *__restrict__ skeys, u32 n_slots, u32 world, u32 *owner_count)
 {
     __shared__ u32 s_cnt[64];
     if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    const u32 n = cc->n_unique;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        atomicAdd(&s_cnt[key_owner(skeys[slist[i]], world)], 1u);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x) {
+        const u64 key = skeys[i];
+        if (key != EMPTY_KEY) atomicAdd(&s_cnt[key_owner(key, world)], 1u);
+    }
     __syncthreads();
     if (threadIdx.x < world && s_cnt[threadIdx.x]) atomicAdd(&owner_count[threadIdx.x], s_cnt[threadIdx.x]);
 }
 
-// pass 2: drain the dedupe table into the send buffer, records grouped by owner.
+// pass 2: drain the dedupe table into the send buffer, records grouped by owner (wire format:
+// the packed key and one (n_occ << 32 | n_free) word per frame, whatever the lane format).
 // owner_base[o] = first record of owner o (exclusive prefix of the counts), owner_fill[o] = cursor.
-__global__ void k_shard_pack(u64 *__restrict__ skeys, u64 *__restrict__ scnt, const u32 *__restrict__ slist,
-                             ChunkCtr *cc, u32 world, const u32 *__restrict__ owner_base, u32 *owner_fill,
-                             u64 *__restrict__ send)
+template <typename CT>
+__global__ void k_shard_pack(u64 *__restrict__ skeys, CT *__restrict__ scnt, u32 n_slots, u32 world,
+                             const u32 *__restrict__ owner_base, u32 *owner_fill, u64 *__restrict__ send)
 {
-    const u32 n = cc->n_unique;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const u32 s = slist[i];
+    for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
         const u64 key = skeys[s];
+        if (key == EMPTY_KEY) continue;
         const u32 o = key_owner(key, world);
         const u32 dst = owner_base[o] + atomicAdd(&owner_fill[o], 1u);
         u64 *rec = send + (size_t)dst * REC_WORDS;
         rec[0] = key;
-        u64 *cp = scnt + (size_t)s * GF;
+        CT *cp = scnt + (size_t)s * GF;
 #pragma unroll
-        for (int f = 0; f < GF; ++f) { rec[1 + f] = cp[f]; cp[f] = 0ull; }
+        for (int f = 0; f < GF; ++f) {
+            const CT c = cp[f];
+            rec[1 + f] = ((u64)Lane<CT>::n_occ(c) << 32) | (u64)Lane<CT>::n_free(c);
+            cp[f] = 0;
+        }
         skeys[s] = EMPTY_KEY;
     }
 }
@@ -736,23 +897,32 @@ __global__ void k_shard_pack(u64 *__restrict__ skeys, u64 *__restrict__ scnt, co
 __global__ void k_shard_reset_cc(ChunkCtr *cc) { cc->n_unique = 0; cc->ticket = 0; }
 
 // owner side: merge received records into the (empty) dedupe table
-__global__ void k_shard_merge(const u64 *__restrict__ recv, u64 n_rec, u64 *skeys, u64 *scnt, u32 *slist, u32 smask,
-                              ChunkCtr *cc, MapCtr *mc)
+template <typename CT>
+__global__ void k_shard_merge(const u64 *__restrict__ recv, u64 n_rec, u64 *skeys, CT *scnt, u32 smask, ChunkCtr *cc,
+                              MapCtr *mc, u64 seq)
 {
     for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n_rec; i += (u64)gridDim.x * blockDim.x) {
         const u64 *rec = recv + i * REC_WORDS;
         const u64 key = rec[0];
-        const u32 base = mix32(key) & smask & ~3u;
+        const u32 base = dedupe_home(key, smask);
         bool created;
         const u32 slot = dedupe_slot(skeys, smask, key, base, load_bucket(skeys, base), created);
-        const bool done = slot != ~0u;
-        if (done) {
-            if (created) slist[atomicAdd(&cc->n_unique, 1u) & smask] = slot;
+        if (slot == ~0u) { raise_abort(mc, ABORT_SCRATCH, seq); continue; }
+        if (created) atomicAdd(&cc->n_unique, 1u);
 #pragma unroll
-            for (int f = 0; f < GF; ++f)
-                if (rec[1 + f]) atomicAdd(&scnt[(size_t)slot * GF + f], rec[1 + f]);
+        for (int f = 0; f < GF; ++f) {
+            const u64 w = rec[1 + f];
+            if (!w) continue;
+            const u32 n_occ = (u32)(w >> 32), n_free = (u32)(w & 0xffffffffu);
+            if (Lane<CT>::narrow) {
+                if ((n_occ | n_free) > 0xffffu) { raise_abort(mc, ABORT_NARROW, seq); continue; }
+                const CT inc = Lane<CT>::make(n_occ, n_free);
+                const CT old = atomicAdd(&scnt[(size_t)slot * GF + f], inc);
+                if (Lane<CT>::overflows(old, inc)) raise_abort(mc, ABORT_NARROW, seq);
+            } else {
+                atomicAdd(&scnt[(size_t)slot * GF + f], Lane<CT>::make(n_occ, n_free));
+            }
         }
-        if (!done) atomicOr(&mc->err, ERR_TABLEFULL);
     }
 }
 
@@ -773,7 +943,7 @@ __global__ void k_fill_u64(u64 *t, u64 n, u64 v)
 __global__ void k_clear_abort(MapCtr *mc, ChunkCtr *cc)
 {
     mc->abort = 0; mc->abort_seq = ~0ull;
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < N_CHUNK_BUF; ++b) {
         cc[b].count0 = 0; cc[b].n_unique = 0; cc[b].ticket = 0;
         for (int f = 0; f < GF; ++f) cc[b].neu[f] = 0;
     }
@@ -968,7 +1138,7 @@ struct s3d_map {
     MapCtr *mc_host = nullptr;       // pinned mirror
     u64 count_known = 0;             // live voxels at the last sync / chunk snapshot
     u64 unique_est = 0;              // voxels touched by a recent chunk (upper bound of what it can insert)
-    static constexpr int RING = 4;   // per-chunk counter snapshots (bounded launch-ahead)
+    static constexpr int RING = 8;   // per-chunk counter snapshots (bounded launch-ahead)
     MapCtr *snap_host = nullptr;     // pinned [RING]
     cudaEvent_t snap_ev[RING] = {};
     InFlight inflight[RING];
@@ -982,7 +1152,6 @@ struct s3d_map {
     DevBuf<u64> send_buf; DevBuf<u32> owner_ctr;      // owner_ctr: [3][64] count / base / fill
     u32 *owner_host = nullptr;                        // pinned [64]
     int l2_policy = 0;               // S3D_L2_POLICY: 0 = no window, 1 = persisting + streaming misses, 2 = persisting + normal
-    int dbg_stage = 0;               // S3D_DEBUG_STAGE: stage-ablation timing experiments (tools/dbg_stage.sh)
     // params / tables
     bool have_params = false, have_tables = false;
     DevParams p{};
@@ -995,15 +1164,18 @@ struct s3d_map {
     // chunk dedupe table: one allocation {counters[C][GF], keys[C], list[C]} so that a single L2
     // access-policy window can keep it resident between the kernels of a chunk
     DevBuf<uint8_t> spool; u64 scratch_cap = 0;
-    u64 *skeys = nullptr, *scnt = nullptr; u32 *slist = nullptr;     // buffer 0 (also the sharded path's)
-    // two chunk buffers: k_expand of chunk c+1 (expand stream) overlaps k_apply_chunk of chunk c
-    struct ChunkBuf { u64 *skeys = nullptr, *scnt = nullptr; u32 *slist = nullptr; ChunkCtr *cc = nullptr;
-                      int *first_hit = nullptr; cudaEvent_t expanded = nullptr, freed = nullptr; bool used = false; };
-    ChunkBuf buf[2];
-    cudaStream_t xstream = nullptr;  // expand stream
+    bool wide = false;               // counter lanes: u32 (16+16 bits) normally, u64 after a count overflowed
+    u64 *skeys = nullptr; void *scnt = nullptr;                      // buffer 0 (also the sharded path's)
+    // NBUF chunk buffers and two expand streams: k_expand of chunks c+1 and c+2 overlap each other
+    // and k_apply_chunk of chunk c (a chunk alone does not fill the GPU)
+    static constexpr int NBUF = N_CHUNK_BUF;
+    struct ChunkBuf { u64 *skeys = nullptr; void *scnt = nullptr; ChunkCtr *cc = nullptr;
+                      cudaEvent_t expanded = nullptr, freed = nullptr; bool used = false; };
+    ChunkBuf buf[NBUF];
+    cudaStream_t xstream = nullptr, xstream2 = nullptr;  // expand streams (chunks alternate)
+    cudaEvent_t x_ev = nullptr;      // orders work queued on xstream before xstream2
     size_t l2_persist_max = 0, l2_window_max = 0, l2_window = 0;
     DevBuf<double> sum_tab;          // [4][SUMT] running sums of n copies of lo_free / lo_occ, and their means
-    DevBuf<int> first_hit;
     ChunkCtr *cc = nullptr;
     DevBuf<DevStats> stats; DevStats *stats_host = nullptr; size_t stats_host_n = 0;
     // staging
@@ -1042,6 +1214,7 @@ int prof_collect(s3d_map *m)
 {
     if (m->spans.empty()) { m->ev_used = 0; return 0; }
     CU(cudaStreamSynchronize(m->xstream));
+    CU(cudaStreamSynchronize(m->xstream2));
     CU(cudaStreamSynchronize(m->stream));
     for (const auto &sp : m->spans) {
         float ms = 0.f;
@@ -1127,51 +1300,41 @@ template <typename T> int upload(DevBuf<T> &b, const T *src, size_t n, cudaStrea
     return 0;
 }
 
-// (re)allocate and wipe the chunk dedupe table; the stream must be idle
-int ensure_scratch(s3d_map *m, u64 want_cap, bool wipe)
+size_t lane_bytes(const s3d_map *m) { return m->wide ? sizeof(u64) : sizeof(u32); }
+
+// (re)allocate and wipe the chunk dedupe tables; the streams must be idle
+int ensure_scratch(s3d_map *m, u64 want_cap, bool wipe, bool force_realloc = false)
 {
     want_cap = next_pow2(std::max<u64>(want_cap, 1u << 12));
     if (want_cap > (1ull << 31)) return fail(S3D_ENOMEM, "chunk dedupe table would exceed 2^31 entries");
-    const bool realloc = want_cap > m->scratch_cap;
+    const bool realloc = want_cap > m->scratch_cap || force_realloc;
+    const size_t cnt_bytes = lane_bytes(m) * (size_t)std::max<u64>(want_cap, m->scratch_cap) * GF;
     if (realloc) {
-        const size_t cnt_bytes = sizeof(u64) * (size_t)want_cap * GF, key_bytes = sizeof(u64) * (size_t)want_cap;
-        const size_t one = cnt_bytes + key_bytes + sizeof(u32) * (size_t)want_cap;
-        const size_t pool = 2 * one;
+        want_cap = std::max<u64>(want_cap, m->scratch_cap);
+        const size_t key_bytes = sizeof(u64) * (size_t)want_cap;
+        const size_t one = cnt_bytes + key_bytes;
+        const size_t pool = s3d_map::NBUF * one;
         CU(cudaStreamSynchronize(m->xstream));
+        CU(cudaStreamSynchronize(m->xstream2));
+        CU(cudaStreamSynchronize(m->stream));
         int rc = m->spool.ensure(pool); if (rc) return rc;
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < s3d_map::NBUF; ++b) {
             uint8_t *base = m->spool.p + (size_t)b * one;
-            m->buf[b].scnt = reinterpret_cast<u64 *>(base);
+            m->buf[b].scnt = base;
             m->buf[b].skeys = reinterpret_cast<u64 *>(base + cnt_bytes);
-            m->buf[b].slist = reinterpret_cast<u32 *>(base + cnt_bytes + key_bytes);
             m->buf[b].used = false;
         }
-        m->scnt = m->buf[0].scnt; m->skeys = m->buf[0].skeys; m->slist = m->buf[0].slist;
+        m->scnt = m->buf[0].scnt; m->skeys = m->buf[0].skeys;
         m->scratch_cap = want_cap;
-        // The dedupe table is hit by every sample of a chunk and re-read by the apply kernel:
-        // ask L2 to keep it (persisting window) while images and voxel-table traffic stream by.
-        if (m->l2_persist_max > 0 && m->l2_window_max > 0 && m->l2_policy > 0) {
-            const size_t win = std::min(pool, m->l2_window_max);
-            const size_t carve = std::min(win, m->l2_persist_max);
-            CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
-            cudaStreamAttrValue av{};
-            av.accessPolicyWindow.base_ptr = m->spool.p;
-            av.accessPolicyWindow.num_bytes = win;
-            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)win);
-            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            av.accessPolicyWindow.missProp = m->l2_policy == 1 ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
-            CU(cudaStreamSetAttribute(m->stream, cudaStreamAttributeAccessPolicyWindow, &av));
-            CU(cudaStreamSetAttribute(m->xstream, cudaStreamAttributeAccessPolicyWindow, &av));
-            m->l2_window = win;
-        }
     }
     if (realloc || wipe) {
         const int blocks = (int)std::min<u64>((m->scratch_cap + 255) / 256, (u64)m->n_sm * 16);
         CU(cudaStreamSynchronize(m->xstream));
-        for (int b = 0; b < 2; ++b) {
+        CU(cudaStreamSynchronize(m->xstream2));
+        for (int b = 0; b < s3d_map::NBUF; ++b) {
             k_fill_u64<<<blocks, 256, 0, m->stream>>>(m->buf[b].skeys, m->scratch_cap, EMPTY_KEY);
             CU(cudaGetLastError());
-            CU(cudaMemsetAsync(m->buf[b].scnt, 0, sizeof(u64) * (size_t)m->scratch_cap * GF, m->stream));
+            CU(cudaMemsetAsync(m->buf[b].scnt, 0, cnt_bytes, m->stream));
             m->buf[b].used = false;
         }
         CU(cudaStreamSynchronize(m->stream));
@@ -1179,45 +1342,59 @@ int ensure_scratch(s3d_map *m, u64 want_cap, bool wipe)
     return 0;
 }
 
+void launch_expand(s3d_map *m, const ExpandArgs &a, int n_beams, int g, cudaStream_t st)
+{
+    const size_t smem = expand_smem_bytes(a.tab.H, a.tab.free_step, a.tab.occ_window);
+    const dim3 grid((n_beams + EX_WARPS - 1) / EX_WARPS, g);
+    if (m->wide) k_expand<u64><<<grid, EX_THREADS, smem, st>>>(a);
+    else k_expand<u32><<<grid, EX_THREADS, smem, st>>>(a);
+    m->launches += 1;
+}
+
+void launch_apply(s3d_map *m, u64 *skeys, void *scnt, int g, ChunkCtr *cc, DevStats *st, cudaStream_t stream)
+{
+    const int blocks = (int)std::min<u64>(m->scratch_cap / AP_THREADS, (u64)m->n_sm * 4);
+    if (m->wide)
+        k_apply_chunk<u64><<<blocks, AP_THREADS, 0, stream>>>(skeys, static_cast<u64 *>(scnt), (u32)m->scratch_cap, g, cc, st,
+                                                             m->table, m->cap - 1, m->p, m->sum_tab.p, m->mc);
+    else
+        k_apply_chunk<u32><<<blocks, AP_THREADS, 0, stream>>>(skeys, static_cast<u32 *>(scnt), (u32)m->scratch_cap, g, cc, st,
+                                                             m->table, m->cap - 1, m->p, m->sum_tab.p, m->mc);
+    m->launches += 1;
+}
+
 int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
 {
     const DevTables &tab = m->tab;
     const size_t img_stride = (size_t)tab.H * tab.W;
     const uint8_t *imgs = j.imgs + (size_t)base * img_stride;
-    const int max_f = (tab.H + tab.free_step - 1) / tab.free_step;
-    const size_t ex_smem = sizeof(int) * (size_t)EX_BEAMS * (size_t)(2 * max_f + 1 + 2 * tab.occ_window);
-    s3d_map::ChunkBuf &cb = m->buf[m->chunk_seq & 1];
-    cudaStream_t xs = m->xstream, as = m->stream;
+    s3d_map::ChunkBuf &cb = m->buf[m->chunk_seq % s3d_map::NBUF];
+    cudaStream_t xs = (m->chunk_seq & 1) ? m->xstream2 : m->xstream, as = m->stream;
     // ---- expand stream: first hits + expansion into this chunk's dedupe buffer.  It may run while
-    // the previous chunk is still being applied; it only waits for its own buffer to be drained.
+    // earlier chunks are still being expanded or applied; it only waits for its own buffer to be drained.
     if (cb.used) CU(cudaStreamWaitEvent(xs, cb.freed, 0));
     const size_t e1 = m->prof_on ? prof_mark(m, xs) : 0;
     ExpandArgs a;
     a.imgs = imgs; a.img_stride = img_stride;
     a.T = j.T + base * 16;
     a.tab = tab; a.p = m->p;
-    a.skeys = cb.skeys; a.scnt = cb.scnt; a.smask = (u32)(m->scratch_cap - 1); a.slist = cb.slist;
+    a.skeys = cb.skeys; a.scnt = cb.scnt; a.smask = (u32)(m->scratch_cap - 1);
     a.cc = cb.cc; a.stats = j.stats + base; a.mc = m->mc;
     a.seq = m->chunk_seq;
-    a.dbg = m->dbg_stage;
     a.beam_lo = 0; a.beam_hi = tab.n_beams;
     a.own_rank = (u32)m->shard_rank; a.own_world = m->shard_filter ? (u32)m->shard_world : 1u;
-    k_expand<<<dim3((tab.n_beams + EX_BEAMS - 1) / EX_BEAMS, g), EX_THREADS, ex_smem, xs>>>(a);
+    launch_expand(m, a, tab.n_beams, g, xs);
     const size_t e2 = m->prof_on ? prof_mark(m, xs) : 0;
     CU(cudaEventRecord(cb.expanded, xs));
     // ---- apply stream: gate, then the chunk's frames in order into the voxel table
     CU(cudaStreamWaitEvent(as, cb.expanded, 0));
     const size_t e3 = m->prof_on ? prof_mark(m, as) : 0;
     k_gate<<<1, 1, 0, as>>>(cb.cc, m->mc, table_limit(m), m->chunk_seq);
-    // one thread per dedupe entry the chunk can have created; blocks past the live count exit at once
-    const u64 ap_want = std::max<u64>((u64)m->n_sm * 4, (m->unique_est + m->unique_est / 4) / AP_THREADS + 1);
-    const int ap_blocks = (int)std::min<u64>((m->scratch_cap + AP_THREADS - 1) / AP_THREADS, ap_want);
-    k_apply_chunk<<<ap_blocks, AP_THREADS, 0, as>>>(cb.skeys, cb.scnt, cb.slist, g, cb.cc, j.stats + base, m->table,
-                                                  m->cap - 1, m->p, m->sum_tab.p, m->mc);
+    launch_apply(m, cb.skeys, cb.scnt, g, cb.cc, j.stats + base, as);
     CU(cudaGetLastError());
     CU(cudaEventRecord(cb.freed, as));
     cb.used = true;
-    m->launches += 3;
+    m->launches += 1;
     if (m->prof_on) {
         const size_t e4 = prof_mark(m, as);
         m->spans.push_back({e1, e2, S3D_K_EXPAND});
@@ -1240,6 +1417,7 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
 int recover(s3d_map *m)
 {
     CU(cudaStreamSynchronize(m->xstream));          // later chunks may still be expanding
+    CU(cudaStreamSynchronize(m->xstream2));
     CU(cudaMemcpyAsync(m->mc_host, m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, m->stream));
     CU(cudaStreamSynchronize(m->stream));
     const MapCtr mc = *m->mc_host;
@@ -1253,7 +1431,9 @@ int recover(s3d_map *m)
     if (mc.abort & ABORT_TABLE) {
         if ((rc = grow_table(m, m->cap * 2))) return rc;
     }
-    if ((rc = ensure_scratch(m, (mc.abort & ABORT_SCRATCH) ? m->scratch_cap * 2 : m->scratch_cap, true))) return rc;
+    const bool widen = (mc.abort & ABORT_NARROW) && !m->wide;
+    if (widen) m->wide = true;
+    if ((rc = ensure_scratch(m, (mc.abort & ABORT_SCRATCH) ? m->scratch_cap * 2 : m->scratch_cap, true, widen))) return rc;
     k_clear_abort<<<1, 1, 0, m->stream>>>(m->mc, m->cc);
     CU(cudaGetLastError());
     bool hit = false;
@@ -1271,8 +1451,9 @@ int recover(s3d_map *m)
 // until everything is applied (re-running chunks that asked for a retry).
 int pump(s3d_map *m, bool drain)
 {
-    constexpr int LOOKAHEAD = 1;          // chunks allowed in flight behind the one being enqueued
+    constexpr int LOOKAHEAD = 2;          // chunks allowed in flight behind the one being enqueued
     static_assert(LOOKAHEAD + 2 <= s3d_map::RING, "snapshot ring too small");
+    static_assert(LOOKAHEAD + 2 <= s3d_map::NBUF, "a chunk buffer per chunk in flight");
     for (;;) {
         Job *job = nullptr;
         for (Job &j : m->jobs) if (j.next < j.n) { job = &j; break; }
@@ -1325,6 +1506,8 @@ int submit_frames(s3d_map *m, const uint8_t *imgs_dev, int64_t n, const double *
 {
     // zeroed on the expand stream: k_expand is the first writer (num_samples)
     CU(cudaMemsetAsync(stats_dev, 0, sizeof(DevStats) * (size_t)n, m->xstream));
+    CU(cudaEventRecord(m->x_ev, m->xstream));
+    CU(cudaStreamWaitEvent(m->xstream2, m->x_ev, 0));
     if (m->tab.n_beams == 0 || m->tab.H == 0) {
         // nothing to expand; len(voxels) still has to be reported
         int rc = pump(m, true); if (rc) return rc;
@@ -1404,7 +1587,6 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     m->n_sm = prop.multiProcessorCount;
-    { const char *e = getenv("S3D_DEBUG_STAGE"); m->dbg_stage = e ? atoi(e) : 0; }
     { const char *e = getenv("S3D_L2_POLICY"); if (e) m->l2_policy = atoi(e); }
     m->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     m->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
@@ -1415,9 +1597,12 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
     for (int i = 0; i < s3d_map::RING; ++i) CU(cudaEventCreateWithFlags(&m->snap_ev[i], cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&m->xstream, cudaStreamNonBlocking));
-    CU(cudaMalloc(&m->cc, sizeof(ChunkCtr) * 2));
-    CU(cudaMemsetAsync(m->cc, 0, sizeof(ChunkCtr) * 2, m->stream));
-    for (int b = 0; b < 2; ++b) {
+    CU(cudaStreamCreateWithFlags(&m->xstream2, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&m->x_ev, cudaEventDisableTiming));
+    { const char *e = getenv("S3D_WIDE_LANES"); m->wide = e && atoi(e) != 0; }
+    CU(cudaMalloc(&m->cc, sizeof(ChunkCtr) * s3d_map::NBUF));
+    CU(cudaMemsetAsync(m->cc, 0, sizeof(ChunkCtr) * s3d_map::NBUF, m->stream));
+    for (int b = 0; b < s3d_map::NBUF; ++b) {
         m->buf[b].cc = m->cc + b;
         CU(cudaEventCreateWithFlags(&m->buf[b].expanded, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&m->buf[b].freed, cudaEventDisableTiming));
@@ -1443,11 +1628,13 @@ int s3d_destroy(s3d_map *m)
     if (m->snap_host) cudaFreeHost(m->snap_host);
     for (int i = 0; i < s3d_map::RING; ++i) if (m->snap_ev[i]) cudaEventDestroy(m->snap_ev[i]);
     if (m->cc) cudaFree(m->cc);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < s3d_map::NBUF; ++b) {
         if (m->buf[b].expanded) cudaEventDestroy(m->buf[b].expanded);
         if (m->buf[b].freed) cudaEventDestroy(m->buf[b].freed);
     }
     if (m->xstream) { cudaStreamSynchronize(m->xstream); cudaStreamDestroy(m->xstream); }
+    if (m->xstream2) { cudaStreamSynchronize(m->xstream2); cudaStreamDestroy(m->xstream2); }
+    if (m->x_ev) cudaEventDestroy(m->x_ev);
     if (m->owner_host) cudaFreeHost(m->owner_host);
     m->send_buf.release(); m->owner_ctr.release();
     for (cudaEvent_t e : m->copy_ev) cudaEventDestroy(e);
@@ -1457,7 +1644,7 @@ int s3d_destroy(s3d_map *m)
     if (m->stats_host) cudaFreeHost(m->stats_host);
     m->d_beam_col.release(); m->d_nv_free.release(); m->d_nv_occ.release();
     m->d_cos_b.release(); m->d_sin_b.release(); m->d_range.release(); m->d_cos_va.release(); m->d_sin_va.release();
-    m->d_col_to_beam.release(); m->spool.release(); m->sum_tab.release(); m->first_hit.release(); m->stats.release();
+    m->d_col_to_beam.release(); m->spool.release(); m->sum_tab.release(); m->stats.release();
     m->img_dev.release(); m->T_dev.release(); m->io_keys.release(); m->io_vals.release(); m->io_flags.release();
     m->ex_xyz.release(); m->ex_prob.release(); m->ex_L.release(); m->ex_cls.release(); m->ex_ijk.release(); m->ex_f32.release();
     for (cudaEvent_t e : m->ev_pool) cudaEventDestroy(e);
@@ -1480,6 +1667,14 @@ int s3d_set_params(s3d_map *m, const s3d_params *q)
     p.l_skip = (p.a_thr > 1e-3 && p.a_thr < 1.0 - 1e-3) ? std::log(p.a_thr / (1.0 - p.a_thr)) + 1e-6
                                                          : std::numeric_limits<double>::infinity();
     p.thr = std::max(-1, std::min(255, q->intensity_threshold));
+    {
+        // fast quantiser: fractional parts in (1e-6, 1 - 1e-6) are decided by the reciprocal product
+        const double lo = 1e-6, hi = 1.0 - 1e-6;
+        u64 blo, bhi;
+        memcpy(&blo, &lo, 8); memcpy(&bhi, &hi, 8);
+        p.fr_hi_lo = (u32)(blo >> 32) + 1u;
+        p.fr_hi_span = (u32)(bhi >> 32) - p.fr_hi_lo;
+    }
     {
         // running sums, one addition at a time, exactly as `sum += log_odds` accumulates them
         int rc = set_device(m); if (rc) return rc;
@@ -1505,6 +1700,8 @@ int s3d_set_tables(s3d_map *m, const s3d_tables *t)
         return fail(S3D_EINVAL, "bad table shape");
     if (t->free_step < 1 || t->occ_window < 0) return fail(S3D_EINVAL, "bad free_step/occ_window");
     if (t->H >= (1 << 16) || t->nv_max >= (1 << 15)) return fail(S3D_EINVAL, "H or nv_max too large");
+    const size_t ex_smem = expand_smem_bytes(t->H, t->free_step, t->occ_window);
+    if (ex_smem > 200 * 1024) return fail(S3D_EINVAL, "image height %d needs %zu bytes of shared memory per block", t->H, ex_smem);
     int rc = set_device(m); if (rc) return rc;
     if ((rc = sync_counters(m))) return rc;
     const size_t nb = (size_t)t->n_beams, H = (size_t)t->H;
@@ -1546,8 +1743,8 @@ int s3d_set_tables(s3d_map *m, const s3d_tables *t)
     d.nv_free = m->d_nv_free.p; d.nv_occ = m->d_nv_occ.p; d.cos_va = m->d_cos_va.p; d.sin_va = m->d_sin_va.p;
     d.col_to_beam = m->d_col_to_beam.p;
     m->have_tables = true;
-    if ((rc = m->first_hit.ensure((size_t)2 * GF * std::max(1, t->n_beams)))) return rc;
-    for (int b = 0; b < 2; ++b) m->buf[b].first_hit = m->first_hit.p + (size_t)b * GF * std::max(1, t->n_beams);
+    CU(cudaFuncSetAttribute(k_expand<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+    CU(cudaFuncSetAttribute(k_expand<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
     // first guess for the chunk dedupe table; it doubles on demand (retry) from here
     return ensure_scratch(m, std::min<u64>(1u << 20, std::max<u64>(1u << 14, m->samples_max / 4)), false);
 }
@@ -1609,6 +1806,7 @@ int s3d_ingest_batch(s3d_map *m, const uint8_t *images, int64_t n, const double 
         for (int64_t s0 = 0; s0 < k; s0 += sub, ++ei) {
             const int64_t kk = std::min<int64_t>(sub, k - s0);
             CU(cudaStreamWaitEvent(m->xstream, m->copy_ev[ei], 0));
+            CU(cudaStreamWaitEvent(m->xstream2, m->copy_ev[ei], 0));
             if ((rc = submit_frames(m, m->img_dev.p + (size_t)s0 * img_bytes, kk, m->T_dev.p + s0 * 16, m->stats.p + base + s0))) return rc;
         }
     }
@@ -1667,30 +1865,29 @@ int s3d_shard_expand(s3d_map *m, const uint8_t *images_dev, const double *T_dev,
         CU(cudaMemsetAsync(st, 0, sizeof(DevStats) * (size_t)g, m->stream));
         u32 n_unique = 0;
         if (tab.n_beams > 0 && tab.H > 0 && hi > lo) {
-            const int max_f = (tab.H + tab.free_step - 1) / tab.free_step;
-            const size_t ex_smem = sizeof(int) * (size_t)EX_BEAMS * (size_t)(2 * max_f + 1 + 2 * tab.occ_window);
             ExpandArgs a;
             a.imgs = images_dev; a.img_stride = img_stride; a.T = T_dev;
             a.tab = tab; a.p = m->p;
-            a.skeys = m->skeys; a.scnt = m->scnt; a.smask = (u32)(m->scratch_cap - 1); a.slist = m->slist;
+            a.skeys = m->skeys; a.scnt = m->scnt; a.smask = (u32)(m->scratch_cap - 1);
             a.cc = m->cc; a.stats = st; a.mc = m->mc;
             a.seq = m->chunk_seq;                                // the owner gates growth, not the expander
-            a.dbg = 0; a.beam_lo = lo; a.beam_hi = hi;
+            a.beam_lo = lo; a.beam_hi = hi;
             a.own_rank = 0; a.own_world = 1;
-            k_expand<<<dim3((hi - lo + EX_BEAMS - 1) / EX_BEAMS, g), EX_THREADS, ex_smem, m->stream>>>(a);
-            m->launches += 1;
+            launch_expand(m, a, hi - lo, g, m->stream);
         }
         // counts per owner -> host (the all-to-all needs the split sizes), and the retry flag
         CU(cudaMemsetAsync(m->owner_ctr.p, 0, sizeof(u32) * 3 * 64, m->stream));
-        k_shard_count<<<m->n_sm * 2, 256, 0, m->stream>>>(m->skeys, m->slist, m->cc, world, m->owner_ctr.p);
+        k_shard_count<<<m->n_sm * 2, 256, 0, m->stream>>>(m->skeys, (u32)m->scratch_cap, world, m->owner_ctr.p);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(m->owner_host, m->owner_ctr.p, sizeof(u32) * 64, cudaMemcpyDeviceToHost, m->stream));
         CU(cudaMemcpyAsync(m->mc_host, m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, m->stream));
         CU(cudaStreamSynchronize(m->stream));
         ++m->chunk_seq; m->snap_floor = m->chunk_seq;
-        if (m->mc_host->abort) {             // dedupe table too small for this chunk: enlarge, wipe, redo
+        if (m->mc_host->abort) {             // dedupe table too small, or a count overflowed: enlarge / widen, wipe, redo
             ++m->n_retries;
-            if ((rc = ensure_scratch(m, m->scratch_cap * 2, true))) return rc;
+            const bool widen = (m->mc_host->abort & ABORT_NARROW) && !m->wide;
+            if (widen) m->wide = true;
+            if ((rc = ensure_scratch(m, (m->mc_host->abort & ABORT_SCRATCH) ? m->scratch_cap * 2 : m->scratch_cap, true, widen))) return rc;
             k_clear_abort<<<1, 1, 0, m->stream>>>(m->mc, m->cc);
             CU(cudaGetLastError());
             continue;
@@ -1700,8 +1897,12 @@ int s3d_shard_expand(s3d_map *m, const uint8_t *images_dev, const double *T_dev,
         for (u32 o = 0; o < world; ++o) { base[o] = n_unique; n_unique += m->owner_host[o]; counts[o] = m->owner_host[o]; }
         if ((rc = m->send_buf.ensure((size_t)std::max<u32>(n_unique, 1) * REC_WORDS))) return rc;
         CU(cudaMemcpyAsync(m->owner_ctr.p + 64, base, sizeof(u32) * 64, cudaMemcpyHostToDevice, m->stream));
-        k_shard_pack<<<m->n_sm * 2, 256, 0, m->stream>>>(m->skeys, m->scnt, m->slist, m->cc, world,
-                                                        m->owner_ctr.p + 64, m->owner_ctr.p + 128, m->send_buf.p);
+        if (m->wide)
+            k_shard_pack<u64><<<m->n_sm * 2, 256, 0, m->stream>>>(m->skeys, static_cast<u64 *>(m->scnt), (u32)m->scratch_cap, world,
+                                                                 m->owner_ctr.p + 64, m->owner_ctr.p + 128, m->send_buf.p);
+        else
+            k_shard_pack<u32><<<m->n_sm * 2, 256, 0, m->stream>>>(m->skeys, static_cast<u32 *>(m->scnt), (u32)m->scratch_cap, world,
+                                                                 m->owner_ctr.p + 64, m->owner_ctr.p + 128, m->send_buf.p);
         k_shard_reset_cc<<<1, 1, 0, m->stream>>>(m->cc);
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(m->stream));
@@ -1725,18 +1926,39 @@ int s3d_shard_apply(s3d_map *m, const void *records_dev, uint64_t n_records, int
     while (m->count_known + n_records > table_limit(m)) if ((rc = grow_table(m, m->cap * 2))) return rc;
     if (2 * n_records > m->scratch_cap && (rc = ensure_scratch(m, 2 * n_records, false))) return rc;
     DevStats *st = reinterpret_cast<DevStats *>(stats_dev);
-    CU(cudaMemsetAsync(st, 0, sizeof(DevStats) * (size_t)g, m->stream));
-    if (n_records) {
-        const int blocks = (int)std::min<u64>((n_records + 255) / 256, (u64)m->n_sm * 8);
-        k_shard_merge<<<blocks, 256, 0, m->stream>>>(reinterpret_cast<const u64 *>(records_dev), n_records, m->skeys,
-                                                    m->scnt, m->slist, (u32)(m->scratch_cap - 1), m->cc, m->mc);
+    for (;;) {
+        CU(cudaMemsetAsync(st, 0, sizeof(DevStats) * (size_t)g, m->stream));
+        if (n_records) {
+            const int blocks = (int)std::min<u64>((n_records + 255) / 256, (u64)m->n_sm * 8);
+            const u64 *rec = reinterpret_cast<const u64 *>(records_dev);
+            if (m->wide)
+                k_shard_merge<u64><<<blocks, 256, 0, m->stream>>>(rec, n_records, m->skeys, static_cast<u64 *>(m->scnt),
+                                                                 (u32)(m->scratch_cap - 1), m->cc, m->mc, m->chunk_seq);
+            else
+                k_shard_merge<u32><<<blocks, 256, 0, m->stream>>>(rec, n_records, m->skeys, static_cast<u32 *>(m->scnt),
+                                                                 (u32)(m->scratch_cap - 1), m->cc, m->mc, m->chunk_seq);
+            CU(cudaGetLastError());
+            // a retryable flag here (dedupe table over-loaded, or a sample count beyond 16 bits) is
+            // handled before anything touches the voxel table: the records are still in `recv`
+            CU(cudaMemcpyAsync(m->mc_host, m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, m->stream));
+            CU(cudaStreamSynchronize(m->stream));
+            if (m->mc_host->abort) {
+                ++m->n_retries;
+                const bool widen = (m->mc_host->abort & ABORT_NARROW) && !m->wide;
+                if (widen) m->wide = true;
+                if ((rc = ensure_scratch(m, (m->mc_host->abort & ABORT_SCRATCH) ? m->scratch_cap * 2 : m->scratch_cap, true, widen))) return rc;
+                k_clear_abort<<<1, 1, 0, m->stream>>>(m->mc, m->cc);
+                CU(cudaGetLastError());
+                continue;
+            }
+        }
+        break;
     }
     k_shard_count0<<<1, 1, 0, m->stream>>>(m->cc, m->mc);
-    const int ap_blocks = (int)((m->scratch_cap + AP_THREADS - 1) / AP_THREADS);
-    k_apply_chunk<<<ap_blocks, AP_THREADS, 0, m->stream>>>(m->skeys, m->scnt, m->slist, g, m->cc, st, m->table,
-                                                          m->cap - 1, m->p, m->sum_tab.p, m->mc);
+    launch_apply(m, m->skeys, m->scnt, g, m->cc, st, m->stream);
     CU(cudaGetLastError());
-    m->launches += 3;
+    m->launches += 2;
+    ++m->chunk_seq; m->snap_floor = m->chunk_seq;
     m->ex_valid = false;
     return sync_counters(m);
 }

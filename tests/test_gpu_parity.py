@@ -206,9 +206,58 @@ def test_dump_load_roundtrip_and_xyzi32(s3d):
     assert m.frame_count == 0 and m.get_point_cloud()["num_voxels"] == 0
 
 
-def test_sharded_single_rank_equals_plain(s3d):
-    """The sharded code path (expand -> pack by owner -> merge -> apply) with world = 1 must
-    reproduce the plain mapper exactly; the 2-rank exchange is covered on CPU (gloo) and by
+def _oracle_parity(s3d, images, pos, quat, cfg, what, gpu_cfg=None):
+    from oracle.oracle import OracleMapper
+    gpu, cpu = s3d.SonarTo3DMapper(dict(cfg, **(gpu_cfg or {}))), OracleMapper(cfg)
+    for f in range(len(images)):
+        a = gpu.process_sonar_image(images[f], list(pos[f]), list(quat[f]))
+        b = cpu.process_sonar_image(images[f], pos[f], quat[f])
+        assert _stats3(a) == _stats3(b), f"{what} frame {f}"
+        assert gpu.last_num_samples == b["num_samples"]
+    kg, vg = gpu.octree.voxels.to_arrays()
+    kc, vc = cpu.dump()
+    assert assert_same_map(kg, vg, kc, vc, LOGODDS_ATOL, what) <= 1e-9
+    return gpu
+
+
+def test_wide_counter_lanes(s3d, monkeypatch):
+    """The 32+32-bit counter-lane format (the fallback of the 16+16-bit one) gives the same map."""
+    from sonar_3d_reconstruction_b200 import synthetic
+    monkeypatch.setenv("S3D_WIDE_LANES", "1")
+    spec = dict(H=160, W=200, config=dict(voxel_resolution=0.06, intensity_threshold=45, max_range=8.0), step_m=0.03)
+    images, pos, quat, cfg = synthetic.make_sequence(spec, 20, seed=11)
+    _oracle_parity(s3d, images, pos, quat, cfg, "wide lanes")
+
+
+def test_sample_count_beyond_16_bits_switches_to_wide_lanes(s3d):
+    """511 beams x 50 bins x 5 vertical steps = 127750 occupied samples of one frame in ONE voxel
+    (10 m voxels around a 2 m sonar): the 16-bit count overflows, the chunk is re-run with wide
+    lanes, and the result still equals the reference's."""
+    H, W = 100, 511
+    img = np.zeros((H, W), dtype=np.uint8)
+    img[10:, :] = 255
+    cfg = dict(voxel_resolution=10.0, max_range=2.0, min_range=0.1, intensity_threshold=35)
+    images = np.stack([img, img, img])
+    pos = np.array([[5.0, 5.0, 5.0], [5.01, 5.0, 5.0], [5.02, 5.0, 5.0]])
+    quat = np.array([[0.0, 0.0, 0.0, 1.0]] * 3)
+    gpu = _oracle_parity(s3d, images, pos, quat, cfg, "count overflow")
+    assert gpu.last_num_samples > 65535
+
+
+def test_samples_far_from_the_sonar_origin(s3d):
+    """Fine voxels and long range: samples more than 512 voxels from the sonar origin do not fit
+    the block combiner's 10-bit local coordinates and take the direct path to the dedupe table."""
+    from sonar_3d_reconstruction_b200 import synthetic
+    spec = dict(H=120, W=48, seabed_depth=8.5, config=dict(voxel_resolution=0.012, intensity_threshold=40, max_range=10.0,
+                                                            vertical_aperture=6.0), step_m=0.02)
+    images, pos, quat, cfg = synthetic.make_sequence(spec, 3, seed=13)
+    _oracle_parity(s3d, images, pos, quat, cfg, "far samples")
+
+
+@pytest.mark.parametrize("mode", ["replicate", "route"])
+def test_sharded_single_rank_equals_plain(s3d, mode):
+    """The sharded code paths (route: expand -> pack by owner -> merge -> apply) with world = 1
+    must reproduce the plain mapper exactly; the 2-rank exchange is covered on CPU (gloo) and by
     tools/sharded_check.py under torchrun on 2+ GPUs."""
     from sonar_3d_reconstruction_b200 import synthetic
     from sonar_3d_reconstruction_b200.sharded import ShardedSonarMapper
@@ -216,7 +265,7 @@ def test_sharded_single_rank_equals_plain(s3d):
     images, pos, quat, cfg = synthetic.make_sequence(spec, 37, seed=4)
     a = s3d.SonarTo3DMapper(cfg)
     sa = [_stats3(s) for s in a.process_sonar_images(images, pos, quat)]
-    b = ShardedSonarMapper(dict(cfg, table_capacity=4096), group=None)
+    b = ShardedSonarMapper(dict(cfg, table_capacity=4096), group=None, mode=mode)
     sb = [_stats3(s) for s in b.process_sonar_images(images, pos, quat)]
     assert sa == sb
     ka, va = a.octree.voxels.to_arrays()

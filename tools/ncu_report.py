@@ -72,7 +72,7 @@ def main():
         samp = sum(stalls.values()) or 1
         print("  warp stall samples: " + ", ".join(f"{k[6:]} {100 * v / samp:.0f}%" for k, v in stalls.most_common(6)))
         print("  hottest source lines (share of executed warp instructions / stall samples):")
-        for ln, v in sorted(lines.items(), key=lambda kv: -kv[1][2])[:10]:
+        for ln, v in sorted(lines.items(), key=lambda kv: -kv[1][2])[:int(__import__("os").environ.get("NCU_TOP", "10"))]:
             print(f"    {ln:5d} {100 * v[2] / tot:5.1f}% {v[1]:6d}  {v[0][:96]}")
         print()
 
