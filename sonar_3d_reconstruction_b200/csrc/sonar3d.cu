@@ -171,7 +171,7 @@ constexpr int LT_MAX_SAMPLES = 0xFFFF;       // 16-bit counts cannot overflow be
 constexpr u32 LT_EMPTY = 0xFFFFFFFFu;
 constexpr int LK_BITS = 10;                  // local key: 3 x 10 bits around the sonar-origin voxel
 constexpr int LK_HALF = 1 << (LK_BITS - 1);
-constexpr int FL_ILP = 2;                    // combiner entries per thread per flush batch
+constexpr int FL_ILP = 4;                    // combiner entries per thread per flush batch
 constexpr u32 SCRATCH_PROBE_LIMIT = 512;
 static_assert(EX_ROUND_SAMPLES <= LT_LIMIT, "a round must fit the combiner");
 
@@ -239,7 +239,9 @@ __device__ __forceinline__ u32 dedupe_slot(u64 *skeys, u32 smask, u64 key, u32 b
 __device__ __forceinline__ u32 dedupe_home(u64 key, u32 smask) { return mix32(key) & smask & ~3u; }
 
 // add n_occ / n_free samples to lane g of the entry of `key`; returns 1 if this call created the entry
-template <typename CT>
+// CHECK: watch narrow lanes for overflow (costs waiting for the atomic's return value); off when
+// the host has proved from the geometry tables that no voxel can collect 2^16 samples in a frame
+template <typename CT, bool CHECK>
 __device__ __forceinline__ u32 dedupe_add(u64 *skeys, CT *scnt, u32 smask, MapCtr *mc, u64 seq, u64 key, u32 home,
                                           const Bucket &k, int g, u32 n_occ, u32 n_free)
 {
@@ -247,7 +249,7 @@ __device__ __forceinline__ u32 dedupe_add(u64 *skeys, CT *scnt, u32 smask, MapCt
     const u32 slot = dedupe_slot(skeys, smask, key, home, k, created);
     if (slot == ~0u) { raise_abort(mc, ABORT_SCRATCH, seq); return 0u; }   // the host enlarges the table and retries
     const CT inc = Lane<CT>::make(n_occ, n_free);
-    if (Lane<CT>::narrow) {
+    if (Lane<CT>::narrow && CHECK) {
         const CT old = atomicAdd(&scnt[(size_t)slot * GF + g], inc);
         if (Lane<CT>::overflows(old, inc)) raise_abort(mc, ABORT_NARROW, seq);   // re-run with wide lanes
     } else {
@@ -258,12 +260,12 @@ __device__ __forceinline__ u32 dedupe_add(u64 *skeys, CT *scnt, u32 smask, MapCt
 
 // a sample that does not fit the block combiner (more than 2^9 voxels from the sonar origin, or
 // a transform too large for the fast quantiser) goes to the dedupe table on its own
-template <typename CT>
+template <typename CT, bool CHECK>
 __device__ __noinline__ void commit_direct(u64 *skeys, CT *scnt, u32 smask, ChunkCtr *cc, MapCtr *mc, u64 seq, u64 key,
                                            int g, bool occ)
 {
     const u32 home = dedupe_home(key, smask);
-    if (dedupe_add<CT>(skeys, scnt, smask, mc, seq, key, home, load_bucket(skeys, home), g, occ ? 1u : 0u, occ ? 0u : 1u))
+    if (dedupe_add<CT, CHECK>(skeys, scnt, smask, mc, seq, key, home, load_bucket(skeys, home), g, occ ? 1u : 0u, occ ? 0u : 1u))
         atomicAdd(&cc->n_unique, 1u);
 }
 
@@ -291,31 +293,15 @@ __device__ __forceinline__ bool key_in_range(int ki, int kj, int kk)
 }
 
 // Block-wide: move every combiner entry into the chunk dedupe table and leave the combiner
-// empty.  All threads of the block call it after a barrier that follows the last insert.
-template <typename CT>
+// empty.  All threads of the block call it after a barrier that follows the last insert;
+// live[0 .. *s_count) lists the slots in use (appended as the entries were created).
+template <typename CT, bool CHECK>
 __device__ __forceinline__ void flush_combiner(const ExpandArgs &a, u32 *tkey, u32 *tcnt, unsigned short *live,
-                                               u32 *s_nlive, volatile u32 *s_count, const int (&o)[3], int g,
-                                               u32 &emitted)
+                                               volatile u32 *s_count, const int (&o)[3], int g, u32 &emitted)
 {
     const int tid = threadIdx.x, lane = tid & 31;
-    const u32 lt_mask = (1u << lane) - 1;
-    if (tid == 0) *s_nlive = 0;
-    __syncthreads();
-    // 1. dense list of the live entries
-#pragma unroll 4
-    for (int i = tid; i < LT_CAP; i += EX_THREADS) {
-        const bool lv = tkey[i] != LT_EMPTY;
-        const u32 m = __ballot_sync(0xffffffffu, lv);
-        if (m) {
-            u32 base = 0;
-            if (lane == 0) base = atomicAdd(s_nlive, (u32)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (lv) live[base + __popc(m & lt_mask)] = (unsigned short)i;
-        }
-    }
-    __syncthreads();
-    const int n = (int)*s_nlive;
-    // 2. FL_ILP entries per thread at a time: home buckets are fetched together, then resolved
+    const int n = (int)*s_count;                 // live[0..n) lists the combiner slots in use
+    // FL_ILP entries per thread at a time: home buckets are fetched together, then resolved
     for (int base = 0; base < n; base += EX_THREADS * FL_ILP) {
         u64 key[FL_ILP]; u32 inc[FL_ILP], home[FL_ILP]; bool ok[FL_ILP]; Bucket bk[FL_ILP];
         u32 made = 0;
@@ -347,12 +333,13 @@ __device__ __forceinline__ void flush_combiner(const ExpandArgs &a, u32 *tkey, u
         }
 #pragma unroll
         for (int j = 0; j < FL_ILP; ++j)
-            if (ok[j]) made += dedupe_add<CT>(a.skeys, static_cast<CT *>(a.scnt), a.smask, a.mc, a.seq, key[j], home[j], bk[j],
+            if (ok[j]) made += dedupe_add<CT, CHECK>(a.skeys, static_cast<CT *>(a.scnt), a.smask, a.mc, a.seq, key[j], home[j], bk[j],
                                               g, inc[j] >> 16, inc[j] & 0xffffu);
         // entries created for the chunk: one reduction per warp per batch (nobody waits for it)
         made = __reduce_add_sync(0xffffffffu, made);
         if (lane == 0 && made) atomicAdd(&a.cc->n_unique, made);
     }
+    __syncthreads();
     if (tid == 0) *s_count = 0;
     __syncthreads();
 }
@@ -364,7 +351,7 @@ __host__ __device__ inline size_t expand_smem_bytes(int H, int free_step, int oc
            sizeof(Fan) * (size_t)EX_WARPS * (size_t)(max_f + occ_window + 1);
 }
 
-template <typename CT>
+template <typename CT, bool CHECK>
 __global__ void __launch_bounds__(EX_THREADS, 4)
 k_expand(ExpandArgs a)
 {
@@ -377,9 +364,10 @@ k_expand(ExpandArgs a)
     const int H = tab.H, W = tab.W;
     const int max_f = (H + tab.free_step - 1) / tab.free_step;        // free candidates per beam
     const int nf_max = max_f + tab.occ_window;                        // fans per beam
-    __shared__ double s_T[12];
-    __shared__ int s_o[3], s_fast, s_tot[EX_WARPS];
-    __shared__ u32 s_count, s_nlive, s_abort;
+    __shared__ __align__(16) double s_T[12];
+    __shared__ int s_o[3], s_fast, s_tot[EX_WARPS], s_nfan[EX_WARPS], s_pfirst[EX_WARPS + 1];
+    __shared__ double s_cb[EX_WARPS], s_sb[EX_WARPS];
+    __shared__ u32 s_count, s_abort;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const u32 lt_mask = (1u << lane) - 1;
@@ -472,37 +460,58 @@ k_expand(ExpandArgs a)
         if (lane == 0) fans[nfan].off = run;
         total = run;
     }
-    if (lane == 0) s_tot[warp] = total;
+    if (lane == 0) { s_tot[warp] = total; s_nfan[warp] = nfan; s_cb[warp] = cb; s_sb[warp] = sb; }
     __syncthreads();
     const bool fast = s_fast != 0;
     const int o[3] = {s_o[0], s_o[1], s_o[2]};
     volatile u32 *v_count = &s_count;
     volatile u32 *v_tkey = tkey;
 
-    // ---- the flattened (fan, vertical step) space of the beam, EX_PASS consecutive samples per pass.
-    // The block walks in rounds of EX_ROUND passes per warp; between rounds it votes on flushing the
-    // combiner, until what is left certainly fits (then the warps run free to the end).
+    // ---- the flattened (fan, vertical step) space of each beam is cut into passes of EX_PASS
+    // consecutive samples; the passes of the block's beams, in beam order, are dealt to the warps
+    // round-robin, so the warps finish together whatever the beams hold.  The block walks in rounds
+    // of EX_ROUND passes per warp; between rounds it votes on flushing the combiner, until what is
+    // left certainly fits (then the warps run free to the end).
     u32 emitted = 0;
-    int c0 = 0;                      // fan that holds the first sample of the next pass
-    int base = 0;                    // first sample of the next pass of this warp
+    if (tid == 0) {                  // first pass of each beam (exclusive prefix of the pass counts)
+        int run = 0;
+        for (int b = 0; b < EX_WARPS; ++b) { s_pfirst[b] = run; run += (s_tot[b] + EX_PASS - 1) / EX_PASS; }
+        s_pfirst[EX_WARPS] = run;
+    }
+    __syncthreads();
+    const int n_pass = s_pfirst[EX_WARPS];       // passes of the whole block
+    const int my_pfirst = lane < EX_WARPS ? s_pfirst[lane] : INT_MAX;
     int since = 0;                   // samples the block has walked since the last flush (>= combiner entries)
-    int rem = 0;                     // samples the block still has to walk
-#pragma unroll
-    for (int b = 0; b < EX_WARPS; ++b) rem += s_tot[b];
-    for (int round = 0; rem > 0; ++round) {
+    for (int p_lo = 0; p_lo < n_pass; p_lo += EX_WARPS * EX_ROUND) {
+        int rem = (n_pass - p_lo) * EX_PASS;                            // samples still to walk (upper bound)
         const bool free_run = since + rem <= LT_LIMIT;                  // block-uniform
-        const int last = free_run ? total : min(total, (round + 1) * (EX_PASS * EX_ROUND));
-        for (; base < last; base += EX_PASS) {
+        const int p_hi = free_run ? n_pass : min(n_pass, p_lo + EX_WARPS * EX_ROUND);
+        for (int p = p_lo + warp; p < p_hi; p += EX_WARPS) {
+            // which beam, and where in it
+            const int b = __popc(__ballot_sync(0xffffffffu, my_pfirst <= p)) - 1;     // last beam that starts at or before p
+            const int base = (p - s_pfirst[b]) * EX_PASS;               // first sample of the pass, in its beam
+            const int total = s_tot[b], nfan = s_nfan[b];
+            const double cb = s_cb[b], sb = s_sb[b];
+            const Fan *fans = fans_all + (size_t)b * (nf_max + 1);
+            // fan that holds sample `base`: two-level search over the beam's fan offsets (32 probes each)
+            int c0;
+            {
+                const int S = (nfan + 31) / 32;
+                const int i1 = min(lane * S, nfan);
+                const int seg = __popc(__ballot_sync(0xffffffffu, fans[i1].off <= base && lane * S < nfan)) - 1;
+                const int i2 = seg * S + lane;
+                c0 = seg * S + __popc(__ballot_sync(0xffffffffu, lane < S && i2 < nfan && fans[min(i2, nfan)].off <= base)) - 1;
+            }
             // fans that start inside this pass: bit (start - base) of a 64-bit mask (a fan has >= 3 samples)
             const int kf = c0 + 1 + lane;
             const int rel = (kf <= nfan ? fans[kf].off : INT_MAX) - base;
             const u32 m_lo = __reduce_or_sync(0xffffffffu, (rel > 0 && rel < 32) ? 1u << rel : 0u);
             const u32 m_hi = __reduce_or_sync(0xffffffffu, (rel >= 32 && rel < 64) ? 1u << (rel - 32) : 0u);
-            const int adv = __popc(__ballot_sync(0xffffffffu, rel > 0 && rel <= EX_PASS));
             const u32 upto = 0xffffffffu >> (31 - lane);                // bits 0..lane
-            int n_new = 0;
+            bool made[EX_ILP]; u32 made_at[EX_ILP];
 #pragma unroll
             for (int j = 0; j < EX_ILP; ++j) {
+                made[j] = false; made_at[j] = 0;
                 const int w = base + j * 32 + lane;
                 if (w >= total) continue;
                 const Fan f = fans[c0 + (j == 0 ? __popc(m_lo & upto) : __popc(m_lo) + __popc(m_hi & upto))];
@@ -537,7 +546,7 @@ k_expand(ExpandArgs a)
                         if (cur == lk) break;
                         if (cur == LT_EMPTY) {
                             cur = atomicCAS(&tkey[h], LT_EMPTY, lk);
-                            if (cur == LT_EMPTY) { ++n_new; break; }
+                            if (cur == LT_EMPTY) { made[j] = true; made_at[j] = h; break; }
                             if (cur == lk) break;
                         }
                         h = (h + 1) & (LT_CAP - 1);
@@ -548,30 +557,34 @@ k_expand(ExpandArgs a)
                     const u64 key = pack_key(ki, kj, kk);
                     if (a.own_world > 1 && key_owner(key, a.own_world) != a.own_rank) continue;
                     ++emitted;
-                    commit_direct<CT>(a.skeys, static_cast<CT *>(a.scnt), a.smask, a.cc, a.mc, a.seq, key, g, occ);
+                    commit_direct<CT, CHECK>(a.skeys, static_cast<CT *>(a.scnt), a.smask, a.cc, a.mc, a.seq, key, g, occ);
                 }
             }
-            c0 += adv;
-            n_new = __reduce_add_sync(0xffffffffu, n_new);
-            if (lane == 0 && n_new) atomicAdd(&s_count, (u32)n_new);
+            // combiner slots created by this pass join the live list: one shared-memory atomic per pass
+            static_assert(EX_ILP == 2, "two ballots below");
+            const u32 mk0 = __ballot_sync(0xffffffffu, made[0]), mk1 = __ballot_sync(0xffffffffu, made[1]);
+            if (mk0 | mk1) {
+                u32 at = 0;
+                if (lane == 0) at = atomicAdd(&s_count, (u32)(__popc(mk0) + __popc(mk1)));
+                at = __shfl_sync(0xffffffffu, at, 0);
+                if (made[0]) live[at + __popc(mk0 & lt_mask)] = (unsigned short)made_at[0];
+                if (made[1]) live[at + __popc(mk0) + __popc(mk1 & lt_mask)] = (unsigned short)made_at[1];
+            }
         }
         if (free_run) break;
-        int rem_next = 0;
-#pragma unroll
-        for (int b = 0; b < EX_WARPS; ++b) rem_next += max(0, s_tot[b] - (round + 1) * (EX_PASS * EX_ROUND));
-        since += rem - rem_next;
-        rem = rem_next;
+        since += (p_hi - p_lo) * EX_PASS;
+        rem -= (p_hi - p_lo) * EX_PASS;
         // flush if the next round could overflow the combiner's entries or its 16-bit counts.  Every
         // thread votes with the entry count it sees on arrival; the last one to arrive sees the final one.
         const int next = min(rem, EX_ROUND_SAMPLES);
         const int want = (*v_count + (u32)next > (u32)LT_LIMIT) || (since + next > LT_MAX_SAMPLES);
         if (__syncthreads_or(want)) {
-            flush_combiner<CT>(a, tkey, tcnt, live, &s_nlive, v_count, o, g, emitted);
+            flush_combiner<CT, CHECK>(a, tkey, tcnt, live, v_count, o, g, emitted);
             since = 0;
         }
     }
     __syncthreads();
-    if (*v_count > 0u) flush_combiner<CT>(a, tkey, tcnt, live, &s_nlive, v_count, o, g, emitted);
+    if (*v_count > 0u) flush_combiner<CT, CHECK>(a, tkey, tcnt, live, v_count, o, g, emitted);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
     if (lane == 0 && emitted) atomicAdd(&a.stats[g].n_samples, (u64)emitted);
@@ -603,7 +616,7 @@ __device__ __forceinline__ double apply_one(double L, double upd, bool adaptive,
         }
     }
     L += upd;                                                   // :107
-    L = fmin(fmax(L, p.lo_min), p.lo_max);                      // :110
+    L = L < p.lo_min ? p.lo_min : (L > p.lo_max ? p.lo_max : L);   // :110 (L is never NaN)
     return L;
 }
 
@@ -693,47 +706,95 @@ __device__ __forceinline__ double seq_avg(u32 n_free, u32 n_occ, const double (*
     return sum / (double)(n_occ + n_free);                       // :559
 }
 
-// The chunk's dedupe table is walked in tiles of AP_THREADS slots.  Per tile:
+// The chunk's dedupe table is walked in tiles of AP_THREADS slots:
 //   1. one thread per slot: a live entry is read into registers and wiped, its voxel is found or
 //      inserted in the table (one probe per voxel per chunk), the per-frame num_occupied /
 //      num_free / new-voxel counts are taken from the counter lanes (they do not depend on L),
-//      and lanes + L are staged in shared memory;
-//   2. the live entries are listed, those that can take the adaptive path (some frame saw the
-//      voxel occupied) first, so that warps are homogeneous;
-//   3. one thread per listed entry walks only the frames that touched the voxel, in order:
+//      and lanes + L are appended to a ring of staged entries in shared memory;
+//   2. whenever the ring holds AP_THREADS entries, they are listed -- those that can take the
+//      adaptive path (some frame saw the voxel occupied) first, so that warps are homogeneous --
+//   3. and one thread per listed entry walks only the frames that touched the voxel, in order:
 //      per-voxel mean of the sample deltas (3d_mapper.py:557-559), then update_voxel (:562-567);
-//      L goes back to the table with one 8-byte store.
+//      L goes back to the table with one 8-byte store.  Every thread has an entry, whatever the
+//      load of the dedupe table.
 // Frames stay strictly ordered per voxel, which is all the reference's sequential semantics
 // require (voxels are independent of each other).
+constexpr int AP_Q = 2 * AP_THREADS;        // ring capacity: a full window plus one more tile
+constexpr int AP_ROW = GF + 1;              // padded row of counter lanes: conflict-free column access
+
+template <typename CT> __host__ __device__ constexpr size_t apply_smem_bytes()
+{
+    return (size_t)AP_Q * (AP_ROW * sizeof(CT) + sizeof(double) + sizeof(u64) + sizeof(unsigned short) + 1);
+}
+
 template <typename CT>
 __global__ void __launch_bounds__(AP_THREADS)
 k_apply_chunk(u64 *__restrict__ skeys, CT *__restrict__ scnt, u32 n_slots, int g, ChunkCtr *cc, DevStats *st,
               Slot *table, u64 tmask, DevParams p, const double *__restrict__ sum_tab, MapCtr *mc)
 {
-    constexpr int ROW = GF + 1;                 // padded row: conflict-free column access
-    __shared__ CT s_lane[AP_THREADS * ROW];
-    __shared__ double s_L[AP_THREADS];
-    __shared__ u64 s_slot[AP_THREADS];
-    __shared__ unsigned short s_mask[AP_THREADS], s_ordA[AP_THREADS], s_ordB[AP_THREADS];
-    __shared__ u32 s_occ[GF], s_free[GF], s_new[GF], s_nA, s_nB;
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    CT *s_lane = reinterpret_cast<CT *>(s_dyn);
+    double *s_L = reinterpret_cast<double *>(s_lane + AP_Q * AP_ROW);
+    u64 *s_slot = reinterpret_cast<u64 *>(s_L + AP_Q);
+    unsigned short *s_mask = reinterpret_cast<unsigned short *>(s_slot + AP_Q);
+    unsigned char *s_cls = reinterpret_cast<unsigned char *>(s_mask + AP_Q);
+    __shared__ unsigned short s_ordA[AP_THREADS], s_ordB[AP_THREADS];
+    __shared__ u32 s_occ[GF], s_free[GF], s_new[GF], s_nA, s_nB, s_qn;
     __shared__ double s_sum[4][SUMT];
     __shared__ bool s_last;
     static_assert(GF <= 16, "s_mask holds one bit per frame");
+    static_assert((AP_Q * AP_ROW * sizeof(CT)) % 8 == 0, "staging alignment");
     if (__ldcg(&mc->abort)) return;
     const u32 tid = threadIdx.x, lane = tid & 31;
     const u32 lt_mask = (1u << lane) - 1;
     if (tid < GF) { s_occ[tid] = 0; s_free[tid] = 0; s_new[tid] = 0; }
+    if (tid == 0) { s_qn = 0; s_nA = 0; s_nB = 0; }
     for (int q = tid; q < 4 * SUMT; q += AP_THREADS) (&s_sum[0][0])[q] = sum_tab[q];
+    __syncthreads();
     u32 w_occ = 0, w_free = 0;                  // lane f of each warp accumulates frame f
+    u32 consumed = 0;                           // ring entries already applied (block-uniform)
     LocalAcc acc; acc_init(acc);
+
+    // steps 2 + 3 on ring entries [consumed, consumed + n_win); all threads call it
+    auto drain = [&](u32 n_win) {
+        {
+            const bool have = tid < n_win;
+            const u32 pos = (consumed + tid) & (AP_Q - 1);
+            const bool isA = have && s_cls[pos] != 0;
+            const u32 mA = __ballot_sync(0xffffffffu, isA), mB = __ballot_sync(0xffffffffu, have && !isA);
+            u32 bA = 0, bB = 0;
+            if (lane == 0) { if (mA) bA = atomicAdd(&s_nA, (u32)__popc(mA)); if (mB) bB = atomicAdd(&s_nB, (u32)__popc(mB)); }
+            bA = __shfl_sync(0xffffffffu, bA, 0); bB = __shfl_sync(0xffffffffu, bB, 0);
+            if (isA) s_ordA[bA + __popc(mA & lt_mask)] = (unsigned short)pos;
+            else if (have) s_ordB[bB + __popc(mB & lt_mask)] = (unsigned short)pos;
+        }
+        __syncthreads();
+        if (tid < n_win) {
+            const u32 nA = s_nA;
+            const u32 e = tid < nA ? s_ordA[tid] : s_ordB[tid - nA];
+            u32 todo = s_mask[e];
+            double Lv = s_L[e];
+            const CT *row = s_lane + e * AP_ROW;
+            while (todo) {
+                const int f = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const CT cf = row[f];
+                const u32 n_occ = Lane<CT>::n_occ(cf), n_free = Lane<CT>::n_free(cf);
+                Lv = apply_one(Lv, seq_avg(n_free, n_occ, s_sum, p), n_occ > 0, p);
+            }
+            table[s_slot[e]].val = Lv;
+        }
+        consumed += n_win;
+        __syncthreads();
+        if (tid == 0) { s_nA = 0; s_nB = 0; }
+    };
+
     const u32 n_tiles = n_slots / AP_THREADS;
     for (u32 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const u32 s = tile * AP_THREADS + tid;
         const u64 key = __ldcg(&skeys[s]);
         bool live = key != EMPTY_KEY;
-        // also the barrier that lets the previous tile's readers of the staging arrays finish
         if (!__syncthreads_or(live)) continue;
-        if (tid == 0) { s_nA = 0; s_nB = 0; }
         // ---- 1. entry -> registers, wipe, probe, per-frame counts, stage
         CT c[GF];
 #pragma unroll
@@ -760,56 +821,44 @@ k_apply_chunk(u64 *__restrict__ skeys, CT *__restrict__ scnt, u32 n_slots, int g
             }
         }
         u32 mask = 0; bool any_occ = false;
+        if (__any_sync(0xffffffffu, live)) {
 #pragma unroll
-        for (int f = 0; f < GF; ++f) {
-            if (f < g) {                                            // uniform
-                const bool hit = live && c[f] != 0;
-                const bool occ = hit && Lane<CT>::n_occ(c[f]) > 0;  // occupied has priority (:544-545)
-                const u32 b_occ = __ballot_sync(0xffffffffu, occ);
-                const u32 b_free = __ballot_sync(0xffffffffu, hit && !occ);
-                if (lane == (u32)f) { w_occ += __popc(b_occ); w_free += __popc(b_free); }
-                if (hit) mask |= 1u << f;
-                any_occ |= occ;
+            for (int f = 0; f < GF; ++f) {
+                if (f < g) {                                            // uniform
+                    const bool hit = live && c[f] != 0;
+                    const bool occ = hit && Lane<CT>::n_occ(c[f]) > 0;  // occupied has priority (:544-545)
+                    const u32 b_occ = __ballot_sync(0xffffffffu, occ);
+                    const u32 b_free = __ballot_sync(0xffffffffu, hit && !occ);
+                    if (lane == (u32)f) { w_occ += __popc(b_occ); w_free += __popc(b_free); }
+                    if (hit) mask |= 1u << f;
+                    any_occ |= occ;
+                }
             }
         }
         live = live && mask != 0;
-        if (live) {
+        {
+            const u32 m_live = __ballot_sync(0xffffffffu, live);
+            u32 at = 0;
+            if (lane == 0 && m_live) at = atomicAdd(&s_qn, (u32)__popc(m_live));
+            at = __shfl_sync(0xffffffffu, at, 0);
+            if (live) {
+                const u32 pos = (at + __popc(m_live & lt_mask)) & (AP_Q - 1);
 #pragma unroll
-            for (int f = 0; f < GF; ++f) s_lane[tid * ROW + f] = c[f];
-            s_L[tid] = L; s_slot[tid] = slot; s_mask[tid] = (unsigned short)mask;
-            if (fresh) atomicAdd(&s_new[__ffs(mask) - 1], 1u);       // len(voxels) grows at the first frame that touched it
-            acc_key(acc, key);
-        }
-        __syncthreads();
-        // ---- 2. list the live entries, adaptive candidates first
-        {
-            const bool isA = live && any_occ && p.adaptive;
-            const u32 mA = __ballot_sync(0xffffffffu, isA), mB = __ballot_sync(0xffffffffu, live && !isA);
-            u32 bA = 0, bB = 0;
-            if (lane == 0) { if (mA) bA = atomicAdd(&s_nA, (u32)__popc(mA)); if (mB) bB = atomicAdd(&s_nB, (u32)__popc(mB)); }
-            bA = __shfl_sync(0xffffffffu, bA, 0); bB = __shfl_sync(0xffffffffu, bB, 0);
-            if (isA) s_ordA[bA + __popc(mA & lt_mask)] = (unsigned short)tid;
-            else if (live) s_ordB[bB + __popc(mB & lt_mask)] = (unsigned short)tid;
-        }
-        __syncthreads();
-        // ---- 3. one thread per listed entry: the frames that touched the voxel, in order
-        {
-            const u32 nA = s_nA, nB = s_nB;
-            if (tid < nA + nB) {
-                const u32 e = tid < nA ? s_ordA[tid] : s_ordB[tid - nA];
-                u32 todo = s_mask[e];
-                double Lv = s_L[e];
-                const CT *row = s_lane + e * ROW;
-                while (todo) {
-                    const int f = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const CT cf = row[f];
-                    const u32 n_occ = Lane<CT>::n_occ(cf), n_free = Lane<CT>::n_free(cf);
-                    Lv = apply_one(Lv, seq_avg(n_free, n_occ, s_sum, p), n_occ > 0, p);
-                }
-                table[s_slot[e]].val = Lv;
+                for (int f = 0; f < GF; ++f) s_lane[pos * AP_ROW + f] = c[f];
+                s_L[pos] = L; s_slot[pos] = slot; s_mask[pos] = (unsigned short)mask;
+                s_cls[pos] = (any_occ && p.adaptive) ? 1 : 0;
+                if (fresh) atomicAdd(&s_new[__ffs(mask) - 1], 1u);   // len(voxels) grows at the first frame that touched it
+                acc_key(acc, key);
             }
         }
+        __syncthreads();
+        // every thread reads the fill before the next barrier, and nobody appends before that barrier
+        if (*(volatile u32 *)&s_qn - consumed >= (u32)AP_THREADS) drain(AP_THREADS);
+    }
+    __syncthreads();
+    {
+        const u32 left = *(volatile u32 *)&s_qn - consumed;
+        if (left) drain(left);
     }
     acc_publish(acc, mc, false);
     __syncthreads();
@@ -1165,6 +1214,8 @@ struct s3d_map {
     // access-policy window can keep it resident between the kernels of a chunk
     DevBuf<uint8_t> spool; u64 scratch_cap = 0;
     bool wide = false;               // counter lanes: u32 (16+16 bits) normally, u64 after a count overflowed
+    bool narrow_safe = false;        // proved on the host: no voxel can collect 2^16 samples of a kind in one frame
+    std::vector<double> h_range; std::vector<int> h_nv_free, h_nv_occ; double half_aperture = 0.0;
     u64 *skeys = nullptr; void *scnt = nullptr;                      // buffer 0 (also the sharded path's)
     // NBUF chunk buffers and two expand streams: k_expand of chunks c+1 and c+2 overlap each other
     // and k_apply_chunk of chunk c (a chunk alone does not fill the GPU)
@@ -1302,6 +1353,37 @@ template <typename T> int upload(DevBuf<T> &b, const T *src, size_t n, cudaStrea
 
 size_t lane_bytes(const s3d_map *m) { return m->wide ? sizeof(u64) : sizeof(u32); }
 
+// Upper bound of the samples of one kind that one frame can put into one voxel, from the tables:
+// every sample of range bin r lies exactly range_m[r] from the sonar origin, a voxel spans at
+// most sqrt(3)*res in distance (so only a few consecutive bins reach it), and on the arc of one
+// (beam, bin) fan consecutive samples are a chord 2*r*sin(ha/(2*nv)) apart.  When the bound stays
+// below 2^16 the narrow counter lanes cannot overflow and k_expand skips the overflow watch.
+void update_count_bound(s3d_map *m)
+{
+    m->narrow_safe = false;
+    if (!m->have_params || m->h_range.empty()) return;
+    const double diam = std::sqrt(3.0) * m->p.res * (1.0 + 1e-9);
+    const size_t H = m->h_range.size();
+    const double rr = H > 1 ? m->h_range[1] - m->h_range[0] : 0.0;
+    const int step = m->tab.free_step > 0 ? m->tab.free_step : 1;
+    const double bins = rr > 0.0 ? std::floor(diam / rr) + 1.0 : (double)H;
+    const double bins_occ = std::min<double>({(double)m->tab.occ_window, bins, (double)H});
+    const double bins_free = std::min<double>((double)((H + step - 1) / step), rr > 0.0 ? std::floor(diam / (rr * step)) + 1.0 : (double)H);
+    auto per_fan = [&](int nv, double r) -> double {
+        if (nv <= 0) return 0.0;
+        const double all = 2.0 * nv + 1.0;
+        const double chord = 2.0 * r * std::sin(m->half_aperture / (2.0 * nv));
+        return chord > 0.0 ? std::min(all, std::floor(diam / chord) + 1.0) : all;
+    };
+    double occ = 0.0, fre = 0.0;
+    for (size_t r = 0; r < H; ++r) {
+        occ = std::max(occ, per_fan(m->h_nv_occ[r], m->h_range[r]));
+        if (r % (size_t)step == 0) fre = std::max(fre, per_fan(m->h_nv_free[r], m->h_range[r]));
+    }
+    const double nb = (double)m->tab.n_beams;
+    m->narrow_safe = nb * bins_occ * occ <= 65535.0 && nb * bins_free * fre <= 65535.0;
+}
+
 // (re)allocate and wipe the chunk dedupe tables; the streams must be idle
 int ensure_scratch(s3d_map *m, u64 want_cap, bool wipe, bool force_realloc = false)
 {
@@ -1346,8 +1428,9 @@ void launch_expand(s3d_map *m, const ExpandArgs &a, int n_beams, int g, cudaStre
 {
     const size_t smem = expand_smem_bytes(a.tab.H, a.tab.free_step, a.tab.occ_window);
     const dim3 grid((n_beams + EX_WARPS - 1) / EX_WARPS, g);
-    if (m->wide) k_expand<u64><<<grid, EX_THREADS, smem, st>>>(a);
-    else k_expand<u32><<<grid, EX_THREADS, smem, st>>>(a);
+    if (m->wide) k_expand<u64, false><<<grid, EX_THREADS, smem, st>>>(a);
+    else if (m->narrow_safe) k_expand<u32, false><<<grid, EX_THREADS, smem, st>>>(a);
+    else k_expand<u32, true><<<grid, EX_THREADS, smem, st>>>(a);
     m->launches += 1;
 }
 
@@ -1355,10 +1438,10 @@ void launch_apply(s3d_map *m, u64 *skeys, void *scnt, int g, ChunkCtr *cc, DevSt
 {
     const int blocks = (int)std::min<u64>(m->scratch_cap / AP_THREADS, (u64)m->n_sm * 4);
     if (m->wide)
-        k_apply_chunk<u64><<<blocks, AP_THREADS, 0, stream>>>(skeys, static_cast<u64 *>(scnt), (u32)m->scratch_cap, g, cc, st,
+        k_apply_chunk<u64><<<blocks, AP_THREADS, apply_smem_bytes<u64>(), stream>>>(skeys, static_cast<u64 *>(scnt), (u32)m->scratch_cap, g, cc, st,
                                                              m->table, m->cap - 1, m->p, m->sum_tab.p, m->mc);
     else
-        k_apply_chunk<u32><<<blocks, AP_THREADS, 0, stream>>>(skeys, static_cast<u32 *>(scnt), (u32)m->scratch_cap, g, cc, st,
+        k_apply_chunk<u32><<<blocks, AP_THREADS, apply_smem_bytes<u32>(), stream>>>(skeys, static_cast<u32 *>(scnt), (u32)m->scratch_cap, g, cc, st,
                                                              m->table, m->cap - 1, m->p, m->sum_tab.p, m->mc);
     m->launches += 1;
 }
@@ -1690,6 +1773,7 @@ int s3d_set_params(s3d_map *m, const s3d_params *q)
     }
     m->have_params = true;
     m->ex_valid = false;
+    update_count_bound(m);
     return 0;
 }
 
@@ -1743,8 +1827,16 @@ int s3d_set_tables(s3d_map *m, const s3d_tables *t)
     d.nv_free = m->d_nv_free.p; d.nv_occ = m->d_nv_occ.p; d.cos_va = m->d_cos_va.p; d.sin_va = m->d_sin_va.p;
     d.col_to_beam = m->d_col_to_beam.p;
     m->have_tables = true;
-    CU(cudaFuncSetAttribute(k_expand<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
-    CU(cudaFuncSetAttribute(k_expand<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+    CU(cudaFuncSetAttribute(k_expand<u32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+    CU(cudaFuncSetAttribute(k_expand<u32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+    CU(cudaFuncSetAttribute(k_expand<u64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+    CU(cudaFuncSetAttribute(k_apply_chunk<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes<u64>()));
+    CU(cudaFuncSetAttribute(k_apply_chunk<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes<u32>()));
+    m->h_range.assign(t->range_m, t->range_m + H);
+    m->h_nv_free.assign(t->nv_free, t->nv_free + H);
+    m->h_nv_occ.assign(t->nv_occ, t->nv_occ + H);
+    m->half_aperture = t->nv_max > 0 ? std::atan2(t->sin_va[nfan - 1], t->cos_va[nfan - 1]) : 0.0;   // va of v_step = +nv_max
+    update_count_bound(m);
     // first guess for the chunk dedupe table; it doubles on demand (retry) from here
     return ensure_scratch(m, std::min<u64>(1u << 20, std::max<u64>(1u << 14, m->samples_max / 4)), false);
 }
