@@ -37,7 +37,8 @@ enum {
     S3D_ENOMEM = -3,      /* device or host allocation failed */
     S3D_EKEYRANGE = -4,   /* a voxel key fell outside +-S3D_KEY_LIMIT (or a coordinate was NaN) */
     S3D_ETABLEFULL = -5,  /* the voxel table could not grow enough; map state is unspecified */
-    S3D_ESCRATCH = -6     /* per-frame dedupe scratch overflow (internal sizing bug) */
+    S3D_ESCRATCH = -6,    /* per-frame dedupe scratch overflow (internal sizing bug) */
+    S3D_EROUTE = -7       /* routed (multi-GPU) map: inbox overflow, silent peer, or a chunk that would need a re-run */
 };
 
 typedef struct s3d_map s3d_map; /* opaque */
@@ -188,6 +189,23 @@ int s3d_shard_config(s3d_map *map, int rank, int world);
  * the price of repeating the (cheap) expansion arithmetic on every rank.  Counters returned by
  * s3d_ingest* are then per-shard partials (sum over ranks = the reference's counters). */
 int s3d_shard_filter(s3d_map *map, int on);
+/* Routed map (the fused form of the exchange): every rank expands its slice of the processed
+ * beams of every frame, and the expansion kernel itself writes the (voxel, frame, counts)
+ * records of voxels owned by other ranks into the owners' inboxes over NVLink peer memory; the
+ * owner merges them before it applies the chunk.  No host synchronisation and no separate
+ * all-to-all per chunk: device-side sequence flags order sources and owners.  Set-up is
+ * collective: every rank exports an exchange block (handle = S3D_ROUTE_HANDLE_BYTES opaque bytes,
+ * to be all-gathered by the caller), attaches the handles of all ranks (rank order), then
+ * enables routing; from then on s3d_ingest* on every rank must be called with the same frames.
+ * The per-frame counters are per-shard partials (sum over ranks = the reference's counters).
+ * A routed map cannot re-run a chunk: reserve table capacity up front (s3d_reserve); the
+ * library grows the table ahead of need, and reports S3D_EROUTE if a chunk still hits the gate. */
+#define S3D_ROUTE_HANDLE_BYTES 80
+int s3d_route_export(s3d_map *map, uint64_t records_per_pair, unsigned char *handle);
+/* handles: world x S3D_ROUTE_HANDLE_BYTES.  same_process != 0: the peers are maps of this process
+ * on the same device (single-GPU tests); otherwise the blocks are opened with CUDA IPC. */
+int s3d_route_attach(s3d_map *map, const unsigned char *handles, int same_process);
+int s3d_route_enable(s3d_map *map, int on);
 /* owner rank of each key (host helper; same function the device uses) */
 int s3d_shard_owner(const int32_t *ijk, int64_t n, int world, int32_t *owner);
 /* Expand g <= 16 frames (device-resident images / transforms) on this rank's beam slice and

@@ -19,6 +19,7 @@ SYMBOLS = (
     "s3d_capacity", "s3d_export_begin", "s3d_export_read", "s3d_export_read_xyzi32",
     "s3d_profile_enable", "s3d_profile_read",
     "s3d_shard_config", "s3d_shard_filter", "s3d_shard_owner", "s3d_shard_expand", "s3d_shard_apply",
+    "s3d_route_export", "s3d_route_attach", "s3d_route_enable",
 )
 
 
@@ -102,6 +103,9 @@ def load_library():
     L.s3d_profile_read.argtypes = [vp, C.POINTER(Profile)]
     L.s3d_shard_config.argtypes = [vp, C.c_int, C.c_int]
     L.s3d_shard_filter.argtypes = [vp, C.c_int]
+    L.s3d_route_export.argtypes = [vp, C.c_uint64, C.c_char_p]
+    L.s3d_route_attach.argtypes = [vp, C.c_char_p, C.c_int]
+    L.s3d_route_enable.argtypes = [vp, C.c_int]
     L.s3d_shard_owner.argtypes = [i32p, C.c_int64, C.c_int, i32p]
     L.s3d_shard_expand.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(vp), u64p]
     L.s3d_shard_apply.argtypes = [vp, vp, C.c_uint64, C.c_int, vp]
@@ -212,6 +216,21 @@ class NativeMap:
 
     def shard_filter(self, on: bool):
         _check(self._lib.s3d_shard_filter(self._h, int(bool(on))))
+
+    ROUTE_HANDLE_BYTES = 80
+
+    def route_export(self, records_per_pair: int) -> bytes:
+        """Allocate this rank's exchange block (flags + inboxes); returns the opaque handle to all-gather."""
+        buf = C.create_string_buffer(self.ROUTE_HANDLE_BYTES)
+        _check(self._lib.s3d_route_export(self._h, int(records_per_pair), buf))
+        return buf.raw
+
+    def route_attach(self, handles: bytes, same_process: bool = False):
+        """handles: the world's handles back to back, in rank order."""
+        _check(self._lib.s3d_route_attach(self._h, bytes(handles), int(bool(same_process))))
+
+    def route_enable(self, on: bool = True):
+        _check(self._lib.s3d_route_enable(self._h, int(bool(on))))
 
     def shard_expand(self, images_ptr: int, T_ptr: int, g: int, stats_dev_ptr: int):
         """-> (device pointer of the packed records, [count per owner])"""

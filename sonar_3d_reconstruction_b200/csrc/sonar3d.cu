@@ -38,6 +38,7 @@ constexpr int KEY_BIAS = 1 << 20;
 constexpr int GF = 16;                                      // frames per chunk = counter lanes per dedupe entry
 constexpr int N_CHUNK_BUF = 4;                              // chunk dedupe buffers in flight
 constexpr u32 ERR_KEYRANGE = 1u, ERR_TABLEFULL = 2u;        // fatal
+constexpr u32 ERR_ROUTE_FULL = 4u, ERR_ROUTE_TIMEOUT = 8u;  // fatal (routed map): a peer inbox overflowed / a peer never signalled
 constexpr u32 ABORT_SCRATCH = 1u, ABORT_TABLE = 2u;         // retryable: the host enlarges and re-runs the chunk
 constexpr u32 ABORT_NARROW = 4u;                            // retryable: a 16-bit sample count overflowed -> wide lanes
 
@@ -177,6 +178,43 @@ static_assert(EX_ROUND_SAMPLES <= LT_LIMIT, "a round must fit the combiner");
 
 struct __align__(16) Fan { int off; u32 code; double range; };   // code = r | nv << 16 | occupied << 31
 
+// ---- routed map (one process per GPU): a rank expands its slice of the beams and its combiner
+// flush writes the entries of voxels it does not own straight into the owner's inbox over
+// NVLink peer memory (plain 16-byte stores, slots handed out by a local atomic) -- the exchange
+// is part of the expansion kernel, there is no separate pack / all-to-all / unpack.  Every rank
+// exports one "exchange block": a header of flags followed by 2 (chunk parity) x world (source)
+// inbox regions of `cap` records.  Ordering: after its k_expand of chunk c a rank publishes, per
+// peer, the record count and the sequence number c+1 (system-scope fence in between); the owner
+// waits for all sources, merges the records into its dedupe table, and acknowledges, which
+// lets the sources reuse that parity for chunk c+2.
+constexpr int ROUTE_MAX_WORLD = 64;
+struct __align__(16) RouteRec { u64 key; u32 counts; u32 frame; };      // counts = n_occ << 16 | n_free
+struct RouteHdr {
+    u64 flag_count[2][ROUTE_MAX_WORLD];   // [parity][source]: records the source wrote for the chunk
+    u64 flag_seq[2][ROUTE_MAX_WORLD];     //                   ... and the chunk's sequence number + 1
+    u64 ack_seq[2][ROUTE_MAX_WORLD];      // [parity][owner]: that owner has merged my records of sequence number - 1
+};
+struct RouteCtx {
+    u32 world, rank, parity;
+    u64 cap;                              // records per (parity, source) inbox region
+    unsigned char *const *peer;           // [world] exchange blocks of all ranks (device array; peer[rank] is mine)
+    u32 *cursor;                          // [2][ROUTE_MAX_WORLD] records written so far per (parity, owner); local
+};
+
+__device__ __forceinline__ RouteRec *route_inbox(const RouteCtx &rt, u32 owner, u32 parity, u32 source)
+{
+    return reinterpret_cast<RouteRec *>(rt.peer[owner] + sizeof(RouteHdr)) + ((size_t)parity * rt.world + source) * rt.cap;
+}
+
+// one record to `owner` (the rare per-sample path; the flush hands out slots per warp)
+__device__ __forceinline__ void route_send_one(const RouteCtx &rt, MapCtr *mc, u32 owner, u64 key, u32 counts, u32 frame)
+{
+    const u32 pos = atomicAdd(&rt.cursor[rt.parity * ROUTE_MAX_WORLD + owner], 1u);
+    if (pos >= rt.cap) { atomicOr(&mc->err, ERR_ROUTE_FULL); return; }
+    RouteRec r; r.key = key; r.counts = counts; r.frame = frame;
+    route_inbox(rt, owner, rt.parity, rt.rank)[pos] = r;
+}
+
 struct ExpandArgs {
     const uint8_t *imgs; size_t img_stride;
     const double *T;             // [g][16]
@@ -187,6 +225,7 @@ struct ExpandArgs {
     MapCtr *mc;
     int beam_lo, beam_hi;        // processed beams [beam_lo, beam_hi) are expanded (a rank's slice when sharded)
     u32 own_rank, own_world;     // own_world > 1: keep only the voxels this rank owns (replicated expansion)
+    RouteCtx rt;                 // rt.world > 1: voxels of other owners are routed to them (routed map)
     u64 seq;                     // chunk sequence number (for abort bookkeeping)
 };
 
@@ -262,8 +301,12 @@ __device__ __forceinline__ u32 dedupe_add(u64 *skeys, CT *scnt, u32 smask, MapCt
 // a transform too large for the fast quantiser) goes to the dedupe table on its own
 template <typename CT, bool CHECK>
 __device__ __noinline__ void commit_direct(u64 *skeys, CT *scnt, u32 smask, ChunkCtr *cc, MapCtr *mc, u64 seq, u64 key,
-                                           int g, bool occ)
+                                           int g, bool occ, RouteCtx rt)
 {
+    if (rt.world > 1) {
+        const u32 owner = key_owner(key, rt.world);
+        if (owner != rt.rank) { route_send_one(rt, mc, owner, key, occ ? 0x10000u : 1u, (u32)g); return; }
+    }
     const u32 home = dedupe_home(key, smask);
     if (dedupe_add<CT, CHECK>(skeys, scnt, smask, mc, seq, key, home, load_bucket(skeys, home), g, occ ? 1u : 0u, occ ? 0u : 1u))
         atomicAdd(&cc->n_unique, 1u);
@@ -304,11 +347,12 @@ __device__ __forceinline__ void flush_combiner(const ExpandArgs &a, u32 *tkey, u
     // FL_ILP entries per thread at a time: home buckets are fetched together, then resolved
     for (int base = 0; base < n; base += EX_THREADS * FL_ILP) {
         u64 key[FL_ILP]; u32 inc[FL_ILP], home[FL_ILP]; bool ok[FL_ILP]; Bucket bk[FL_ILP];
+        u32 dst[FL_ILP];                      // routed map: owner the entry is sent to, or ~0u
         u32 made = 0;
 #pragma unroll
         for (int j = 0; j < FL_ILP; ++j) {
             const int e = base + j * EX_THREADS + tid;
-            ok[j] = false; key[j] = 0; inc[j] = 0; home[j] = 0;
+            ok[j] = false; key[j] = 0; inc[j] = 0; home[j] = 0; dst[j] = ~0u;
             bk[j].a = bk[j].b = make_ulonglong2(0ull, 0ull);
             if (e < n) {
                 const int idx = live[e];
@@ -321,7 +365,11 @@ __device__ __forceinline__ void flush_combiner(const ExpandArgs &a, u32 *tkey, u
                 else {
                     key[j] = pack_key(ki, kj, kk);
                     // replicated expansion: every rank computes every sample and keeps the voxels it owns
-                    if (a.own_world <= 1 || key_owner(key[j], a.own_world) == a.own_rank) {
+                    const u32 owner = a.rt.world > 1 ? key_owner(key[j], a.rt.world) : a.rt.rank;
+                    if (owner != a.rt.rank) {
+                        dst[j] = owner; inc[j] = c;
+                        emitted += (c >> 16) + (c & 0xffffu);
+                    } else if (a.own_world <= 1 || key_owner(key[j], a.own_world) == a.own_rank) {
                         ok[j] = true;
                         inc[j] = c;
                         emitted += (c >> 16) + (c & 0xffffu);
@@ -338,6 +386,28 @@ __device__ __forceinline__ void flush_combiner(const ExpandArgs &a, u32 *tkey, u
         // entries created for the chunk: one reduction per warp per batch (nobody waits for it)
         made = __reduce_add_sync(0xffffffffu, made);
         if (lane == 0 && made) atomicAdd(&a.cc->n_unique, made);
+        // routed map: entries of other owners go into their inboxes; lanes with the same owner
+        // take consecutive slots from one local atomic, the records are plain peer-memory stores
+        if (a.rt.world > 1) {
+#pragma unroll
+            for (int j = 0; j < FL_ILP; ++j) {
+                const bool send = dst[j] != ~0u;
+                if (!__any_sync(0xffffffffu, send)) continue;
+                const u32 peers = __match_any_sync(0xffffffffu, dst[j]);
+                const int leader = __ffs(peers) - 1;
+                u32 at = 0;
+                if (send && lane == leader) at = atomicAdd(&a.rt.cursor[a.rt.parity * ROUTE_MAX_WORLD + dst[j]], (u32)__popc(peers));
+                at = __shfl_sync(0xffffffffu, at, leader);
+                if (send) {
+                    const u32 pos = at + __popc(peers & ((1u << lane) - 1));
+                    if (pos >= a.rt.cap) atomicOr(&a.mc->err, ERR_ROUTE_FULL);
+                    else {
+                        RouteRec r; r.key = key[j]; r.counts = inc[j]; r.frame = (u32)g;
+                        route_inbox(a.rt, dst[j], a.rt.parity, a.rt.rank)[pos] = r;
+                    }
+                }
+            }
+        }
     }
     __syncthreads();
     if (tid == 0) *s_count = 0;
@@ -557,7 +627,7 @@ k_expand(ExpandArgs a)
                     const u64 key = pack_key(ki, kj, kk);
                     if (a.own_world > 1 && key_owner(key, a.own_world) != a.own_rank) continue;
                     ++emitted;
-                    commit_direct<CT, CHECK>(a.skeys, static_cast<CT *>(a.scnt), a.smask, a.cc, a.mc, a.seq, key, g, occ);
+                    commit_direct<CT, CHECK>(a.skeys, static_cast<CT *>(a.scnt), a.smask, a.cc, a.mc, a.seq, key, g, occ, a.rt);
                 }
             }
             // combiner slots created by this pass join the live list: one shared-memory atomic per pass
@@ -740,6 +810,7 @@ k_apply_chunk(u64 *__restrict__ skeys, CT *__restrict__ scnt, u32 n_slots, int g
     unsigned char *s_cls = reinterpret_cast<unsigned char *>(s_mask + AP_Q);
     __shared__ unsigned short s_ordA[AP_THREADS], s_ordB[AP_THREADS];
     __shared__ u32 s_occ[GF], s_free[GF], s_new[GF], s_nA, s_nB, s_qn;
+    __shared__ u32 s_hist[AP_THREADS / 32][2 * GF];   // per warp: voxels updated as free / occupied in frame f
     __shared__ double s_sum[4][SUMT];
     __shared__ bool s_last;
     static_assert(GF <= 16, "s_mask holds one bit per frame");
@@ -750,8 +821,9 @@ k_apply_chunk(u64 *__restrict__ skeys, CT *__restrict__ scnt, u32 n_slots, int g
     if (tid < GF) { s_occ[tid] = 0; s_free[tid] = 0; s_new[tid] = 0; }
     if (tid == 0) { s_qn = 0; s_nA = 0; s_nB = 0; }
     for (int q = tid; q < 4 * SUMT; q += AP_THREADS) (&s_sum[0][0])[q] = sum_tab[q];
+    for (int q = tid; q < (AP_THREADS / 32) * 2 * GF; q += AP_THREADS) (&s_hist[0][0])[q] = 0;
     __syncthreads();
-    u32 w_occ = 0, w_free = 0;                  // lane f of each warp accumulates frame f
+    u32 *hist = s_hist[tid >> 5];
     u32 consumed = 0;                           // ring entries already applied (block-uniform)
     LocalAcc acc; acc_init(acc);
 
@@ -781,6 +853,10 @@ k_apply_chunk(u64 *__restrict__ skeys, CT *__restrict__ scnt, u32 n_slots, int g
                 const CT cf = row[f];
                 const u32 n_occ = Lane<CT>::n_occ(cf), n_free = Lane<CT>::n_free(cf);
                 Lv = apply_one(Lv, seq_avg(n_free, n_occ, s_sum, p), n_occ > 0, p);
+                // num_occupied / num_free of frame f (:562-567); lanes on the same (frame, kind) add once
+                const u32 bin = 2u * (u32)f + (n_occ > 0 ? 1u : 0u);
+                const u32 peers = __match_any_sync(__activemask(), bin);
+                if (lane == (u32)__ffs(peers) - 1) atomicAdd(&hist[bin], (u32)__popc(peers));
             }
             table[s_slot[e]].val = Lv;
         }
@@ -821,17 +897,12 @@ k_apply_chunk(u64 *__restrict__ skeys, CT *__restrict__ scnt, u32 n_slots, int g
             }
         }
         u32 mask = 0; bool any_occ = false;
-        if (__any_sync(0xffffffffu, live)) {
+        if (live) {
 #pragma unroll
             for (int f = 0; f < GF; ++f) {
-                if (f < g) {                                            // uniform
-                    const bool hit = live && c[f] != 0;
-                    const bool occ = hit && Lane<CT>::n_occ(c[f]) > 0;  // occupied has priority (:544-545)
-                    const u32 b_occ = __ballot_sync(0xffffffffu, occ);
-                    const u32 b_free = __ballot_sync(0xffffffffu, hit && !occ);
-                    if (lane == (u32)f) { w_occ += __popc(b_occ); w_free += __popc(b_free); }
-                    if (hit) mask |= 1u << f;
-                    any_occ |= occ;
+                if (f < g && c[f] != 0) {
+                    mask |= 1u << f;
+                    any_occ |= Lane<CT>::n_occ(c[f]) > 0;               // occupied has priority (:544-545)
                 }
             }
         }
@@ -862,9 +933,10 @@ k_apply_chunk(u64 *__restrict__ skeys, CT *__restrict__ scnt, u32 n_slots, int g
     }
     acc_publish(acc, mc, false);
     __syncthreads();
-    if (lane < GF) {
-        if (w_occ) atomicAdd(&s_occ[lane], w_occ);
-        if (w_free) atomicAdd(&s_free[lane], w_free);
+    if (tid < 2 * GF) {
+        u32 sum = 0;
+        for (int w = 0; w < AP_THREADS / 32; ++w) sum += s_hist[w][tid];
+        if (tid & 1) s_occ[tid >> 1] = sum; else s_free[tid >> 1] = sum;
     }
     __syncthreads();
     if (tid < (u32)g) {
@@ -973,6 +1045,73 @@ __global__ void k_shard_merge(const u64 *__restrict__ recv, u64 n_rec, u64 *skey
             }
         }
     }
+}
+
+// ---- routed map: signalling and the owner-side merge
+__device__ __forceinline__ u64 global_ns() { u64 t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
+// after k_expand of a chunk: tell every peer how many records it got and that they are complete
+__global__ void k_route_signal(RouteCtx rt, u64 seq_plus_1)
+{
+    const u32 o = threadIdx.x;
+    if (o >= rt.world || o == rt.rank) return;
+    u32 *cur = &rt.cursor[rt.parity * ROUTE_MAX_WORLD + o];
+    const u64 cnt = min((u64)*cur, rt.cap);
+    *cur = 0;                                              // this parity's next use is two chunks away, on this stream
+    RouteHdr *h = reinterpret_cast<RouteHdr *>(rt.peer[o]);
+    __threadfence_system();                                // the records (written by the kernel before this one) first
+    *(volatile u64 *)&h->flag_count[rt.parity][rt.rank] = cnt;
+    __threadfence_system();
+    *(volatile u64 *)&h->flag_seq[rt.parity][rt.rank] = seq_plus_1;
+}
+
+// one warp: lane s waits until word[s] >= want (skipping this rank); a peer that stays silent for
+// `timeout_ns` raises ERR_ROUTE_TIMEOUT instead of hanging the GPU
+__global__ void k_route_wait(const u64 *words, u32 world, u32 rank, u64 want, u64 timeout_ns, MapCtr *mc)
+{
+    const u32 s = threadIdx.x;
+    if (s >= world || s == rank) return;
+    const volatile u64 *w = words + s;
+    const u64 t0 = global_ns();
+    while (*w < want) {
+        if (global_ns() - t0 > timeout_ns) { atomicOr(&mc->err, ERR_ROUTE_TIMEOUT); break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+// owner side: records of all sources -> this rank's dedupe table of the chunk
+template <typename CT, bool CHECK>
+__global__ void k_route_merge(RouteCtx rt, u64 *skeys, CT *scnt, u32 smask, ChunkCtr *cc, MapCtr *mc, u64 seq)
+{
+    if (__ldcg(&mc->abort)) return;
+    const RouteHdr *h = reinterpret_cast<const RouteHdr *>(rt.peer[rt.rank]);
+    u32 made = 0;
+    for (u32 src = 0; src < rt.world; ++src) {
+        if (src == rt.rank) continue;
+        const u64 n = *(const volatile u64 *)&h->flag_count[rt.parity][src];
+        const RouteRec *in = route_inbox(rt, rt.rank, rt.parity, src);
+        for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+            const ulonglong2 raw = __ldcv(reinterpret_cast<const ulonglong2 *>(in + i));   // written by a peer: do not cache
+            const u64 key = raw.x;
+            const u32 counts = (u32)raw.y, frame = (u32)(raw.y >> 32);
+            const u32 home = dedupe_home(key, smask);
+            made += dedupe_add<CT, CHECK>(skeys, scnt, smask, mc, seq, key, home, load_bucket(skeys, home), (int)(frame & (GF - 1)),
+                                          counts >> 16, counts & 0xffffu);
+        }
+    }
+    made = __reduce_add_sync(0xffffffffu, made);
+    if ((threadIdx.x & 31) == 0 && made) atomicAdd(&cc->n_unique, made);
+}
+
+// after the merge: the sources may reuse this parity
+__global__ void k_route_ack(RouteCtx rt, u64 seq_plus_1)
+{
+    const u32 s = threadIdx.x;
+    if (s >= rt.world || s == rt.rank) return;
+    RouteHdr *h = reinterpret_cast<RouteHdr *>(rt.peer[s]);
+    __threadfence_system();
+    *(volatile u64 *)&h->ack_seq[rt.parity][rt.rank] = seq_plus_1;
 }
 
 __global__ void k_shard_count0(ChunkCtr *cc, const MapCtr *mc) { cc->count0 = mc->count; }
@@ -1198,6 +1337,13 @@ struct s3d_map {
     // sharded map (multi-GPU): this rank's identity and beam slice, exchange staging
     int shard_rank = 0, shard_world = 1, beam_lo = 0, beam_hi = -1;
     bool shard_filter = false;       // replicated expansion: s3d_ingest* keeps only the voxels this rank owns
+    // routed map: exchange block (flags + inboxes) of this rank, the peers' blocks, local cursors
+    bool route_on = false;
+    unsigned char *xblock = nullptr; size_t xblock_bytes = 0; u64 route_cap = 0;
+    std::vector<unsigned char *> peer_ptr; std::vector<void *> ipc_opened;
+    DevBuf<unsigned char *> d_peers; DevBuf<u32> route_cursor;
+    u64 route_seq = 0;               // chunks routed so far (the same on every rank)
+    u64 route_timeout_ns = 5000000000ull;
     DevBuf<u64> send_buf; DevBuf<u32> owner_ctr;      // owner_ctr: [3][64] count / base / fill
     u32 *owner_host = nullptr;                        // pinned [64]
     int l2_policy = 0;               // S3D_L2_POLICY: 0 = no window, 1 = persisting + streaming misses, 2 = persisting + normal
@@ -1250,6 +1396,22 @@ namespace {
 
 int set_device(s3d_map *m) { CU(cudaSetDevice(m->device)); return 0; }
 
+// With lazy module loading the first launch of a kernel may have to wait for the device to go
+// idle; a routed map keeps kernels spinning on peer flags, so every pipeline kernel is loaded
+// up front.
+template <typename F> int preload(F f) { cudaFuncAttributes at; CU(cudaFuncGetAttributes(&at, f)); return 0; }
+int preload_pipeline_kernels()
+{
+    int rc;
+    if ((rc = preload(k_expand<u32, false>)) || (rc = preload(k_expand<u32, true>)) || (rc = preload(k_expand<u64, false>)) ||
+        (rc = preload(k_apply_chunk<u32>)) || (rc = preload(k_apply_chunk<u64>)) || (rc = preload(k_gate)) ||
+        (rc = preload(k_route_signal)) || (rc = preload(k_route_wait)) || (rc = preload(k_route_ack)) ||
+        (rc = preload(k_route_merge<u32, true>)) || (rc = preload(k_route_merge<u64, false>)) ||
+        (rc = preload(k_fill_slots)) || (rc = preload(k_fill_u64)) || (rc = preload(k_rehash)) || (rc = preload(k_clear_abort)))
+        return rc;
+    return 0;
+}
+
 // CUDA-event bracket around one kernel group, on the launching stream
 size_t prof_mark(s3d_map *m, cudaStream_t st)
 {
@@ -1293,6 +1455,10 @@ int fatal_from_flags(s3d_map *m, u32 err)
     cudaMemcpyAsync(&m->mc->err, &zero, sizeof zero, cudaMemcpyHostToDevice, m->stream);
     cudaStreamSynchronize(m->stream);
     if (err & ERR_TABLEFULL) return fail(S3D_ETABLEFULL, "voxel table full (capacity %llu slots)", (unsigned long long)m->cap);
+    if (err & ERR_ROUTE_FULL) return fail(S3D_EROUTE, "routed map: a peer inbox overflowed (%llu records per pair; export a larger one)",
+                                          (unsigned long long)m->route_cap);
+    if (err & ERR_ROUTE_TIMEOUT) return fail(S3D_EROUTE, "routed map: a peer rank did not signal within %.1f s (every rank must ingest the same frames)",
+                                             (double)m->route_timeout_ns * 1e-9);
     return fail(S3D_EKEYRANGE, "voxel key outside +-2^20 or non-finite coordinate");
 }
 
@@ -1436,7 +1602,9 @@ void launch_expand(s3d_map *m, const ExpandArgs &a, int n_beams, int g, cudaStre
 
 void launch_apply(s3d_map *m, u64 *skeys, void *scnt, int g, ChunkCtr *cc, DevStats *st, cudaStream_t stream)
 {
-    const int blocks = (int)std::min<u64>(m->scratch_cap / AP_THREADS, (u64)m->n_sm * 4);
+    // as many blocks as stay resident, every block with the same number of tiles
+    const u64 tiles = m->scratch_cap / AP_THREADS, resident = (u64)m->n_sm * 4;
+    const int blocks = (int)(tiles / ((tiles + resident - 1) / resident));
     if (m->wide)
         k_apply_chunk<u64><<<blocks, AP_THREADS, apply_smem_bytes<u64>(), stream>>>(skeys, static_cast<u64 *>(scnt), (u32)m->scratch_cap, g, cc, st,
                                                              m->table, m->cap - 1, m->p, m->sum_tab.p, m->mc);
@@ -1466,12 +1634,42 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     a.seq = m->chunk_seq;
     a.beam_lo = 0; a.beam_hi = tab.n_beams;
     a.own_rank = (u32)m->shard_rank; a.own_world = m->shard_filter ? (u32)m->shard_world : 1u;
-    launch_expand(m, a, tab.n_beams, g, xs);
+    a.rt = RouteCtx{1u, 0u, 0u, 0ull, nullptr, nullptr};
+    const bool routed = m->route_on && m->shard_world > 1;
+    if (routed) {
+        // this rank's contiguous slice of the processed beams; voxels of other owners travel to them
+        a.beam_lo = (int)((int64_t)tab.n_beams * m->shard_rank / m->shard_world);
+        a.beam_hi = (int)((int64_t)tab.n_beams * (m->shard_rank + 1) / m->shard_world);
+        a.own_world = 1u;
+        a.rt = RouteCtx{(u32)m->shard_world, (u32)m->shard_rank, (u32)(m->route_seq & 1), m->route_cap, m->d_peers.p, m->route_cursor.p};
+        // the owners must have merged what this rank sent them two chunks ago (same parity)
+        if (m->route_seq >= 2) {
+            const RouteHdr *h = reinterpret_cast<const RouteHdr *>(m->xblock);
+            k_route_wait<<<1, ROUTE_MAX_WORLD, 0, xs>>>(h->ack_seq[a.rt.parity], a.rt.world, a.rt.rank, m->route_seq - 1,
+                                                       m->route_timeout_ns, m->mc);
+            m->launches += 1;
+        }
+    }
+    if (a.beam_hi > a.beam_lo) launch_expand(m, a, a.beam_hi - a.beam_lo, g, xs);
+    if (routed) { k_route_signal<<<1, ROUTE_MAX_WORLD, 0, xs>>>(a.rt, m->route_seq + 1); m->launches += 1; }
     const size_t e2 = m->prof_on ? prof_mark(m, xs) : 0;
     CU(cudaEventRecord(cb.expanded, xs));
     // ---- apply stream: gate, then the chunk's frames in order into the voxel table
     CU(cudaStreamWaitEvent(as, cb.expanded, 0));
     const size_t e3 = m->prof_on ? prof_mark(m, as) : 0;
+    if (routed) {
+        const RouteHdr *h = reinterpret_cast<const RouteHdr *>(m->xblock);
+        k_route_wait<<<1, ROUTE_MAX_WORLD, 0, as>>>(h->flag_seq[a.rt.parity], a.rt.world, a.rt.rank, m->route_seq + 1,
+                                                   m->route_timeout_ns, m->mc);
+        const int mb = m->n_sm * 4;
+        if (m->wide)
+            k_route_merge<u64, false><<<mb, 256, 0, as>>>(a.rt, cb.skeys, static_cast<u64 *>(cb.scnt), a.smask, cb.cc, m->mc, m->chunk_seq);
+        else
+            k_route_merge<u32, true><<<mb, 256, 0, as>>>(a.rt, cb.skeys, static_cast<u32 *>(cb.scnt), a.smask, cb.cc, m->mc, m->chunk_seq);
+        k_route_ack<<<1, ROUTE_MAX_WORLD, 0, as>>>(a.rt, m->route_seq + 1);
+        m->launches += 3;
+        ++m->route_seq;
+    }
     k_gate<<<1, 1, 0, as>>>(cb.cc, m->mc, table_limit(m), m->chunk_seq);
     launch_apply(m, cb.skeys, cb.scnt, g, cb.cc, j.stats + base, as);
     CU(cudaGetLastError());
@@ -1505,6 +1703,10 @@ int recover(s3d_map *m)
     CU(cudaStreamSynchronize(m->stream));
     const MapCtr mc = *m->mc_host;
     if (!mc.abort) return 0;
+    if (m->route_on && m->shard_world > 1)
+        return fail(S3D_EROUTE, "routed map: chunk %llu needs a re-run (flags %u: 1 = dedupe table, 2 = voxel table, 4 = counter width); "
+                                "peers cannot replay it -- reserve capacity (s3d_reserve) before ingesting",
+                    (unsigned long long)mc.abort_seq, mc.abort);
     const InFlight inf = m->inflight[mc.abort_seq % s3d_map::RING];
     if (inf.seq != mc.abort_seq) return fail(S3D_ECUDA, "internal: lost track of chunk %llu", (unsigned long long)mc.abort_seq);
     ++m->n_retries;
@@ -1553,16 +1755,16 @@ int pump(s3d_map *m, bool drain)
                 m->unique_est = std::max<u64>(sn.last_unique, m->unique_est - m->unique_est / 8);
             }
             // grow ahead of the gate when the chunks in flight could reach it (saves a retry)
-            if (m->count_known + (u64)(LOOKAHEAD + 2) * m->unique_est > table_limit(m) ||
-                3 * m->unique_est > 2 * m->scratch_cap) {
+            // (a routed map cannot re-run a chunk, so it keeps twice the margin)
+            const u64 margin = (u64)(LOOKAHEAD + 2) * m->unique_est * (m->route_on ? 2 : 1);
+            if (m->count_known + margin > table_limit(m) || 3 * m->unique_est > 2 * m->scratch_cap) {
                 CU(cudaMemcpyAsync(m->mc_host, m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, m->stream));
                 CU(cudaStreamSynchronize(m->stream));
                 if (m->mc_host->abort) { int rc = recover(m); if (rc) return rc; continue; }
                 m->count_known = m->mc_host->count;
                 m->snap_floor = m->chunk_seq;
                 int rc;
-                if (m->count_known + (u64)(LOOKAHEAD + 2) * m->unique_est > table_limit(m) &&
-                    (rc = grow_table(m, m->cap * 2))) return rc;
+                if (m->count_known + margin > table_limit(m) && (rc = grow_table(m, m->cap * 2))) return rc;
                 if (3 * m->unique_est > 2 * m->scratch_cap && (rc = ensure_scratch(m, m->scratch_cap * 2, false))) return rc;
             }
             const int g = (int)std::min<int64_t>(GF, job->n - job->next);
@@ -1720,6 +1922,9 @@ int s3d_destroy(s3d_map *m)
     if (m->x_ev) cudaEventDestroy(m->x_ev);
     if (m->owner_host) cudaFreeHost(m->owner_host);
     m->send_buf.release(); m->owner_ctr.release();
+    for (void *q : m->ipc_opened) cudaIpcCloseMemHandle(q);
+    if (m->xblock) cudaFree(m->xblock);
+    m->d_peers.release(); m->route_cursor.release();
     for (cudaEvent_t e : m->copy_ev) cudaEventDestroy(e);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->ex_counts) cudaFree(m->ex_counts);
@@ -1930,6 +2135,85 @@ int s3d_shard_filter(s3d_map *m, int on)
     return 0;
 }
 
+int s3d_route_export(s3d_map *m, uint64_t records_per_pair, unsigned char *handle)
+{
+    if (!m || !handle) return fail(S3D_EINVAL, "null argument");
+    if (!m->owner_host) return fail(S3D_EINVAL, "s3d_shard_config has not been called");
+    if (records_per_pair < 1024) records_per_pair = 1024;
+    int rc = set_device(m); if (rc) return rc;
+    if ((rc = sync_counters(m))) return rc;
+    if (m->route_on) return fail(S3D_EINVAL, "routing is enabled; disable it before exporting a new exchange block");
+    if (m->xblock) { cudaFree(m->xblock); m->xblock = nullptr; }
+    m->route_cap = records_per_pair;
+    m->xblock_bytes = sizeof(RouteHdr) + sizeof(RouteRec) * 2 * (size_t)m->shard_world * (size_t)records_per_pair;
+    cudaError_t e = cudaMalloc(&m->xblock, m->xblock_bytes);
+    if (e != cudaSuccess) return fail(S3D_ENOMEM, "exchange block of %zu bytes: %s", m->xblock_bytes, cudaGetErrorString(e));
+    CU(cudaMemset(m->xblock, 0, sizeof(RouteHdr)));
+    m->route_seq = 0;
+    memset(handle, 0, S3D_ROUTE_HANDLE_BYTES);
+    memcpy(handle, &m->xblock, sizeof(void *));                       // same-process peers use the pointer itself
+    cudaIpcMemHandle_t ipc;
+    e = cudaIpcGetMemHandle(&ipc, m->xblock);
+    if (e == cudaSuccess) memcpy(handle + 8, &ipc, sizeof ipc);
+    else cudaGetLastError();                                          // no IPC on this platform: same-process use only
+    static_assert(sizeof(cudaIpcMemHandle_t) + 8 <= S3D_ROUTE_HANDLE_BYTES, "handle size");
+    return 0;
+}
+
+int s3d_route_attach(s3d_map *m, const unsigned char *handles, int same_process)
+{
+    if (!m || !handles) return fail(S3D_EINVAL, "null argument");
+    if (!m->xblock) return fail(S3D_EINVAL, "s3d_route_export has not been called");
+    int rc = set_device(m); if (rc) return rc;
+    if ((rc = sync_counters(m))) return rc;
+    for (void *q : m->ipc_opened) cudaIpcCloseMemHandle(q);
+    m->ipc_opened.clear();
+    const int world = m->shard_world;
+    m->peer_ptr.assign((size_t)world, nullptr);
+    for (int o = 0; o < world; ++o) {
+        const unsigned char *h = handles + (size_t)o * S3D_ROUTE_HANDLE_BYTES;
+        if (o == m->shard_rank) { m->peer_ptr[(size_t)o] = m->xblock; continue; }
+        if (same_process) {
+            unsigned char *ptr = nullptr;
+            memcpy(&ptr, h, sizeof ptr);
+            m->peer_ptr[(size_t)o] = ptr;
+        } else {
+            cudaIpcMemHandle_t ipc;
+            memcpy(&ipc, h + 8, sizeof ipc);
+            void *ptr = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return fail(S3D_ECUDA, "cudaIpcOpenMemHandle(rank %d): %s", o, cudaGetErrorString(e));
+            m->ipc_opened.push_back(ptr);
+            m->peer_ptr[(size_t)o] = static_cast<unsigned char *>(ptr);
+        }
+        if (!m->peer_ptr[(size_t)o]) return fail(S3D_EINVAL, "rank %d: empty exchange handle", o);
+    }
+    if ((rc = m->d_peers.ensure((size_t)world))) return rc;
+    CU(cudaMemcpy(m->d_peers.p, m->peer_ptr.data(), sizeof(unsigned char *) * (size_t)world, cudaMemcpyHostToDevice));
+    if ((rc = m->route_cursor.ensure(2 * ROUTE_MAX_WORLD))) return rc;
+    CU(cudaMemset(m->route_cursor.p, 0, sizeof(u32) * 2 * ROUTE_MAX_WORLD));
+    { const char *e = getenv("S3D_ROUTE_TIMEOUT_MS"); if (e && atof(e) > 0) m->route_timeout_ns = (u64)(atof(e) * 1e6); }
+    return 0;
+}
+
+int s3d_route_enable(s3d_map *m, int on)
+{
+    if (!m) return fail(S3D_EINVAL, "null map");
+    int rc = set_device(m); if (rc) return rc;
+    if ((rc = sync_counters(m))) return rc;
+    if (on && m->shard_world > 1 && m->peer_ptr.size() != (size_t)m->shard_world)
+        return fail(S3D_EINVAL, "s3d_route_attach has not been called");
+    if (on && m->shard_filter) return fail(S3D_EINVAL, "routing and the replicated-expansion filter exclude each other");
+    if (on && (rc = preload_pipeline_kernels())) return rc;
+    if (on && !m->wide && !m->narrow_safe && m->have_tables) {
+        // a count overflow would need a re-run that the peers cannot replay: start with wide lanes
+        m->wide = true;
+        if ((rc = ensure_scratch(m, m->scratch_cap, true, true))) return rc;
+    }
+    m->route_on = on != 0;
+    return 0;
+}
+
 int s3d_shard_owner(const int32_t *ijk, int64_t n, int world, int32_t *owner)
 {
     if (world < 1) return fail(S3D_EINVAL, "world < 1");
@@ -1965,6 +2249,7 @@ int s3d_shard_expand(s3d_map *m, const uint8_t *images_dev, const double *T_dev,
             a.seq = m->chunk_seq;                                // the owner gates growth, not the expander
             a.beam_lo = lo; a.beam_hi = hi;
             a.own_rank = 0; a.own_world = 1;
+            a.rt = RouteCtx{1u, 0u, 0u, 0ull, nullptr, nullptr};
             launch_expand(m, a, hi - lo, g, m->stream);
         }
         // counts per owner -> host (the all-to-all needs the split sizes), and the retry flag

@@ -7,7 +7,13 @@ map shards by a hash of the voxel key (`owner_of_keys`); every rank sees every f
   integer counts, the counts travel to the owning rank in one variable-size all-to-all per chunk
   of 16 frames (NCCL over NVLink/NVSwitch through torch.distributed; gloo works for CPU tests),
   and the owner merges them by integer addition and applies the chunk's frames in order.
-* ``mode="replicate"`` (default) -- each rank expands ALL beams but keeps only the samples whose
+* ``mode="fused"`` (default) -- the same partition as "route", but the exchange is part of the
+  expansion kernel: its flush writes the records of voxels owned by other ranks straight into the
+  owners' inboxes over NVLink peer memory (CUDA IPC mappings, set up once), device-side sequence
+  flags order sources and owners, and the owner merges before it applies.  No host
+  synchronisation and no separate all-to-all per chunk; the rank-local pipeline stays asynchronous.
+  Only the per-frame counters are all-reduced, once per call.
+* ``mode="replicate"`` -- each rank expands ALL beams but keeps only the samples whose
   voxel it owns, so its dedupe table already holds exactly its shard's counts and no exchange is
   needed; the cheap expansion arithmetic is repeated on every rank, the hash-table work (the
   expensive part, see profiles/README.md) and the voxel table are split N ways, and the rank-local
@@ -132,6 +138,10 @@ class Exchange:
                 w.wait()
         return recv, recv_counts
 
+    def barrier(self):
+        if self.world > 1:
+            _dist().barrier(group=self.group)
+
     def all_reduce_sum(self, t):
         if self.world > 1:
             _dist().all_reduce(t, group=self.group)
@@ -181,8 +191,18 @@ class CudaShardBackend:
         self.native.shard_config(rank, world)
         self.world = world
 
-    def set_mode(self, mode: str):
+    def set_mode(self, mode: str, exchange=None, inbox_records: int = 1 << 21):
+        self.native.route_enable(False)
         self.native.shard_filter(mode == "replicate" and self.world > 1)
+        if mode == "fused" and self.world > 1:
+            # collective: exchange blocks of all ranks, mapped into every rank through CUDA IPC
+            t = self.torch
+            mine = t.frombuffer(bytearray(self.native.route_export(inbox_records)), dtype=t.uint8).to(self.device)
+            allh = exchange.all_gather_rows(mine[None, :]).cpu().numpy().tobytes()
+            self.native.route_attach(allh, same_process=False)
+            exchange.barrier()
+            self.native.route_enable(True)
+            exchange.barrier()
 
     def ingest_owned_dev(self, d_img, d_T):
         """replicate mode, inputs on the device: per-shard counters int64[n, 4] (device tensor)."""
@@ -248,9 +268,9 @@ class ShardedSonarMapper:
     same arguments.  `group=None` means a single rank (no torch.distributed needed)."""
 
     def __init__(self, config: Optional[Dict[str, Any]] = None, group=None, backend_factory=None,
-                 mode: str = "replicate"):
-        if mode not in ("replicate", "route"):
-            raise ValueError("mode must be 'replicate' or 'route'")
+                 mode: str = "fused"):
+        if mode not in ("fused", "replicate", "route"):
+            raise ValueError("mode must be 'fused', 'replicate' or 'route'")
         self.mode = mode
         self.ex = Exchange(group)
         self.rank, self.world = self.ex.rank, self.ex.world
@@ -260,7 +280,10 @@ class ShardedSonarMapper:
             self.backend = CudaShardBackend(self.mapper, self.rank, self.world)
         else:
             self.mapper, self.backend = backend_factory(config, self.rank, self.world)
-        self.backend.set_mode(mode)
+        if mode == "fused":
+            self.backend.set_mode(mode, exchange=self.ex)
+        else:
+            self.backend.set_mode(mode)
         self.frame_count = 0
         self.processed_frame_count = 0
         self.total_processing_time = 0.0
@@ -281,7 +304,7 @@ class ShardedSonarMapper:
         m._check_width(W)
         T = m.compose_transforms(robot_positions, robot_orientations)
         m._sync_device_config(H, W)
-        if self.mode == "replicate":
+        if self.mode in ("replicate", "fused"):
             stats = self.ex.all_reduce_sum(self.backend.ingest_owned_host(polar_images, T))
             self.last_exchange_bytes = 0
             return self._finish(stats, n, t0)
@@ -294,7 +317,7 @@ class ShardedSonarMapper:
         num_occupied, num_free, num_voxels, num_samples."""
         import torch
         n = int(d_img.shape[0])
-        if self.mode == "replicate":
+        if self.mode in ("replicate", "fused"):
             self.last_exchange_bytes = 0
             return self.ex.all_reduce_sum(self.backend.ingest_owned_dev(d_img, d_T))
         samples, applied = [], []

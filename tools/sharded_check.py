@@ -30,7 +30,7 @@ def main():
     images, pos, quat, cfg = synthetic.make_sequence("cfg2", n, seed=2)
     cfg = dict(cfg, device=local)
     plain_ref = None
-    for mode in ("replicate", "route"):
+    for mode in ("fused", "replicate", "route"):
         sh = ShardedSonarMapper(cfg, group=dist.group.WORLD, mode=mode)
         stats = sh.process_sonar_images(images, pos, quat)
         keys, L = sh.gather_map()
