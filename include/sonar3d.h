@@ -239,6 +239,10 @@ typedef struct s3d_profile {
 } s3d_profile;
 
 int s3d_profile_enable(s3d_map *map, int on);
+/* Development aid (maps created with S3D_TRACE=1 in the environment): GPU timestamps
+ * (%globaltimer, ns) of the pipeline kernels of the first chunks, 10 uint64 per chunk =
+ * {start, end} x {ack wait, expand, flag wait, merge, apply}; untouched slots read ~0 / 0. */
+int s3d_trace_read(s3d_map *map, uint64_t *out, uint64_t max_chunks, uint64_t *n_chunks);
 /* Synchronises the stream, fills `out`, resets the accumulators. */
 int s3d_profile_read(s3d_map *map, s3d_profile *out);
 

@@ -19,7 +19,7 @@ SYMBOLS = (
     "s3d_capacity", "s3d_export_begin", "s3d_export_read", "s3d_export_read_xyzi32",
     "s3d_profile_enable", "s3d_profile_read",
     "s3d_shard_config", "s3d_shard_filter", "s3d_shard_owner", "s3d_shard_expand", "s3d_shard_apply",
-    "s3d_route_export", "s3d_route_attach", "s3d_route_enable",
+    "s3d_route_export", "s3d_route_attach", "s3d_route_enable", "s3d_trace_read",
 )
 
 
@@ -106,6 +106,7 @@ def load_library():
     L.s3d_route_export.argtypes = [vp, C.c_uint64, C.c_char_p]
     L.s3d_route_attach.argtypes = [vp, C.c_char_p, C.c_int]
     L.s3d_route_enable.argtypes = [vp, C.c_int]
+    L.s3d_trace_read.argtypes = [vp, u64p, C.c_uint64, u64p]
     L.s3d_shard_owner.argtypes = [i32p, C.c_int64, C.c_int, i32p]
     L.s3d_shard_expand.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(vp), u64p]
     L.s3d_shard_apply.argtypes = [vp, vp, C.c_uint64, C.c_int, vp]
@@ -228,6 +229,13 @@ class NativeMap:
     def route_attach(self, handles: bytes, same_process: bool = False):
         """handles: the world's handles back to back, in rank order."""
         _check(self._lib.s3d_route_attach(self._h, bytes(handles), int(bool(same_process))))
+
+    def trace_read(self, max_chunks: int = 4096) -> np.ndarray:
+        """S3D_TRACE=1: uint64[n_chunks, 5, 2] = {start, end} ns of ack wait, expand, flag wait, merge, apply."""
+        out = np.zeros(max_chunks * 10, dtype=np.uint64)
+        n = C.c_uint64(0)
+        _check(self._lib.s3d_trace_read(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), int(max_chunks), C.byref(n)))
+        return out[: n.value * 10].reshape(-1, 5, 2)
 
     def route_enable(self, on: bool = True):
         _check(self._lib.s3d_route_enable(self._h, int(bool(on))))

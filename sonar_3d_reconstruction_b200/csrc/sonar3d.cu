@@ -94,7 +94,8 @@ struct MapCtr {       // device-resident map counters
 struct ChunkCtr {     // working counters of the chunk in flight (chunks are serialised on the stream)
     u64 count0;       // live voxels before the chunk
     u32 n_unique;     // dedupe entries created for the chunk (k_expand, k_shard_merge)
-    u32 ticket;       // last-block-out election
+    u32 ticket;       // last-block-out election (k_apply_chunk)
+    u32 xticket;      // last-block-out election of k_expand / k_route_merge (routed map)
     u32 neu[GF];      // voxels first inserted at frame f of the chunk
 };
 
@@ -182,24 +183,61 @@ struct __align__(16) Fan { int off; u32 code; double range; };   // code = r | n
 // flush writes the entries of voxels it does not own straight into the owner's inbox over
 // NVLink peer memory (plain 16-byte stores, slots handed out by a local atomic) -- the exchange
 // is part of the expansion kernel, there is no separate pack / all-to-all / unpack.  Every rank
-// exports one "exchange block": a header of flags followed by 2 (chunk parity) x world (source)
+// exports one "exchange block": a header of flags followed by ROUTE_DEPTH (chunk parity) x world (source)
 // inbox regions of `cap` records.  Ordering: after its k_expand of chunk c a rank publishes, per
 // peer, the record count and the sequence number c+1 (system-scope fence in between); the owner
 // waits for all sources, merges the records into its dedupe table, and acknowledges, which
-// lets the sources reuse that parity for chunk c+2.
+// lets the sources reuse that parity for chunk c + ROUTE_DEPTH.
 constexpr int ROUTE_MAX_WORLD = 64;
+constexpr int ROUTE_DEPTH = 4;            // inbox regions per source: chunk c uses region c % ROUTE_DEPTH ("parity")
 struct __align__(16) RouteRec { u64 key; u32 counts; u32 frame; };      // counts = n_occ << 16 | n_free
 struct RouteHdr {
-    u64 flag_count[2][ROUTE_MAX_WORLD];   // [parity][source]: records the source wrote for the chunk
-    u64 flag_seq[2][ROUTE_MAX_WORLD];     //                   ... and the chunk's sequence number + 1
-    u64 ack_seq[2][ROUTE_MAX_WORLD];      // [parity][owner]: that owner has merged my records of sequence number - 1
+    u64 flag_count[ROUTE_DEPTH][ROUTE_MAX_WORLD];   // [parity][source]: records the source wrote for the chunk
+    u64 flag_seq[ROUTE_DEPTH][ROUTE_MAX_WORLD];     //                   ... and the chunk's sequence number + 1
+    u64 ack_seq[ROUTE_DEPTH][ROUTE_MAX_WORLD];      // [parity][owner]: that owner has merged my records of sequence number - 1
 };
 struct RouteCtx {
     u32 world, rank, parity;
     u64 cap;                              // records per (parity, source) inbox region
     unsigned char *const *peer;           // [world] exchange blocks of all ranks (device array; peer[rank] is mine)
-    u32 *cursor;                          // [2][ROUTE_MAX_WORLD] records written so far per (parity, owner); local
+    u32 *cursor;                          // [ROUTE_DEPTH][ROUTE_MAX_WORLD] records written so far per (parity, owner); local
+    u64 seq;                              // sequence number of the chunk among the routed chunks (same on every rank)
+    u64 timeout_ns;                       // a peer silent for this long raises ERR_ROUTE_TIMEOUT instead of hanging
 };
+
+__device__ __forceinline__ u64 global_ns() { u64 t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
+// S3D_TRACE=1 (development): first-block-in / last-block-out GPU timestamps of the pipeline kernels
+// of each chunk, slot[0] = earliest start, slot[1] = latest end (ns, %globaltimer)
+__device__ __forceinline__ void trace_begin(u64 *slot) { if (slot && threadIdx.x == 0) atomicMin(slot, global_ns()); }
+__device__ __forceinline__ void trace_end(u64 *slot) { if (slot && threadIdx.x == 0) atomicMax(slot + 1, global_ns()); }
+
+// spin until *w >= want (a word a peer writes into this rank's exchange block)
+__device__ __forceinline__ void route_wait_word(const u64 *word, u64 want, u64 timeout_ns, MapCtr *mc)
+{
+    const volatile u64 *w = word;
+    const u64 t0 = global_ns();
+    while (*w < want) {
+        if (global_ns() - t0 > timeout_ns) { atomicOr(&mc->err, ERR_ROUTE_TIMEOUT); break; }
+        __nanosleep(100);
+    }
+}
+
+// publish to every peer how many records it got from this rank for the chunk, then the chunk's
+// sequence number + 1 (threads o < world of one block; all record stores are fenced before)
+__device__ __forceinline__ void route_signal(const RouteCtx &rt)
+{
+    const u32 o = threadIdx.x;
+    if (o >= rt.world || o == rt.rank) return;
+    u32 *cur = &rt.cursor[rt.parity * ROUTE_MAX_WORLD + o];
+    const u64 cnt = min((u64)atomicAdd(cur, 0u), rt.cap);
+    *cur = 0;                                              // this parity's next use is ROUTE_DEPTH chunks away, on this stream
+    RouteHdr *h = reinterpret_cast<RouteHdr *>(rt.peer[o]);
+    __threadfence_system();
+    *(volatile u64 *)&h->flag_count[rt.parity][rt.rank] = cnt;
+    __threadfence_system();
+    *(volatile u64 *)&h->flag_seq[rt.parity][rt.rank] = rt.seq + 1;
+}
 
 __device__ __forceinline__ RouteRec *route_inbox(const RouteCtx &rt, u32 owner, u32 parity, u32 source)
 {
@@ -227,6 +265,7 @@ struct ExpandArgs {
     u32 own_rank, own_world;     // own_world > 1: keep only the voxels this rank owns (replicated expansion)
     RouteCtx rt;                 // rt.world > 1: voxels of other owners are routed to them (routed map)
     u64 seq;                     // chunk sequence number (for abort bookkeeping)
+    u64 *trace;                  // S3D_TRACE: {start, end} of this launch, or null
 };
 
 __device__ __forceinline__ void raise_abort(MapCtr *mc, u32 why, u64 seq)
@@ -414,6 +453,23 @@ __device__ __forceinline__ void flush_combiner(const ExpandArgs &a, u32 *tkey, u
     __syncthreads();
 }
 
+// Routed map: the last block of the grid to get here tells the peers that their records of this
+// chunk are complete.  Block-wide; every block calls it exactly once.
+__device__ __forceinline__ void expand_finish(const ExpandArgs &a)
+{
+    trace_end(a.trace);
+    if (a.rt.world <= 1) return;
+    __shared__ bool s_last;
+    __threadfence_system();                     // this thread's record stores, before the ticket
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&a.cc->xticket, 1u) == gridDim.x * gridDim.y - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    route_signal(a.rt);
+    if (threadIdx.x == 0) a.cc->xticket = 0;
+}
+
 __host__ __device__ inline size_t expand_smem_bytes(int H, int free_step, int occ_window)
 {
     const int max_f = (H + free_step - 1) / free_step;
@@ -444,6 +500,7 @@ k_expand(ExpandArgs a)
     const int g = blockIdx.y;
     const uint8_t *img = a.imgs + (size_t)g * a.img_stride;
     if (tid == 0) { s_abort = __ldcg(&a.mc->abort); s_count = 0; }
+    trace_begin(a.trace);
     if (tid < 12) s_T[tid] = a.T[g * 16 + tid];
     if (tid == 32) {
         // voxel of the sonar origin (the combiner's key origin), and whether every sample of this
@@ -466,7 +523,10 @@ k_expand(ExpandArgs a)
         reinterpret_cast<uint4 *>(tcnt)[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
-    if (s_abort) return;                // a chunk must be retried first: stay side-effect free (block-uniform)
+    if (s_abort) {                      // a chunk must be retried first: stay side-effect free (block-uniform)
+        expand_finish(a);
+        return;
+    }
 
     // ---- per warp: first hit and fan list of its beam
     Fan *fans = fans_all + (size_t)warp * (nf_max + 1);
@@ -658,6 +718,7 @@ k_expand(ExpandArgs a)
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
     if (lane == 0 && emitted) atomicAdd(&a.stats[g].n_samples, (u64)emitted);
+    expand_finish(a);
 }
 
 // The gate, one thread, on the apply stream between k_expand and k_apply_chunk of a chunk (the
@@ -800,9 +861,10 @@ template <typename CT> __host__ __device__ constexpr size_t apply_smem_bytes()
 template <typename CT>
 __global__ void __launch_bounds__(AP_THREADS)
 k_apply_chunk(u64 *__restrict__ skeys, CT *__restrict__ scnt, u32 n_slots, int g, ChunkCtr *cc, DevStats *st,
-              Slot *table, u64 tmask, DevParams p, const double *__restrict__ sum_tab, MapCtr *mc)
+              Slot *table, u64 tmask, DevParams p, const double *__restrict__ sum_tab, MapCtr *mc, u64 *trace)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
+    trace_begin(trace);
     CT *s_lane = reinterpret_cast<CT *>(s_dyn);
     double *s_L = reinterpret_cast<double *>(s_lane + AP_Q * AP_ROW);
     u64 *s_slot = reinterpret_cast<u64 *>(s_L + AP_Q);
@@ -947,6 +1009,7 @@ k_apply_chunk(u64 *__restrict__ skeys, CT *__restrict__ scnt, u32 n_slots, int g
     }
     // last block out: len(voxels) after each frame (:592), publish the new count, re-arm the chunk
     __syncthreads();
+    trace_end(trace);
     if (tid == 0) {
         __threadfence();
         const u32 t = atomicAdd(&cc->ticket, 1u);
@@ -1048,70 +1111,74 @@ __global__ void k_shard_merge(const u64 *__restrict__ recv, u64 n_rec, u64 *skey
 }
 
 // ---- routed map: signalling and the owner-side merge
-__device__ __forceinline__ u64 global_ns() { u64 t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-
-// after k_expand of a chunk: tell every peer how many records it got and that they are complete
-__global__ void k_route_signal(RouteCtx rt, u64 seq_plus_1)
+// One small block: thread s waits until word[s] >= want (skipping this rank).  Kept out of the
+// big kernels on purpose: blocks that spin while holding registers and shared memory could keep
+// the very kernel they wait for (a peer's merge, behind that peer's own spinning blocks) off the SMs.
+__global__ void k_route_wait(const u64 *words, u32 world, u32 rank, u64 want, u64 timeout_ns, MapCtr *mc, u64 *trace)
 {
-    const u32 o = threadIdx.x;
-    if (o >= rt.world || o == rt.rank) return;
-    u32 *cur = &rt.cursor[rt.parity * ROUTE_MAX_WORLD + o];
-    const u64 cnt = min((u64)*cur, rt.cap);
-    *cur = 0;                                              // this parity's next use is two chunks away, on this stream
-    RouteHdr *h = reinterpret_cast<RouteHdr *>(rt.peer[o]);
-    __threadfence_system();                                // the records (written by the kernel before this one) first
-    *(volatile u64 *)&h->flag_count[rt.parity][rt.rank] = cnt;
-    __threadfence_system();
-    *(volatile u64 *)&h->flag_seq[rt.parity][rt.rank] = seq_plus_1;
-}
-
-// one warp: lane s waits until word[s] >= want (skipping this rank); a peer that stays silent for
-// `timeout_ns` raises ERR_ROUTE_TIMEOUT instead of hanging the GPU
-__global__ void k_route_wait(const u64 *words, u32 world, u32 rank, u64 want, u64 timeout_ns, MapCtr *mc)
-{
+    trace_begin(trace);
     const u32 s = threadIdx.x;
-    if (s >= world || s == rank) return;
-    const volatile u64 *w = words + s;
-    const u64 t0 = global_ns();
-    while (*w < want) {
-        if (global_ns() - t0 > timeout_ns) { atomicOr(&mc->err, ERR_ROUTE_TIMEOUT); break; }
-        __nanosleep(200);
-    }
+    if (s < world && s != rank) route_wait_word(words + s, want, timeout_ns, mc);
     __threadfence_system();
+    __syncthreads();
+    trace_end(trace);
 }
 
-// owner side: records of all sources -> this rank's dedupe table of the chunk
+// a rank whose beam slice is empty still has to tell its peers that nothing is coming
+__global__ void k_route_signal(RouteCtx rt) { route_signal(rt); }
+
+// Owner side, one kernel: wait until every source has published the chunk, merge the records
+// into this rank's dedupe table of the chunk; the last block out acknowledges to the sources
+// (they may reuse the parity) and runs the gate (the chunk may be applied only if the voxel
+// table keeps its load bound even when every voxel of the chunk is new).
 template <typename CT, bool CHECK>
-__global__ void k_route_merge(RouteCtx rt, u64 *skeys, CT *scnt, u32 smask, ChunkCtr *cc, MapCtr *mc, u64 seq)
+__global__ void k_route_merge(RouteCtx rt, u64 *skeys, CT *scnt, u32 smask, ChunkCtr *cc, MapCtr *mc, u64 seq, u64 table_limit,
+                              u64 *trace)
 {
-    if (__ldcg(&mc->abort)) return;
+    __shared__ bool s_last;
+    trace_begin(trace);
     const RouteHdr *h = reinterpret_cast<const RouteHdr *>(rt.peer[rt.rank]);
     u32 made = 0;
-    for (u32 src = 0; src < rt.world; ++src) {
-        if (src == rt.rank) continue;
-        const u64 n = *(const volatile u64 *)&h->flag_count[rt.parity][src];
-        const RouteRec *in = route_inbox(rt, rt.rank, rt.parity, src);
-        for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-            const ulonglong2 raw = __ldcv(reinterpret_cast<const ulonglong2 *>(in + i));   // written by a peer: do not cache
-            const u64 key = raw.x;
-            const u32 counts = (u32)raw.y, frame = (u32)(raw.y >> 32);
-            const u32 home = dedupe_home(key, smask);
-            made += dedupe_add<CT, CHECK>(skeys, scnt, smask, mc, seq, key, home, load_bucket(skeys, home), (int)(frame & (GF - 1)),
-                                          counts >> 16, counts & 0xffffu);
+    if (!__ldcg(&mc->abort)) {
+        for (u32 src = 0; src < rt.world; ++src) {
+            if (src == rt.rank) continue;
+            const u64 n = *(const volatile u64 *)&h->flag_count[rt.parity][src];
+            const RouteRec *in = route_inbox(rt, rt.rank, rt.parity, src);
+            for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+                const ulonglong2 raw = __ldcv(reinterpret_cast<const ulonglong2 *>(in + i));   // written by a peer: do not cache
+                const u64 key = raw.x;
+                const u32 counts = (u32)raw.y, frame = (u32)(raw.y >> 32);
+                const u32 home = dedupe_home(key, smask);
+                made += dedupe_add<CT, CHECK>(skeys, scnt, smask, mc, seq, key, home, load_bucket(skeys, home),
+                                              (int)(frame & (GF - 1)), counts >> 16, counts & 0xffffu);
+            }
         }
     }
     made = __reduce_add_sync(0xffffffffu, made);
     if ((threadIdx.x & 31) == 0 && made) atomicAdd(&cc->n_unique, made);
-}
-
-// after the merge: the sources may reuse this parity
-__global__ void k_route_ack(RouteCtx rt, u64 seq_plus_1)
-{
-    const u32 s = threadIdx.x;
-    if (s >= rt.world || s == rt.rank) return;
-    RouteHdr *h = reinterpret_cast<RouteHdr *>(rt.peer[s]);
-    __threadfence_system();
-    *(volatile u64 *)&h->ack_seq[rt.parity][rt.rank] = seq_plus_1;
+    __syncthreads();
+    trace_end(trace);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&cc->xticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < rt.world && threadIdx.x != rt.rank) {
+        RouteHdr *ph = reinterpret_cast<RouteHdr *>(rt.peer[threadIdx.x]);
+        __threadfence_system();
+        *(volatile u64 *)&ph->ack_seq[rt.parity][rt.rank] = rt.seq + 1;
+    }
+    if (threadIdx.x == 0) {
+        cc->xticket = 0;
+        if (!atomicAdd(&mc->abort, 0u)) {
+            const u64 cnt = mc->count;
+            cc->count0 = cnt;
+            cc->ticket = 0;
+            if (cnt + atomicAdd(&cc->n_unique, 0u) > table_limit) raise_abort(mc, ABORT_TABLE, seq);
+        }
+    }
 }
 
 __global__ void k_shard_count0(ChunkCtr *cc, const MapCtr *mc) { cc->count0 = mc->count; }
@@ -1132,7 +1199,7 @@ __global__ void k_clear_abort(MapCtr *mc, ChunkCtr *cc)
 {
     mc->abort = 0; mc->abort_seq = ~0ull;
     for (int b = 0; b < N_CHUNK_BUF; ++b) {
-        cc[b].count0 = 0; cc[b].n_unique = 0; cc[b].ticket = 0;
+        cc[b].count0 = 0; cc[b].n_unique = 0; cc[b].ticket = 0; cc[b].xticket = 0;
         for (int f = 0; f < GF; ++f) cc[b].neu[f] = 0;
     }
 }
@@ -1344,6 +1411,8 @@ struct s3d_map {
     DevBuf<unsigned char *> d_peers; DevBuf<u32> route_cursor;
     u64 route_seq = 0;               // chunks routed so far (the same on every rank)
     u64 route_timeout_ns = 5000000000ull;
+    // S3D_TRACE: per chunk 5 x {start, end}: ack wait, expand, flag wait, merge, apply
+    DevBuf<u64> trace; static constexpr u64 TRACE_CHUNKS = 4096; static constexpr int TRACE_W = 10;
     DevBuf<u64> send_buf; DevBuf<u32> owner_ctr;      // owner_ctr: [3][64] count / base / fill
     u32 *owner_host = nullptr;                        // pinned [64]
     int l2_policy = 0;               // S3D_L2_POLICY: 0 = no window, 1 = persisting + streaming misses, 2 = persisting + normal
@@ -1371,6 +1440,7 @@ struct s3d_map {
     ChunkBuf buf[NBUF];
     cudaStream_t xstream = nullptr, xstream2 = nullptr;  // expand streams (chunks alternate)
     cudaEvent_t x_ev = nullptr;      // orders work queued on xstream before xstream2
+    cudaStream_t snap_stream = nullptr;  // per-chunk counter snapshots (device -> pinned host)
     size_t l2_persist_max = 0, l2_window_max = 0, l2_window = 0;
     DevBuf<double> sum_tab;          // [4][SUMT] running sums of n copies of lo_free / lo_occ, and their means
     ChunkCtr *cc = nullptr;
@@ -1405,7 +1475,7 @@ int preload_pipeline_kernels()
     int rc;
     if ((rc = preload(k_expand<u32, false>)) || (rc = preload(k_expand<u32, true>)) || (rc = preload(k_expand<u64, false>)) ||
         (rc = preload(k_apply_chunk<u32>)) || (rc = preload(k_apply_chunk<u64>)) || (rc = preload(k_gate)) ||
-        (rc = preload(k_route_signal)) || (rc = preload(k_route_wait)) || (rc = preload(k_route_ack)) ||
+        (rc = preload(k_route_signal)) || (rc = preload(k_route_wait)) ||
         (rc = preload(k_route_merge<u32, true>)) || (rc = preload(k_route_merge<u64, false>)) ||
         (rc = preload(k_fill_slots)) || (rc = preload(k_fill_u64)) || (rc = preload(k_rehash)) || (rc = preload(k_clear_abort)))
         return rc;
@@ -1600,6 +1670,12 @@ void launch_expand(s3d_map *m, const ExpandArgs &a, int n_beams, int g, cudaStre
     m->launches += 1;
 }
 
+u64 *trace_slot(s3d_map *m, int which)
+{
+    if (!m->trace.p || m->chunk_seq >= s3d_map::TRACE_CHUNKS) return nullptr;
+    return m->trace.p + m->chunk_seq * s3d_map::TRACE_W + 2 * which;
+}
+
 void launch_apply(s3d_map *m, u64 *skeys, void *scnt, int g, ChunkCtr *cc, DevStats *st, cudaStream_t stream)
 {
     // as many blocks as stay resident, every block with the same number of tiles
@@ -1607,10 +1683,10 @@ void launch_apply(s3d_map *m, u64 *skeys, void *scnt, int g, ChunkCtr *cc, DevSt
     const int blocks = (int)(tiles / ((tiles + resident - 1) / resident));
     if (m->wide)
         k_apply_chunk<u64><<<blocks, AP_THREADS, apply_smem_bytes<u64>(), stream>>>(skeys, static_cast<u64 *>(scnt), (u32)m->scratch_cap, g, cc, st,
-                                                             m->table, m->cap - 1, m->p, m->sum_tab.p, m->mc);
+                                                             m->table, m->cap - 1, m->p, m->sum_tab.p, m->mc, trace_slot(m, 4));
     else
         k_apply_chunk<u32><<<blocks, AP_THREADS, apply_smem_bytes<u32>(), stream>>>(skeys, static_cast<u32 *>(scnt), (u32)m->scratch_cap, g, cc, st,
-                                                             m->table, m->cap - 1, m->p, m->sum_tab.p, m->mc);
+                                                             m->table, m->cap - 1, m->p, m->sum_tab.p, m->mc, trace_slot(m, 4));
     m->launches += 1;
 }
 
@@ -1632,45 +1708,51 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     a.skeys = cb.skeys; a.scnt = cb.scnt; a.smask = (u32)(m->scratch_cap - 1);
     a.cc = cb.cc; a.stats = j.stats + base; a.mc = m->mc;
     a.seq = m->chunk_seq;
+    a.trace = trace_slot(m, 1);
     a.beam_lo = 0; a.beam_hi = tab.n_beams;
     a.own_rank = (u32)m->shard_rank; a.own_world = m->shard_filter ? (u32)m->shard_world : 1u;
-    a.rt = RouteCtx{1u, 0u, 0u, 0ull, nullptr, nullptr};
+    a.rt = RouteCtx{1u, 0u, 0u, 0ull, nullptr, nullptr, 0ull, 0ull};
     const bool routed = m->route_on && m->shard_world > 1;
     if (routed) {
         // this rank's contiguous slice of the processed beams; voxels of other owners travel to them
         a.beam_lo = (int)((int64_t)tab.n_beams * m->shard_rank / m->shard_world);
         a.beam_hi = (int)((int64_t)tab.n_beams * (m->shard_rank + 1) / m->shard_world);
         a.own_world = 1u;
-        a.rt = RouteCtx{(u32)m->shard_world, (u32)m->shard_rank, (u32)(m->route_seq & 1), m->route_cap, m->d_peers.p, m->route_cursor.p};
-        // the owners must have merged what this rank sent them two chunks ago (same parity)
-        if (m->route_seq >= 2) {
+        a.rt = RouteCtx{(u32)m->shard_world, (u32)m->shard_rank, (u32)(m->route_seq % ROUTE_DEPTH), m->route_cap, m->d_peers.p,
+                        m->route_cursor.p, m->route_seq, m->route_timeout_ns};
+        // the owners must have merged what this rank sent them ROUTE_DEPTH chunks ago (same parity)
+        if (m->route_seq >= (u64)ROUTE_DEPTH) {
             const RouteHdr *h = reinterpret_cast<const RouteHdr *>(m->xblock);
-            k_route_wait<<<1, ROUTE_MAX_WORLD, 0, xs>>>(h->ack_seq[a.rt.parity], a.rt.world, a.rt.rank, m->route_seq - 1,
-                                                       m->route_timeout_ns, m->mc);
+            k_route_wait<<<1, ROUTE_MAX_WORLD, 0, xs>>>(h->ack_seq[a.rt.parity], a.rt.world, a.rt.rank, m->route_seq - ROUTE_DEPTH + 1,
+                                                       m->route_timeout_ns, m->mc, trace_slot(m, 0));
             m->launches += 1;
         }
     }
+    // (routed: the kernel's last block publishes the record counts to the peers)
     if (a.beam_hi > a.beam_lo) launch_expand(m, a, a.beam_hi - a.beam_lo, g, xs);
-    if (routed) { k_route_signal<<<1, ROUTE_MAX_WORLD, 0, xs>>>(a.rt, m->route_seq + 1); m->launches += 1; }
+    else if (routed) { k_route_signal<<<1, ROUTE_MAX_WORLD, 0, xs>>>(a.rt); m->launches += 1; }
     const size_t e2 = m->prof_on ? prof_mark(m, xs) : 0;
     CU(cudaEventRecord(cb.expanded, xs));
     // ---- apply stream: gate, then the chunk's frames in order into the voxel table
     CU(cudaStreamWaitEvent(as, cb.expanded, 0));
     const size_t e3 = m->prof_on ? prof_mark(m, as) : 0;
     if (routed) {
+        // wait for the sources; then merge their records, acknowledge and gate in one kernel
         const RouteHdr *h = reinterpret_cast<const RouteHdr *>(m->xblock);
         k_route_wait<<<1, ROUTE_MAX_WORLD, 0, as>>>(h->flag_seq[a.rt.parity], a.rt.world, a.rt.rank, m->route_seq + 1,
-                                                   m->route_timeout_ns, m->mc);
-        const int mb = m->n_sm * 4;
+                                                   m->route_timeout_ns, m->mc, trace_slot(m, 2));
+        m->launches += 2;
+        const int mb = m->n_sm * 2;
         if (m->wide)
-            k_route_merge<u64, false><<<mb, 256, 0, as>>>(a.rt, cb.skeys, static_cast<u64 *>(cb.scnt), a.smask, cb.cc, m->mc, m->chunk_seq);
+            k_route_merge<u64, false><<<mb, 256, 0, as>>>(a.rt, cb.skeys, static_cast<u64 *>(cb.scnt), a.smask, cb.cc, m->mc,
+                                                         m->chunk_seq, table_limit(m), trace_slot(m, 3));
         else
-            k_route_merge<u32, true><<<mb, 256, 0, as>>>(a.rt, cb.skeys, static_cast<u32 *>(cb.scnt), a.smask, cb.cc, m->mc, m->chunk_seq);
-        k_route_ack<<<1, ROUTE_MAX_WORLD, 0, as>>>(a.rt, m->route_seq + 1);
-        m->launches += 3;
+            k_route_merge<u32, true><<<mb, 256, 0, as>>>(a.rt, cb.skeys, static_cast<u32 *>(cb.scnt), a.smask, cb.cc, m->mc,
+                                                        m->chunk_seq, table_limit(m), trace_slot(m, 3));
         ++m->route_seq;
+    } else {
+        k_gate<<<1, 1, 0, as>>>(cb.cc, m->mc, table_limit(m), m->chunk_seq);
     }
-    k_gate<<<1, 1, 0, as>>>(cb.cc, m->mc, table_limit(m), m->chunk_seq);
     launch_apply(m, cb.skeys, cb.scnt, g, cb.cc, j.stats + base, as);
     CU(cudaGetLastError());
     CU(cudaEventRecord(cb.freed, as));
@@ -1683,9 +1765,12 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
         m->prof.launches[S3D_K_EXPAND] += 1; m->prof.launches[S3D_K_APPLY] += 1;
         m->prof.frames += (u64)g;
     }
+    // counter snapshot for the host (growth estimates, retry flags): copied on its own stream so
+    // that the copy engine's latency is not between this chunk's apply and the next chunk's kernels
     const int ri = (int)(m->chunk_seq % s3d_map::RING);
-    CU(cudaMemcpyAsync(&m->snap_host[ri], m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, as));
-    CU(cudaEventRecord(m->snap_ev[ri], as));
+    CU(cudaStreamWaitEvent(m->snap_stream, cb.freed, 0));
+    CU(cudaMemcpyAsync(&m->snap_host[ri], m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, m->snap_stream));
+    CU(cudaEventRecord(m->snap_ev[ri], m->snap_stream));
     m->inflight[ri] = InFlight{m->chunk_seq, j.id, base, g};
     ++m->chunk_seq;
     m->ex_valid = false;
@@ -1736,9 +1821,12 @@ int recover(s3d_map *m)
 // until everything is applied (re-running chunks that asked for a retry).
 int pump(s3d_map *m, bool drain)
 {
-    constexpr int LOOKAHEAD = 2;          // chunks allowed in flight behind the one being enqueued
+    // chunks the host may queue behind the one being enqueued.  Deeper than the chunk buffers on
+    // purpose: buffer reuse is ordered on the device (events), so the host's wait for an old
+    // snapshot -- and its launch latency -- stay off the GPU's critical path.
+    constexpr int LOOKAHEAD = 5;
     static_assert(LOOKAHEAD + 2 <= s3d_map::RING, "snapshot ring too small");
-    static_assert(LOOKAHEAD + 2 <= s3d_map::NBUF, "a chunk buffer per chunk in flight");
+    static_assert(ROUTE_DEPTH % 2 == 0 && N_CHUNK_BUF % 2 == 0, "a region / buffer is always reused on the same expand stream");
     for (;;) {
         Job *job = nullptr;
         for (Job &j : m->jobs) if (j.next < j.n) { job = &j; break; }
@@ -1883,8 +1971,15 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
     CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&m->xstream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&m->xstream2, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&m->snap_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&m->x_ev, cudaEventDisableTiming));
     { const char *e = getenv("S3D_WIDE_LANES"); m->wide = e && atoi(e) != 0; }
+    if (const char *e = getenv("S3D_TRACE")) if (atoi(e) != 0) {
+        if (m->trace.ensure(s3d_map::TRACE_CHUNKS * s3d_map::TRACE_W)) return S3D_ENOMEM;
+        std::vector<u64> init(s3d_map::TRACE_CHUNKS * s3d_map::TRACE_W);
+        for (size_t i = 0; i < init.size(); ++i) init[i] = (i & 1) ? 0ull : ~0ull;
+        CU(cudaMemcpy(m->trace.p, init.data(), init.size() * sizeof(u64), cudaMemcpyHostToDevice));
+    }
     CU(cudaMalloc(&m->cc, sizeof(ChunkCtr) * s3d_map::NBUF));
     CU(cudaMemsetAsync(m->cc, 0, sizeof(ChunkCtr) * s3d_map::NBUF, m->stream));
     for (int b = 0; b < s3d_map::NBUF; ++b) {
@@ -1920,11 +2015,12 @@ int s3d_destroy(s3d_map *m)
     if (m->xstream) { cudaStreamSynchronize(m->xstream); cudaStreamDestroy(m->xstream); }
     if (m->xstream2) { cudaStreamSynchronize(m->xstream2); cudaStreamDestroy(m->xstream2); }
     if (m->x_ev) cudaEventDestroy(m->x_ev);
+    if (m->snap_stream) { cudaStreamSynchronize(m->snap_stream); cudaStreamDestroy(m->snap_stream); }
     if (m->owner_host) cudaFreeHost(m->owner_host);
     m->send_buf.release(); m->owner_ctr.release();
     for (void *q : m->ipc_opened) cudaIpcCloseMemHandle(q);
     if (m->xblock) cudaFree(m->xblock);
-    m->d_peers.release(); m->route_cursor.release();
+    m->d_peers.release(); m->route_cursor.release(); m->trace.release();
     for (cudaEvent_t e : m->copy_ev) cudaEventDestroy(e);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->ex_counts) cudaFree(m->ex_counts);
@@ -2145,7 +2241,7 @@ int s3d_route_export(s3d_map *m, uint64_t records_per_pair, unsigned char *handl
     if (m->route_on) return fail(S3D_EINVAL, "routing is enabled; disable it before exporting a new exchange block");
     if (m->xblock) { cudaFree(m->xblock); m->xblock = nullptr; }
     m->route_cap = records_per_pair;
-    m->xblock_bytes = sizeof(RouteHdr) + sizeof(RouteRec) * 2 * (size_t)m->shard_world * (size_t)records_per_pair;
+    m->xblock_bytes = sizeof(RouteHdr) + sizeof(RouteRec) * ROUTE_DEPTH * (size_t)m->shard_world * (size_t)records_per_pair;
     cudaError_t e = cudaMalloc(&m->xblock, m->xblock_bytes);
     if (e != cudaSuccess) return fail(S3D_ENOMEM, "exchange block of %zu bytes: %s", m->xblock_bytes, cudaGetErrorString(e));
     CU(cudaMemset(m->xblock, 0, sizeof(RouteHdr)));
@@ -2190,8 +2286,8 @@ int s3d_route_attach(s3d_map *m, const unsigned char *handles, int same_process)
     }
     if ((rc = m->d_peers.ensure((size_t)world))) return rc;
     CU(cudaMemcpy(m->d_peers.p, m->peer_ptr.data(), sizeof(unsigned char *) * (size_t)world, cudaMemcpyHostToDevice));
-    if ((rc = m->route_cursor.ensure(2 * ROUTE_MAX_WORLD))) return rc;
-    CU(cudaMemset(m->route_cursor.p, 0, sizeof(u32) * 2 * ROUTE_MAX_WORLD));
+    if ((rc = m->route_cursor.ensure(ROUTE_DEPTH * ROUTE_MAX_WORLD))) return rc;
+    CU(cudaMemset(m->route_cursor.p, 0, sizeof(u32) * ROUTE_DEPTH * ROUTE_MAX_WORLD));
     { const char *e = getenv("S3D_ROUTE_TIMEOUT_MS"); if (e && atof(e) > 0) m->route_timeout_ns = (u64)(atof(e) * 1e6); }
     return 0;
 }
@@ -2247,9 +2343,10 @@ int s3d_shard_expand(s3d_map *m, const uint8_t *images_dev, const double *T_dev,
             a.skeys = m->skeys; a.scnt = m->scnt; a.smask = (u32)(m->scratch_cap - 1);
             a.cc = m->cc; a.stats = st; a.mc = m->mc;
             a.seq = m->chunk_seq;                                // the owner gates growth, not the expander
+            a.trace = nullptr;
             a.beam_lo = lo; a.beam_hi = hi;
             a.own_rank = 0; a.own_world = 1;
-            a.rt = RouteCtx{1u, 0u, 0u, 0ull, nullptr, nullptr};
+            a.rt = RouteCtx{1u, 0u, 0u, 0ull, nullptr, nullptr, 0ull, 0ull};
             launch_expand(m, a, hi - lo, g, m->stream);
         }
         // counts per owner -> host (the all-to-all needs the split sizes), and the retry flag
@@ -2528,6 +2625,19 @@ int s3d_export_read_xyzi32(s3d_map *m, float *xyzi, uint64_t n)
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(xyzi, m->ex_f32.p, sizeof(float4) * n, cudaMemcpyDeviceToHost, m->stream));
     CU(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int s3d_trace_read(s3d_map *m, uint64_t *out, uint64_t max_chunks, uint64_t *n_chunks)
+{
+    if (!m || !out || !n_chunks) return fail(S3D_EINVAL, "null argument");
+    *n_chunks = 0;
+    if (!m->trace.p) return 0;
+    int rc = set_device(m); if (rc) return rc;
+    if ((rc = sync_counters(m))) return rc;
+    const u64 n = std::min<u64>({max_chunks, m->chunk_seq, s3d_map::TRACE_CHUNKS});
+    CU(cudaMemcpy(out, m->trace.p, n * s3d_map::TRACE_W * sizeof(u64), cudaMemcpyDeviceToHost));
+    *n_chunks = n;
     return 0;
 }
 

@@ -191,7 +191,7 @@ class CudaShardBackend:
         self.native.shard_config(rank, world)
         self.world = world
 
-    def set_mode(self, mode: str, exchange=None, inbox_records: int = 1 << 21):
+    def set_mode(self, mode: str, exchange=None, inbox_records: int = 1 << 20):
         self.native.route_enable(False)
         self.native.shard_filter(mode == "replicate" and self.world > 1)
         if mode == "fused" and self.world > 1:
