@@ -95,7 +95,8 @@ struct ChunkCtr {     // working counters of the chunk in flight (chunks are ser
     u64 count0;       // live voxels before the chunk
     u32 n_unique;     // dedupe entries created for the chunk (k_expand, k_shard_merge)
     u32 ticket;       // last-block-out election (k_apply_chunk)
-    u32 xticket;      // last-block-out election of k_expand / k_route_merge (routed map)
+    u32 xticket;      // last-block-out election of k_expand (routed map)
+    u32 mticket;      // last-block-out election of k_route_merge (routed map)
     u32 neu[GF];      // voxels first inserted at frame f of the chunk
 };
 
@@ -721,19 +722,6 @@ k_expand(ExpandArgs a)
     expand_finish(a);
 }
 
-// The gate, one thread, on the apply stream between k_expand and k_apply_chunk of a chunk (the
-// previous chunk's apply has finished there, so `count` is final).  The chunk may be applied only
-// if the table keeps its load bound even when every voxel of the chunk is new; otherwise the
-// host grows the table and re-runs the chunk.
-__global__ void k_gate(ChunkCtr *cc, MapCtr *mc, u64 table_limit, u64 seq)
-{
-    if (mc->abort) return;
-    const u64 cnt = mc->count;
-    cc->count0 = cnt;
-    cc->ticket = 0;
-    if (cnt + cc->n_unique > table_limit) raise_abort(mc, ABORT_TABLE, seq);
-}
-
 // ------------------------------------------------------------------------------------ K4
 // update_voxel (3d_mapper.py:83-115) on one table slot.
 __device__ __forceinline__ double apply_one(double L, double upd, bool adaptive, const DevParams &p)
@@ -861,10 +849,20 @@ template <typename CT> __host__ __device__ constexpr size_t apply_smem_bytes()
 template <typename CT>
 __global__ void __launch_bounds__(AP_THREADS)
 k_apply_chunk(u64 *__restrict__ skeys, CT *__restrict__ scnt, u32 n_slots, int g, ChunkCtr *cc, DevStats *st,
-              Slot *table, u64 tmask, DevParams p, const double *__restrict__ sum_tab, MapCtr *mc, u64 *trace)
+              Slot *table, u64 tmask, DevParams p, const double *__restrict__ sum_tab, MapCtr *mc, u64 table_limit,
+              u64 seq, u64 *trace)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     trace_begin(trace);
+    // The gate: the chunk may be applied only if the table keeps its load bound even when every
+    // voxel of the chunk is new; otherwise nothing of it touches the table and the host grows the
+    // table and re-runs the chunk.  Every block takes the same decision from the same two numbers
+    // (the previous chunk has finished on this stream, so `count` is final until our last block).
+    const u64 count0 = __ldcg(&mc->count);
+    if (count0 + __ldcg(&cc->n_unique) > table_limit) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && !__ldcg(&mc->abort)) raise_abort(mc, ABORT_TABLE, seq);
+        return;
+    }
     CT *s_lane = reinterpret_cast<CT *>(s_dyn);
     double *s_L = reinterpret_cast<double *>(s_lane + AP_Q * AP_ROW);
     u64 *s_slot = reinterpret_cast<u64 *>(s_L + AP_Q);
@@ -1018,13 +1016,13 @@ k_apply_chunk(u64 *__restrict__ skeys, CT *__restrict__ scnt, u32 n_slots, int g
     __syncthreads();
     if (s_last && tid == 0) {
         __threadfence();
-        u64 run = cc->count0;
+        u64 run = count0;
         for (int f = 0; f < g; ++f) {
             run += atomicAdd(&cc->neu[f], 0u);
             st[f].n_voxels = run;
             cc->neu[f] = 0;
         }
-        mc->last_new = (u32)(run - cc->count0);
+        mc->last_new = (u32)(run - count0);
         mc->last_unique = atomicAdd(&cc->n_unique, 0u);
         atomicExch(&mc->count, run);
         cc->n_unique = 0; cc->ticket = 0;
@@ -1127,13 +1125,12 @@ __global__ void k_route_wait(const u64 *words, u32 world, u32 rank, u64 want, u6
 // a rank whose beam slice is empty still has to tell its peers that nothing is coming
 __global__ void k_route_signal(RouteCtx rt) { route_signal(rt); }
 
-// Owner side, one kernel: wait until every source has published the chunk, merge the records
-// into this rank's dedupe table of the chunk; the last block out acknowledges to the sources
-// (they may reuse the parity) and runs the gate (the chunk may be applied only if the voxel
-// table keeps its load bound even when every voxel of the chunk is new).
+// Owner side (its own stream: it runs beside this rank's own k_expand of the chunk -- both add into
+// the same dedupe table with atomics -- and beside the apply of the chunk before): merge the
+// records of all sources into this rank's dedupe table of the chunk; the last block out
+// acknowledges to the sources (they may reuse the parity).
 template <typename CT, bool CHECK>
-__global__ void k_route_merge(RouteCtx rt, u64 *skeys, CT *scnt, u32 smask, ChunkCtr *cc, MapCtr *mc, u64 seq, u64 table_limit,
-                              u64 *trace)
+__global__ void k_route_merge(RouteCtx rt, u64 *skeys, CT *scnt, u32 smask, ChunkCtr *cc, MapCtr *mc, u64 seq, u64 *trace)
 {
     __shared__ bool s_last;
     trace_begin(trace);
@@ -1160,7 +1157,7 @@ __global__ void k_route_merge(RouteCtx rt, u64 *skeys, CT *scnt, u32 smask, Chun
     trace_end(trace);
     if (threadIdx.x == 0) {
         __threadfence();
-        s_last = atomicAdd(&cc->xticket, 1u) == gridDim.x - 1;
+        s_last = atomicAdd(&cc->mticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
     if (!s_last) return;
@@ -1170,15 +1167,7 @@ __global__ void k_route_merge(RouteCtx rt, u64 *skeys, CT *scnt, u32 smask, Chun
         __threadfence_system();
         *(volatile u64 *)&ph->ack_seq[rt.parity][rt.rank] = rt.seq + 1;
     }
-    if (threadIdx.x == 0) {
-        cc->xticket = 0;
-        if (!atomicAdd(&mc->abort, 0u)) {
-            const u64 cnt = mc->count;
-            cc->count0 = cnt;
-            cc->ticket = 0;
-            if (cnt + atomicAdd(&cc->n_unique, 0u) > table_limit) raise_abort(mc, ABORT_TABLE, seq);
-        }
-    }
+    if (threadIdx.x == 0) cc->mticket = 0;
 }
 
 __global__ void k_shard_count0(ChunkCtr *cc, const MapCtr *mc) { cc->count0 = mc->count; }
@@ -1199,7 +1188,7 @@ __global__ void k_clear_abort(MapCtr *mc, ChunkCtr *cc)
 {
     mc->abort = 0; mc->abort_seq = ~0ull;
     for (int b = 0; b < N_CHUNK_BUF; ++b) {
-        cc[b].count0 = 0; cc[b].n_unique = 0; cc[b].ticket = 0; cc[b].xticket = 0;
+        cc[b].count0 = 0; cc[b].n_unique = 0; cc[b].ticket = 0; cc[b].xticket = 0; cc[b].mticket = 0;
         for (int f = 0; f < GF; ++f) cc[b].neu[f] = 0;
     }
 }
@@ -1411,6 +1400,7 @@ struct s3d_map {
     DevBuf<unsigned char *> d_peers; DevBuf<u32> route_cursor;
     u64 route_seq = 0;               // chunks routed so far (the same on every rank)
     u64 route_timeout_ns = 5000000000ull;
+    int lookahead_env = 0;           // S3D_LOOKAHEAD (experiments)
     // S3D_TRACE: per chunk 5 x {start, end}: ack wait, expand, flag wait, merge, apply
     DevBuf<u64> trace; static constexpr u64 TRACE_CHUNKS = 4096; static constexpr int TRACE_W = 10;
     DevBuf<u64> send_buf; DevBuf<u32> owner_ctr;      // owner_ctr: [3][64] count / base / fill
@@ -1436,11 +1426,12 @@ struct s3d_map {
     // and k_apply_chunk of chunk c (a chunk alone does not fill the GPU)
     static constexpr int NBUF = N_CHUNK_BUF;
     struct ChunkBuf { u64 *skeys = nullptr; void *scnt = nullptr; ChunkCtr *cc = nullptr;
-                      cudaEvent_t expanded = nullptr, freed = nullptr; bool used = false; };
+                      cudaEvent_t expanded = nullptr, freed = nullptr, merged = nullptr; bool used = false; };
     ChunkBuf buf[NBUF];
     cudaStream_t xstream = nullptr, xstream2 = nullptr;  // expand streams (chunks alternate)
     cudaEvent_t x_ev = nullptr;      // orders work queued on xstream before xstream2
     cudaStream_t snap_stream = nullptr;  // per-chunk counter snapshots (device -> pinned host)
+    cudaStream_t mstream = nullptr;      // routed map: owner-side merges
     size_t l2_persist_max = 0, l2_window_max = 0, l2_window = 0;
     DevBuf<double> sum_tab;          // [4][SUMT] running sums of n copies of lo_free / lo_occ, and their means
     ChunkCtr *cc = nullptr;
@@ -1474,7 +1465,7 @@ int preload_pipeline_kernels()
 {
     int rc;
     if ((rc = preload(k_expand<u32, false>)) || (rc = preload(k_expand<u32, true>)) || (rc = preload(k_expand<u64, false>)) ||
-        (rc = preload(k_apply_chunk<u32>)) || (rc = preload(k_apply_chunk<u64>)) || (rc = preload(k_gate)) ||
+        (rc = preload(k_apply_chunk<u32>)) || (rc = preload(k_apply_chunk<u64>)) ||
         (rc = preload(k_route_signal)) || (rc = preload(k_route_wait)) ||
         (rc = preload(k_route_merge<u32, true>)) || (rc = preload(k_route_merge<u64, false>)) ||
         (rc = preload(k_fill_slots)) || (rc = preload(k_fill_u64)) || (rc = preload(k_rehash)) || (rc = preload(k_clear_abort)))
@@ -1683,10 +1674,12 @@ void launch_apply(s3d_map *m, u64 *skeys, void *scnt, int g, ChunkCtr *cc, DevSt
     const int blocks = (int)(tiles / ((tiles + resident - 1) / resident));
     if (m->wide)
         k_apply_chunk<u64><<<blocks, AP_THREADS, apply_smem_bytes<u64>(), stream>>>(skeys, static_cast<u64 *>(scnt), (u32)m->scratch_cap, g, cc, st,
-                                                             m->table, m->cap - 1, m->p, m->sum_tab.p, m->mc, trace_slot(m, 4));
+                                                             m->table, m->cap - 1, m->p, m->sum_tab.p, m->mc, table_limit(m),
+                                                             m->chunk_seq, trace_slot(m, 4));
     else
         k_apply_chunk<u32><<<blocks, AP_THREADS, apply_smem_bytes<u32>(), stream>>>(skeys, static_cast<u32 *>(scnt), (u32)m->scratch_cap, g, cc, st,
-                                                             m->table, m->cap - 1, m->p, m->sum_tab.p, m->mc, trace_slot(m, 4));
+                                                             m->table, m->cap - 1, m->p, m->sum_tab.p, m->mc, table_limit(m),
+                                                             m->chunk_seq, trace_slot(m, 4));
     m->launches += 1;
 }
 
@@ -1733,31 +1726,32 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     else if (routed) { k_route_signal<<<1, ROUTE_MAX_WORLD, 0, xs>>>(a.rt); m->launches += 1; }
     const size_t e2 = m->prof_on ? prof_mark(m, xs) : 0;
     CU(cudaEventRecord(cb.expanded, xs));
-    // ---- apply stream: gate, then the chunk's frames in order into the voxel table
-    CU(cudaStreamWaitEvent(as, cb.expanded, 0));
-    const size_t e3 = m->prof_on ? prof_mark(m, as) : 0;
     if (routed) {
-        // wait for the sources; then merge their records, acknowledge and gate in one kernel
+        // ---- merge stream: wait for the sources, merge their records (beside our own k_expand), acknowledge
+        cudaStream_t ms = m->mstream;
+        if (cb.used) CU(cudaStreamWaitEvent(ms, cb.freed, 0));
         const RouteHdr *h = reinterpret_cast<const RouteHdr *>(m->xblock);
-        k_route_wait<<<1, ROUTE_MAX_WORLD, 0, as>>>(h->flag_seq[a.rt.parity], a.rt.world, a.rt.rank, m->route_seq + 1,
+        k_route_wait<<<1, ROUTE_MAX_WORLD, 0, ms>>>(h->flag_seq[a.rt.parity], a.rt.world, a.rt.rank, m->route_seq + 1,
                                                    m->route_timeout_ns, m->mc, trace_slot(m, 2));
-        m->launches += 2;
         const int mb = m->n_sm * 2;
         if (m->wide)
-            k_route_merge<u64, false><<<mb, 256, 0, as>>>(a.rt, cb.skeys, static_cast<u64 *>(cb.scnt), a.smask, cb.cc, m->mc,
-                                                         m->chunk_seq, table_limit(m), trace_slot(m, 3));
+            k_route_merge<u64, false><<<mb, 256, 0, ms>>>(a.rt, cb.skeys, static_cast<u64 *>(cb.scnt), a.smask, cb.cc, m->mc,
+                                                         m->chunk_seq, trace_slot(m, 3));
         else
-            k_route_merge<u32, true><<<mb, 256, 0, as>>>(a.rt, cb.skeys, static_cast<u32 *>(cb.scnt), a.smask, cb.cc, m->mc,
-                                                        m->chunk_seq, table_limit(m), trace_slot(m, 3));
+            k_route_merge<u32, true><<<mb, 256, 0, ms>>>(a.rt, cb.skeys, static_cast<u32 *>(cb.scnt), a.smask, cb.cc, m->mc,
+                                                        m->chunk_seq, trace_slot(m, 3));
+        CU(cudaEventRecord(cb.merged, ms));
+        m->launches += 2;
         ++m->route_seq;
-    } else {
-        k_gate<<<1, 1, 0, as>>>(cb.cc, m->mc, table_limit(m), m->chunk_seq);
     }
+    // ---- apply stream: the gate and the chunk's frames, in order, into the voxel table
+    CU(cudaStreamWaitEvent(as, cb.expanded, 0));
+    if (routed) CU(cudaStreamWaitEvent(as, cb.merged, 0));
+    const size_t e3 = m->prof_on ? prof_mark(m, as) : 0;
     launch_apply(m, cb.skeys, cb.scnt, g, cb.cc, j.stats + base, as);
     CU(cudaGetLastError());
     CU(cudaEventRecord(cb.freed, as));
     cb.used = true;
-    m->launches += 1;
     if (m->prof_on) {
         const size_t e4 = prof_mark(m, as);
         m->spans.push_back({e1, e2, S3D_K_EXPAND});
@@ -1784,6 +1778,7 @@ int recover(s3d_map *m)
 {
     CU(cudaStreamSynchronize(m->xstream));          // later chunks may still be expanding
     CU(cudaStreamSynchronize(m->xstream2));
+    CU(cudaStreamSynchronize(m->mstream));
     CU(cudaMemcpyAsync(m->mc_host, m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, m->stream));
     CU(cudaStreamSynchronize(m->stream));
     const MapCtr mc = *m->mc_host;
@@ -1821,11 +1816,12 @@ int recover(s3d_map *m)
 // until everything is applied (re-running chunks that asked for a retry).
 int pump(s3d_map *m, bool drain)
 {
-    // chunks the host may queue behind the one being enqueued.  Deeper than the chunk buffers on
-    // purpose: buffer reuse is ordered on the device (events), so the host's wait for an old
-    // snapshot -- and its launch latency -- stay off the GPU's critical path.
-    constexpr int LOOKAHEAD = 5;
-    static_assert(LOOKAHEAD + 2 <= s3d_map::RING, "snapshot ring too small");
+    // Chunks the host may queue behind the one being enqueued.  A routed map queues deeper than
+    // its chunk buffers (buffer reuse is ordered on the device by events), which keeps the host's
+    // wait for an old snapshot and its launch latency off the critical path of the exchange; a
+    // single map runs best with a short queue (more chunks in flight only fight over L2).
+    const int LOOKAHEAD = m->lookahead_env > 0 ? std::min(m->lookahead_env, s3d_map::RING - 2)
+                                               : (m->route_on && m->shard_world > 1 ? 5 : 2);
     static_assert(ROUTE_DEPTH % 2 == 0 && N_CHUNK_BUF % 2 == 0, "a region / buffer is always reused on the same expand stream");
     for (;;) {
         Job *job = nullptr;
@@ -1972,8 +1968,10 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
     CU(cudaStreamCreateWithFlags(&m->xstream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&m->xstream2, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&m->snap_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&m->mstream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&m->x_ev, cudaEventDisableTiming));
     { const char *e = getenv("S3D_WIDE_LANES"); m->wide = e && atoi(e) != 0; }
+    { const char *e = getenv("S3D_LOOKAHEAD"); if (e) m->lookahead_env = atoi(e); }
     if (const char *e = getenv("S3D_TRACE")) if (atoi(e) != 0) {
         if (m->trace.ensure(s3d_map::TRACE_CHUNKS * s3d_map::TRACE_W)) return S3D_ENOMEM;
         std::vector<u64> init(s3d_map::TRACE_CHUNKS * s3d_map::TRACE_W);
@@ -1986,6 +1984,7 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
         m->buf[b].cc = m->cc + b;
         CU(cudaEventCreateWithFlags(&m->buf[b].expanded, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&m->buf[b].freed, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&m->buf[b].merged, cudaEventDisableTiming));
     }
     CU(cudaMalloc(&m->ex_counts, sizeof(u64) * 4));
     CU(cudaMallocHost(&m->ex_counts_host, sizeof(u64) * 4));
@@ -2011,7 +2010,9 @@ int s3d_destroy(s3d_map *m)
     for (int b = 0; b < s3d_map::NBUF; ++b) {
         if (m->buf[b].expanded) cudaEventDestroy(m->buf[b].expanded);
         if (m->buf[b].freed) cudaEventDestroy(m->buf[b].freed);
+        if (m->buf[b].merged) cudaEventDestroy(m->buf[b].merged);
     }
+    if (m->mstream) { cudaStreamSynchronize(m->mstream); cudaStreamDestroy(m->mstream); }
     if (m->xstream) { cudaStreamSynchronize(m->xstream); cudaStreamDestroy(m->xstream); }
     if (m->xstream2) { cudaStreamSynchronize(m->xstream2); cudaStreamDestroy(m->xstream2); }
     if (m->x_ev) cudaEventDestroy(m->x_ev);
@@ -2139,7 +2140,9 @@ int s3d_set_tables(s3d_map *m, const s3d_tables *t)
     m->half_aperture = t->nv_max > 0 ? std::atan2(t->sin_va[nfan - 1], t->cos_va[nfan - 1]) : 0.0;   // va of v_step = +nv_max
     update_count_bound(m);
     // first guess for the chunk dedupe table; it doubles on demand (retry) from here
-    return ensure_scratch(m, std::min<u64>(1u << 20, std::max<u64>(1u << 14, m->samples_max / 4)), false);
+    // (a rank of a sharded map holds about 1/world of the entries; 1.5x margin, it doubles on demand)
+    const u64 share = m->shard_world > 1 ? (m->samples_max / 4) * 3 / (2 * (u64)m->shard_world) : m->samples_max / 4;
+    return ensure_scratch(m, std::min<u64>(1u << 20, std::max<u64>(1u << 14, share)), false);
 }
 
 int s3d_ingest_batch_dev(s3d_map *m, const uint8_t *images_dev, int64_t n, const double *T_dev,
