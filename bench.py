@@ -380,6 +380,7 @@ def run_sharded(args, rank, world, local_rank, images, pos, quat, cfg, barrier):
     if not args.no_e2e:
         sh2 = ShardedSonarMapper(dict(cfg, table_capacity=cap), group=dist.group.WORLD, mode=args.shard_mode)
         pinned = torch.from_numpy(images).pin_memory().numpy()
+        barrier()                              # page-locking takes a different time on every rank
         for s in range(args.warmup):
             f0 = s * fps_step
             sh2.process_sonar_images(pinned[f0:f0 + fps_step], pos[f0:f0 + fps_step], quat[f0:f0 + fps_step])

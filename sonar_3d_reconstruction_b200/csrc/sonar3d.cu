@@ -263,6 +263,7 @@ struct ExpandArgs {
     DevStats *stats;             // [g]
     MapCtr *mc;
     int beam_lo, beam_hi;        // processed beams [beam_lo, beam_hi) are expanded (a rank's slice when sharded)
+    int bpb;                     // beams per block, 1..EX_WARPS: fewer beams = shorter blocks, more of them
     u32 own_rank, own_world;     // own_world > 1: keep only the voxels this rank owns (replicated expansion)
     RouteCtx rt;                 // rt.world > 1: voxels of other owners are routed to them (routed map)
     u64 seq;                     // chunk sequence number (for abort bookkeeping)
@@ -531,10 +532,10 @@ k_expand(ExpandArgs a)
 
     // ---- per warp: first hit and fan list of its beam
     Fan *fans = fans_all + (size_t)warp * (nf_max + 1);
-    const int beam = a.beam_lo + blockIdx.x * EX_WARPS + warp;
+    const int beam = a.beam_lo + blockIdx.x * a.bpb + warp;
     int total = 0, nfan = 0;
     double cb = 0.0, sb = 0.0;
-    if (beam < a.beam_hi) {
+    if (warp < a.bpb && beam < a.beam_hi) {
         const int col = tab.beam_col[beam];
         cb = tab.cos_b[beam]; sb = tab.sin_b[beam];
         // first above-threshold range bin of this beam (:406-409): 128 rows per step, lanes = rows
@@ -1110,8 +1111,11 @@ __global__ void k_shard_merge(const u64 *__restrict__ recv, u64 n_rec, u64 *skey
 
 // ---- routed map: signalling and the owner-side merge
 // One small block: thread s waits until word[s] >= want (skipping this rank).  Kept out of the
-// big kernels on purpose: blocks that spin while holding registers and shared memory could keep
-// the very kernel they wait for (a peer's merge, behind that peer's own spinning blocks) off the SMs.
+// big kernels on purpose.  Measured on B200: a merge kernel that spins in all of its blocks while
+// it waits for the sources deadlocks the rank -- its blocks sit on every SM, an SM cannot switch to
+// the large shared-memory carve-out k_expand needs while other blocks are resident, so this
+// rank's own k_expand never starts, never signals, and the peers spin for ever too.  One spinning
+// block ties up one SM at most.
 __global__ void k_route_wait(const u64 *words, u32 world, u32 rank, u64 want, u64 timeout_ns, MapCtr *mc, u64 *trace)
 {
     trace_begin(trace);
@@ -1133,22 +1137,33 @@ template <typename CT, bool CHECK>
 __global__ void k_route_merge(RouteCtx rt, u64 *skeys, CT *scnt, u32 smask, ChunkCtr *cc, MapCtr *mc, u64 seq, u64 *trace)
 {
     __shared__ bool s_last;
+    __shared__ u64 s_first[ROUTE_MAX_WORLD + 1];       // exclusive prefix of the sources' record counts
     trace_begin(trace);
     const RouteHdr *h = reinterpret_cast<const RouteHdr *>(rt.peer[rt.rank]);
+    // (every source has published the chunk: k_route_wait ran before this kernel on this stream)
+    __threadfence_system();
+    if (threadIdx.x == 0) {
+        u64 run = 0;
+        for (u32 src = 0; src < rt.world; ++src) {
+            s_first[src] = run;
+            if (src != rt.rank) run += *(const volatile u64 *)&h->flag_count[rt.parity][src];
+        }
+        s_first[rt.world] = run;
+    }
+    __syncthreads();
     u32 made = 0;
     if (!__ldcg(&mc->abort)) {
-        for (u32 src = 0; src < rt.world; ++src) {
-            if (src == rt.rank) continue;
-            const u64 n = *(const volatile u64 *)&h->flag_count[rt.parity][src];
-            const RouteRec *in = route_inbox(rt, rt.rank, rt.parity, src);
-            for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-                const ulonglong2 raw = __ldcv(reinterpret_cast<const ulonglong2 *>(in + i));   // written by a peer: do not cache
-                const u64 key = raw.x;
-                const u32 counts = (u32)raw.y, frame = (u32)(raw.y >> 32);
-                const u32 home = dedupe_home(key, smask);
-                made += dedupe_add<CT, CHECK>(skeys, scnt, smask, mc, seq, key, home, load_bucket(skeys, home),
-                                              (int)(frame & (GF - 1)), counts >> 16, counts & 0xffffu);
-            }
+        const u64 total = s_first[rt.world];
+        for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
+            u32 src = 0;
+            while (s_first[src + 1] <= i) ++src;                     // world <= 64: a short walk
+            const RouteRec *in = route_inbox(rt, rt.rank, rt.parity, src) + (i - s_first[src]);
+            const ulonglong2 raw = __ldcv(reinterpret_cast<const ulonglong2 *>(in));   // written by a peer: do not cache
+            const u64 key = raw.x;
+            const u32 counts = (u32)raw.y, frame = (u32)(raw.y >> 32);
+            const u32 home = dedupe_home(key, smask);
+            made += dedupe_add<CT, CHECK>(skeys, scnt, smask, mc, seq, key, home, load_bucket(skeys, home),
+                                          (int)(frame & (GF - 1)), counts >> 16, counts & 0xffffu);
         }
     }
     made = __reduce_add_sync(0xffffffffu, made);
@@ -1399,8 +1414,9 @@ struct s3d_map {
     std::vector<unsigned char *> peer_ptr; std::vector<void *> ipc_opened;
     DevBuf<unsigned char *> d_peers; DevBuf<u32> route_cursor;
     u64 route_seq = 0;               // chunks routed so far (the same on every rank)
-    u64 route_timeout_ns = 5000000000ull;
+    u64 route_timeout_ns = 30000000000ull;   // S3D_ROUTE_TIMEOUT_MS
     int lookahead_env = 0;           // S3D_LOOKAHEAD (experiments)
+    int bpb_env = 0;                 // S3D_BEAMS_PER_BLOCK (experiments)
     // S3D_TRACE: per chunk 5 x {start, end}: ack wait, expand, flag wait, merge, apply
     DevBuf<u64> trace; static constexpr u64 TRACE_CHUNKS = 4096; static constexpr int TRACE_W = 10;
     DevBuf<u64> send_buf; DevBuf<u32> owner_ctr;      // owner_ctr: [3][64] count / base / fill
@@ -1467,7 +1483,8 @@ int preload_pipeline_kernels()
     if ((rc = preload(k_expand<u32, false>)) || (rc = preload(k_expand<u32, true>)) || (rc = preload(k_expand<u64, false>)) ||
         (rc = preload(k_apply_chunk<u32>)) || (rc = preload(k_apply_chunk<u64>)) ||
         (rc = preload(k_route_signal)) || (rc = preload(k_route_wait)) ||
-        (rc = preload(k_route_merge<u32, true>)) || (rc = preload(k_route_merge<u64, false>)) ||
+        (rc = preload(k_route_merge<u32, true>)) || (rc = preload(k_route_merge<u32, false>)) ||
+        (rc = preload(k_route_merge<u64, false>)) ||
         (rc = preload(k_fill_slots)) || (rc = preload(k_fill_u64)) || (rc = preload(k_rehash)) || (rc = preload(k_clear_abort)))
         return rc;
     return 0;
@@ -1651,10 +1668,14 @@ int ensure_scratch(s3d_map *m, u64 want_cap, bool wipe, bool force_realloc = fal
     return 0;
 }
 
-void launch_expand(s3d_map *m, const ExpandArgs &a, int n_beams, int g, cudaStream_t st)
+void launch_expand(s3d_map *m, ExpandArgs &a, int n_beams, int g, cudaStream_t st)
 {
     const size_t smem = expand_smem_bytes(a.tab.H, a.tab.free_step, a.tab.occ_window);
-    const dim3 grid((n_beams + EX_WARPS - 1) / EX_WARPS, g);
+    // beams per block: all warps of a block share the passes of its beams, so fewer beams per
+    // block means shorter blocks.  A small slice (a rank of a routed map) is cut finer so that
+    // the grid still has a few hundred blocks.
+    a.bpb = m->bpb_env > 0 ? std::min(m->bpb_env, EX_WARPS) : std::max(1, std::min(EX_WARPS, n_beams / 16));
+    const dim3 grid((n_beams + a.bpb - 1) / a.bpb, g);
     if (m->wide) k_expand<u64, false><<<grid, EX_THREADS, smem, st>>>(a);
     else if (m->narrow_safe) k_expand<u32, false><<<grid, EX_THREADS, smem, st>>>(a);
     else k_expand<u32, true><<<grid, EX_THREADS, smem, st>>>(a);
@@ -1727,21 +1748,27 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     const size_t e2 = m->prof_on ? prof_mark(m, xs) : 0;
     CU(cudaEventRecord(cb.expanded, xs));
     if (routed) {
-        // ---- merge stream: wait for the sources, merge their records (beside our own k_expand), acknowledge
+        // ---- merge stream: wait for the sources (one small block), merge their records (beside our own k_expand), acknowledge
         cudaStream_t ms = m->mstream;
         if (cb.used) CU(cudaStreamWaitEvent(ms, cb.freed, 0));
-        const RouteHdr *h = reinterpret_cast<const RouteHdr *>(m->xblock);
-        k_route_wait<<<1, ROUTE_MAX_WORLD, 0, ms>>>(h->flag_seq[a.rt.parity], a.rt.world, a.rt.rank, m->route_seq + 1,
-                                                   m->route_timeout_ns, m->mc, trace_slot(m, 2));
+        {
+            const RouteHdr *h = reinterpret_cast<const RouteHdr *>(m->xblock);
+            k_route_wait<<<1, ROUTE_MAX_WORLD, 0, ms>>>(h->flag_seq[a.rt.parity], a.rt.world, a.rt.rank, m->route_seq + 1,
+                                                       m->route_timeout_ns, m->mc, trace_slot(m, 2));
+            m->launches += 1;
+        }
         const int mb = m->n_sm * 2;
         if (m->wide)
             k_route_merge<u64, false><<<mb, 256, 0, ms>>>(a.rt, cb.skeys, static_cast<u64 *>(cb.scnt), a.smask, cb.cc, m->mc,
+                                                         m->chunk_seq, trace_slot(m, 3));
+        else if (m->narrow_safe)
+            k_route_merge<u32, false><<<mb, 256, 0, ms>>>(a.rt, cb.skeys, static_cast<u32 *>(cb.scnt), a.smask, cb.cc, m->mc,
                                                          m->chunk_seq, trace_slot(m, 3));
         else
             k_route_merge<u32, true><<<mb, 256, 0, ms>>>(a.rt, cb.skeys, static_cast<u32 *>(cb.scnt), a.smask, cb.cc, m->mc,
                                                         m->chunk_seq, trace_slot(m, 3));
         CU(cudaEventRecord(cb.merged, ms));
-        m->launches += 2;
+        m->launches += 1;
         ++m->route_seq;
     }
     // ---- apply stream: the gate and the chunk's frames, in order, into the voxel table
@@ -1972,6 +1999,7 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
     CU(cudaEventCreateWithFlags(&m->x_ev, cudaEventDisableTiming));
     { const char *e = getenv("S3D_WIDE_LANES"); m->wide = e && atoi(e) != 0; }
     { const char *e = getenv("S3D_LOOKAHEAD"); if (e) m->lookahead_env = atoi(e); }
+    { const char *e = getenv("S3D_BEAMS_PER_BLOCK"); if (e) m->bpb_env = atoi(e); }
     if (const char *e = getenv("S3D_TRACE")) if (atoi(e) != 0) {
         if (m->trace.ensure(s3d_map::TRACE_CHUNKS * s3d_map::TRACE_W)) return S3D_ENOMEM;
         std::vector<u64> init(s3d_map::TRACE_CHUNKS * s3d_map::TRACE_W);
