@@ -117,6 +117,11 @@ int s3d_ingest(s3d_map *map, const uint8_t *image, const double T[16], s3d_frame
 int s3d_ingest_batch(s3d_map *map, const uint8_t *images, int64_t n, const double *T,
                      s3d_frame_stats *out);
 
+/* 16-bit frames (ROS encodings mono16 / 16UC1): uint16[n][H][W] host images.  The node converts
+ * them with `(img / 256).astype(uint8)` before it calls the mapper (scripts/3d_mapper_node.py:308-310);
+ * here the raw 16-bit pixels are uploaded and the high byte is taken on the device, then the frames
+ * go through the same path as s3d_ingest_batch. */
+int s3d_ingest_batch_mono16(s3d_map *map, const uint16_t *images, int64_t n, const double *T, s3d_frame_stats *out);
 /* Same with inputs already resident in device memory (bench `value` path; multi-GPU path).
  * Asynchronous on the map's stream when out == NULL; s3d_sync() or any synchronous call
  * orders after it.  `stats_dev`, if not NULL, receives n s3d_frame_stats in device memory. */

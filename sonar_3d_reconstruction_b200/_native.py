@@ -19,7 +19,7 @@ SYMBOLS = (
     "s3d_capacity", "s3d_export_begin", "s3d_export_read", "s3d_export_read_xyzi32",
     "s3d_profile_enable", "s3d_profile_read",
     "s3d_shard_config", "s3d_shard_filter", "s3d_shard_owner", "s3d_shard_expand", "s3d_shard_apply",
-    "s3d_route_export", "s3d_route_attach", "s3d_route_enable", "s3d_trace_read",
+    "s3d_route_export", "s3d_route_attach", "s3d_route_enable", "s3d_trace_read", "s3d_ingest_batch_mono16",
 )
 
 
@@ -106,6 +106,7 @@ def load_library():
     L.s3d_route_export.argtypes = [vp, C.c_uint64, C.c_char_p]
     L.s3d_route_attach.argtypes = [vp, C.c_char_p, C.c_int]
     L.s3d_route_enable.argtypes = [vp, C.c_int]
+    L.s3d_ingest_batch_mono16.argtypes = [vp, C.POINTER(C.c_uint16), C.c_int64, dp, vp]
     L.s3d_trace_read.argtypes = [vp, u64p, C.c_uint64, u64p]
     L.s3d_shard_owner.argtypes = [i32p, C.c_int64, C.c_int, i32p]
     L.s3d_shard_expand.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(vp), u64p]
@@ -184,6 +185,16 @@ class NativeMap:
         T = np.ascontiguousarray(T, dtype=np.float64).reshape(n, 16)
         out = np.zeros(n, dtype=STATS_DTYPE)
         _check(self._lib.s3d_ingest_batch(self._h, images_u8.ctypes.data, n, _ptr(T, C.c_double), out.ctypes.data))
+        return out
+
+    def ingest_batch_mono16(self, images_u16: np.ndarray, T: np.ndarray) -> np.ndarray:
+        """uint16[n, H, W] frames; the device keeps the high byte of every pixel (the node's img / 256)."""
+        n = int(images_u16.shape[0])
+        images_u16 = np.ascontiguousarray(images_u16, dtype=np.uint16)
+        T = np.ascontiguousarray(T, dtype=np.float64).reshape(n, 16)
+        out = np.zeros(n, dtype=STATS_DTYPE)
+        _check(self._lib.s3d_ingest_batch_mono16(self._h, images_u16.ctypes.data_as(C.POINTER(C.c_uint16)), n,
+                                                 _ptr(T, C.c_double), out.ctypes.data))
         return out
 
     def ingest_batch_dev(self, images_ptr: int, n: int, T_ptr: int, want_stats: bool = True,

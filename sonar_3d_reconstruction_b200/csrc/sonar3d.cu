@@ -340,11 +340,11 @@ __device__ __forceinline__ u32 dedupe_add(u64 *skeys, CT *scnt, u32 smask, MapCt
 
 // a sample that does not fit the block combiner (more than 2^9 voxels from the sonar origin, or
 // a transform too large for the fast quantiser) goes to the dedupe table on its own
-template <typename CT, bool CHECK>
+template <typename CT, bool CHECK, bool ROUTE>
 __device__ __noinline__ void commit_direct(u64 *skeys, CT *scnt, u32 smask, ChunkCtr *cc, MapCtr *mc, u64 seq, u64 key,
                                            int g, bool occ, RouteCtx rt)
 {
-    if (rt.world > 1) {
+    if (ROUTE && rt.world > 1) {
         const u32 owner = key_owner(key, rt.world);
         if (owner != rt.rank) { route_send_one(rt, mc, owner, key, occ ? 0x10000u : 1u, (u32)g); return; }
     }
@@ -379,7 +379,7 @@ __device__ __forceinline__ bool key_in_range(int ki, int kj, int kk)
 // Block-wide: move every combiner entry into the chunk dedupe table and leave the combiner
 // empty.  All threads of the block call it after a barrier that follows the last insert;
 // live[0 .. *s_count) lists the slots in use (appended as the entries were created).
-template <typename CT, bool CHECK>
+template <typename CT, bool CHECK, bool ROUTE>
 __device__ __forceinline__ void flush_combiner(const ExpandArgs &a, u32 *tkey, u32 *tcnt, unsigned short *live,
                                                volatile u32 *s_count, const int (&o)[3], int g, u32 &emitted)
 {
@@ -406,7 +406,7 @@ __device__ __forceinline__ void flush_combiner(const ExpandArgs &a, u32 *tkey, u
                 else {
                     key[j] = pack_key(ki, kj, kk);
                     // replicated expansion: every rank computes every sample and keeps the voxels it owns
-                    const u32 owner = a.rt.world > 1 ? key_owner(key[j], a.rt.world) : a.rt.rank;
+                    const u32 owner = (ROUTE && a.rt.world > 1) ? key_owner(key[j], a.rt.world) : a.rt.rank;
                     if (owner != a.rt.rank) {
                         dst[j] = owner; inc[j] = c;
                         emitted += (c >> 16) + (c & 0xffffu);
@@ -429,7 +429,7 @@ __device__ __forceinline__ void flush_combiner(const ExpandArgs &a, u32 *tkey, u
         if (lane == 0 && made) atomicAdd(&a.cc->n_unique, made);
         // routed map: entries of other owners go into their inboxes; lanes with the same owner
         // take consecutive slots from one local atomic, the records are plain peer-memory stores
-        if (a.rt.world > 1) {
+        if (ROUTE && a.rt.world > 1) {
 #pragma unroll
             for (int j = 0; j < FL_ILP; ++j) {
                 const bool send = dst[j] != ~0u;
@@ -457,10 +457,11 @@ __device__ __forceinline__ void flush_combiner(const ExpandArgs &a, u32 *tkey, u
 
 // Routed map: the last block of the grid to get here tells the peers that their records of this
 // chunk are complete.  Block-wide; every block calls it exactly once.
+template <bool ROUTE>
 __device__ __forceinline__ void expand_finish(const ExpandArgs &a)
 {
     trace_end(a.trace);
-    if (a.rt.world <= 1) return;
+    if (!ROUTE || a.rt.world <= 1) return;
     __shared__ bool s_last;
     __threadfence_system();                     // this thread's record stores, before the ticket
     __syncthreads();
@@ -479,8 +480,10 @@ __host__ __device__ inline size_t expand_smem_bytes(int H, int free_step, int oc
            sizeof(Fan) * (size_t)EX_WARPS * (size_t)(max_f + occ_window + 1);
 }
 
-template <typename CT, bool CHECK>
-__global__ void __launch_bounds__(EX_THREADS, 4)
+// ROUTE: compiled with the routed-map code (records of remote owners go to their inboxes); the
+// single-map instantiation does not carry it
+template <typename CT, bool CHECK, bool ROUTE>
+__global__ void __launch_bounds__(EX_THREADS, ROUTE ? 3 : 4)
 k_expand(ExpandArgs a)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -526,7 +529,7 @@ k_expand(ExpandArgs a)
     }
     __syncthreads();
     if (s_abort) {                      // a chunk must be retried first: stay side-effect free (block-uniform)
-        expand_finish(a);
+        expand_finish<ROUTE>(a);
         return;
     }
 
@@ -689,7 +692,7 @@ k_expand(ExpandArgs a)
                     const u64 key = pack_key(ki, kj, kk);
                     if (a.own_world > 1 && key_owner(key, a.own_world) != a.own_rank) continue;
                     ++emitted;
-                    commit_direct<CT, CHECK>(a.skeys, static_cast<CT *>(a.scnt), a.smask, a.cc, a.mc, a.seq, key, g, occ, a.rt);
+                    commit_direct<CT, CHECK, ROUTE>(a.skeys, static_cast<CT *>(a.scnt), a.smask, a.cc, a.mc, a.seq, key, g, occ, a.rt);
                 }
             }
             // combiner slots created by this pass join the live list: one shared-memory atomic per pass
@@ -711,16 +714,16 @@ k_expand(ExpandArgs a)
         const int next = min(rem, EX_ROUND_SAMPLES);
         const int want = (*v_count + (u32)next > (u32)LT_LIMIT) || (since + next > LT_MAX_SAMPLES);
         if (__syncthreads_or(want)) {
-            flush_combiner<CT, CHECK>(a, tkey, tcnt, live, v_count, o, g, emitted);
+            flush_combiner<CT, CHECK, ROUTE>(a, tkey, tcnt, live, v_count, o, g, emitted);
             since = 0;
         }
     }
     __syncthreads();
-    if (*v_count > 0u) flush_combiner<CT, CHECK>(a, tkey, tcnt, live, v_count, o, g, emitted);
+    if (*v_count > 0u) flush_combiner<CT, CHECK, ROUTE>(a, tkey, tcnt, live, v_count, o, g, emitted);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
     if (lane == 0 && emitted) atomicAdd(&a.stats[g].n_samples, (u64)emitted);
-    expand_finish(a);
+    expand_finish<ROUTE>(a);
 }
 
 // ------------------------------------------------------------------------------------ K4
@@ -1335,6 +1338,22 @@ __global__ void k_pack_xyzi32(const double *__restrict__ xyz, const double *__re
     if (i < n) out[i] = make_float4((float)xyz[3 * i], (float)xyz[3 * i + 1], (float)xyz[3 * i + 2], (float)prob[i]);
 }
 
+// 16-bit sonar frames (mono16 / 16UC1): the node's `(img / 256).astype(uint8)`
+// (scripts/3d_mapper_node.py:308-310) folded into the upload -- the high byte of every pixel
+__global__ void k_mono16_to_u8(const uint16_t *__restrict__ in, uint8_t *__restrict__ out, size_t n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n) {
+            const ushort4 v = *reinterpret_cast<const ushort4 *>(in + i);      // i is a multiple of 4: 8-byte aligned
+            *reinterpret_cast<uchar4 *>(out + i) = make_uchar4((unsigned char)(v.x >> 8), (unsigned char)(v.y >> 8),
+                                                               (unsigned char)(v.z >> 8), (unsigned char)(v.w >> 8));
+        } else {
+            for (size_t q = i; q < n; ++q) out[q] = (uint8_t)(in[q] >> 8);
+        }
+    }
+}
+
 __global__ void k_reset_ctr(MapCtr *mc)
 {
     mc->count = 0; mc->err = 0; mc->abort = 0; mc->abort_seq = ~0ull; mc->last_new = 0; mc->last_unique = 0;
@@ -1453,7 +1472,7 @@ struct s3d_map {
     ChunkCtr *cc = nullptr;
     DevBuf<DevStats> stats; DevStats *stats_host = nullptr; size_t stats_host_n = 0;
     // staging
-    DevBuf<uint8_t> img_dev; DevBuf<double> T_dev;
+    DevBuf<uint8_t> img_dev; DevBuf<double> T_dev; DevBuf<uint16_t> img16_dev;
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> copy_ev;
     DevBuf<u64> io_keys; DevBuf<double> io_vals; DevBuf<uint8_t> io_flags;
@@ -1480,7 +1499,8 @@ template <typename F> int preload(F f) { cudaFuncAttributes at; CU(cudaFuncGetAt
 int preload_pipeline_kernels()
 {
     int rc;
-    if ((rc = preload(k_expand<u32, false>)) || (rc = preload(k_expand<u32, true>)) || (rc = preload(k_expand<u64, false>)) ||
+    if ((rc = preload(k_expand<u32, false, true>)) || (rc = preload(k_expand<u32, true, true>)) ||
+        (rc = preload(k_expand<u64, false, true>)) || (rc = preload(k_expand<u32, false, false>)) ||
         (rc = preload(k_apply_chunk<u32>)) || (rc = preload(k_apply_chunk<u64>)) ||
         (rc = preload(k_route_signal)) || (rc = preload(k_route_wait)) ||
         (rc = preload(k_route_merge<u32, true>)) || (rc = preload(k_route_merge<u32, false>)) ||
@@ -1676,9 +1696,15 @@ void launch_expand(s3d_map *m, ExpandArgs &a, int n_beams, int g, cudaStream_t s
     // the grid still has a few hundred blocks.
     a.bpb = m->bpb_env > 0 ? std::min(m->bpb_env, EX_WARPS) : std::max(1, std::min(EX_WARPS, n_beams / 16));
     const dim3 grid((n_beams + a.bpb - 1) / a.bpb, g);
-    if (m->wide) k_expand<u64, false><<<grid, EX_THREADS, smem, st>>>(a);
-    else if (m->narrow_safe) k_expand<u32, false><<<grid, EX_THREADS, smem, st>>>(a);
-    else k_expand<u32, true><<<grid, EX_THREADS, smem, st>>>(a);
+    if (a.rt.world > 1) {
+        if (m->wide) k_expand<u64, false, true><<<grid, EX_THREADS, smem, st>>>(a);
+        else if (m->narrow_safe) k_expand<u32, false, true><<<grid, EX_THREADS, smem, st>>>(a);
+        else k_expand<u32, true, true><<<grid, EX_THREADS, smem, st>>>(a);
+    } else {
+        if (m->wide) k_expand<u64, false, false><<<grid, EX_THREADS, smem, st>>>(a);
+        else if (m->narrow_safe) k_expand<u32, false, false><<<grid, EX_THREADS, smem, st>>>(a);
+        else k_expand<u32, true, false><<<grid, EX_THREADS, smem, st>>>(a);
+    }
     m->launches += 1;
 }
 
@@ -2058,7 +2084,7 @@ int s3d_destroy(s3d_map *m)
     m->d_beam_col.release(); m->d_nv_free.release(); m->d_nv_occ.release();
     m->d_cos_b.release(); m->d_sin_b.release(); m->d_range.release(); m->d_cos_va.release(); m->d_sin_va.release();
     m->d_col_to_beam.release(); m->spool.release(); m->sum_tab.release(); m->stats.release();
-    m->img_dev.release(); m->T_dev.release(); m->io_keys.release(); m->io_vals.release(); m->io_flags.release();
+    m->img_dev.release(); m->T_dev.release(); m->img16_dev.release(); m->io_keys.release(); m->io_vals.release(); m->io_flags.release();
     m->ex_xyz.release(); m->ex_prob.release(); m->ex_L.release(); m->ex_cls.release(); m->ex_ijk.release(); m->ex_f32.release();
     for (cudaEvent_t e : m->ev_pool) cudaEventDestroy(e);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -2157,9 +2183,12 @@ int s3d_set_tables(s3d_map *m, const s3d_tables *t)
     d.nv_free = m->d_nv_free.p; d.nv_occ = m->d_nv_occ.p; d.cos_va = m->d_cos_va.p; d.sin_va = m->d_sin_va.p;
     d.col_to_beam = m->d_col_to_beam.p;
     m->have_tables = true;
-    CU(cudaFuncSetAttribute(k_expand<u32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
-    CU(cudaFuncSetAttribute(k_expand<u32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
-    CU(cudaFuncSetAttribute(k_expand<u64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+    CU(cudaFuncSetAttribute(k_expand<u32, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+    CU(cudaFuncSetAttribute(k_expand<u32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+    CU(cudaFuncSetAttribute(k_expand<u64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+    CU(cudaFuncSetAttribute(k_expand<u32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+    CU(cudaFuncSetAttribute(k_expand<u32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+    CU(cudaFuncSetAttribute(k_expand<u64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
     CU(cudaFuncSetAttribute(k_apply_chunk<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes<u64>()));
     CU(cudaFuncSetAttribute(k_apply_chunk<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes<u32>()));
     m->h_range.assign(t->range_m, t->range_m + H);
@@ -2233,6 +2262,44 @@ int s3d_ingest_batch(s3d_map *m, const uint8_t *images, int64_t n, const double 
             CU(cudaStreamWaitEvent(m->xstream2, m->copy_ev[ei], 0));
             if ((rc = submit_frames(m, m->img_dev.p + (size_t)s0 * img_bytes, kk, m->T_dev.p + s0 * 16, m->stats.p + base + s0))) return rc;
         }
+    }
+    return finish_stats(m, m->stats.p, n, out);
+}
+
+int s3d_ingest_batch_mono16(s3d_map *m, const uint16_t *images, int64_t n, const double *T, s3d_frame_stats *out)
+{
+    int rc = check_ready(m); if (rc) return rc;
+    if (n < 0) return fail(S3D_EINVAL, "n < 0");
+    if (n == 0) return 0;
+    if (!images || !T) return fail(S3D_EINVAL, "null input");
+    if ((rc = set_device(m))) return rc;
+    if ((rc = pump(m, true))) return rc;                  // staging buffers are about to be reused
+    const size_t img_px = (size_t)m->tab.H * m->tab.W;
+    if ((rc = m->stats.ensure((size_t)n))) return rc;
+    // staged in pieces of up to 256 MiB of 16-bit pixels; the conversion runs on the copy stream
+    // right behind its copy, and the frames are submitted behind the conversion
+    const int64_t stage = std::max<int64_t>(GF, std::min<int64_t>(n, (int64_t)((1ull << 27) / std::max<size_t>(1, img_px))));
+    if ((rc = m->img16_dev.ensure(std::max<size_t>(16, img_px * (size_t)stage)))) return rc;
+    if ((rc = m->img_dev.ensure(std::max<size_t>(16, img_px * (size_t)stage)))) return rc;
+    if ((rc = m->T_dev.ensure(16 * (size_t)stage))) return rc;
+    if (m->copy_ev.empty()) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); m->copy_ev.push_back(e); }
+    for (int64_t base = 0; base < n; base += stage) {
+        const int64_t k = std::min<int64_t>(stage, n - base);
+        if (base > 0 && (rc = pump(m, true))) return rc;
+        CU(cudaMemcpyAsync(m->T_dev.p, T + base * 16, sizeof(double) * 16 * (size_t)k, cudaMemcpyHostToDevice, m->copy_stream));
+        if (img_px) {
+            CU(cudaMemcpyAsync(m->img16_dev.p, images + (size_t)base * img_px, sizeof(uint16_t) * img_px * (size_t)k,
+                               cudaMemcpyHostToDevice, m->copy_stream));
+            const size_t px = img_px * (size_t)k;
+            const int blocks = (int)std::min<size_t>((px / 4 + 255) / 256 + 1, (size_t)m->n_sm * 8);
+            k_mono16_to_u8<<<blocks, 256, 0, m->copy_stream>>>(m->img16_dev.p, m->img_dev.p, px);
+            CU(cudaGetLastError());
+            m->launches += 1;
+        }
+        CU(cudaEventRecord(m->copy_ev[0], m->copy_stream));
+        CU(cudaStreamWaitEvent(m->xstream, m->copy_ev[0], 0));
+        CU(cudaStreamWaitEvent(m->xstream2, m->copy_ev[0], 0));
+        if ((rc = submit_frames(m, m->img_dev.p, k, m->T_dev.p, m->stats.p + base))) return rc;
     }
     return finish_stats(m, m->stats.p, n, out);
 }

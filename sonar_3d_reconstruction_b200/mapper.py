@@ -457,20 +457,39 @@ class SonarTo3DMapper:
         T = self.compose_transforms(robot_positions, robot_orientations)
         self._sync_device_config(range_bins, bearing_bins)
         st = self.octree._native.ingest_batch(np.ascontiguousarray(polar_images), T)
-        dt = time.time() - start_time
-        out = []
-        for f in range(n):
-            self.frame_count += 1
-            self.processed_frame_count += 1
-            self.last_processing_time = dt / n
-            self.total_processing_time += dt / n
-            out.append({'frame_count': self.frame_count, 'processed_count': self.processed_frame_count,
-                        'num_occupied': int(st['num_occupied'][f]), 'num_free': int(st['num_free'][f]),
-                        'num_voxels': int(st['num_voxels'][f]), 'processing_time': dt / n,
-                        'avg_processing_time': self.total_processing_time / max(1, self.processed_frame_count)})
+        return self._batch_stats(st, n, time.time() - start_time)
+
+    def _batch_stats(self, st, n: int, dt: float) -> List[Dict[str, Any]]:
+        """The per-frame dicts of process_sonar_image (:587-595) for a batch (time split evenly)."""
+        occ, fre, vox = st['num_occupied'].tolist(), st['num_free'].tolist(), st['num_voxels'].tolist()
+        fc0, pc0, tot0 = self.frame_count, self.processed_frame_count, self.total_processing_time
+        per = dt / n if n else 0.0
+        out = [{'frame_count': fc0 + f + 1, 'processed_count': pc0 + f + 1,
+                'num_occupied': occ[f], 'num_free': fre[f], 'num_voxels': vox[f], 'processing_time': per,
+                'avg_processing_time': (tot0 + per * (f + 1)) / (pc0 + f + 1)} for f in range(n)]
+        self.frame_count = fc0 + n
+        self.processed_frame_count = pc0 + n
+        self.total_processing_time = tot0 + dt
         if n:
+            self.last_processing_time = per
             self.last_num_samples = int(st['num_samples'][-1])
         return out
+
+    def process_sonar_images_mono16(self, polar_images_u16: np.ndarray, robot_positions, robot_orientations
+                                    ) -> List[Dict[str, Any]]:
+        """16-bit frames (ROS mono16 / 16UC1) as the node receives them (extension).  The
+        node's `(img / 256).astype(np.uint8)` (scripts/3d_mapper_node.py:308-310) happens on the device:
+        same result as process_sonar_images((img / 256).astype(np.uint8), ...)."""
+        start_time = time.time()
+        polar_images_u16 = np.asarray(polar_images_u16)
+        if polar_images_u16.dtype != np.uint16 or polar_images_u16.ndim != 3:
+            raise TypeError("process_sonar_images_mono16 expects uint16 images [n, range bins, bearings]")
+        n, range_bins, bearing_bins = polar_images_u16.shape
+        self._check_width(bearing_bins)
+        T = self.compose_transforms(robot_positions, robot_orientations)
+        self._sync_device_config(range_bins, bearing_bins)
+        st = self.octree._native.ingest_batch_mono16(polar_images_u16, T)
+        return self._batch_stats(st, n, time.time() - start_time)
 
     # -- export (:597-642) ------------------------------------------------------------------------
     def get_point_cloud(self, include_free: bool = False) -> Dict[str, Any]:

@@ -254,6 +254,21 @@ def test_samples_far_from_the_sonar_origin(s3d):
     _oracle_parity(s3d, images, pos, quat, cfg, "far samples")
 
 
+def test_mono16_frames_take_the_high_byte_on_the_device(s3d):
+    """16-bit frames: same map as the node's (img / 256).astype(uint8) followed by the 8-bit path."""
+    from sonar_3d_reconstruction_b200 import synthetic
+    spec = dict(H=150, W=130, config=dict(voxel_resolution=0.07, intensity_threshold=45, max_range=8.0), step_m=0.03)
+    images, pos, quat, cfg = synthetic.make_sequence(spec, 19, seed=21)
+    rng = np.random.default_rng(5)
+    img16 = (images.astype(np.uint16) << 8) | rng.integers(0, 256, size=images.shape, dtype=np.uint16)
+    assert np.array_equal((img16 / 256).astype(np.uint8), images)
+    a, b = s3d.SonarTo3DMapper(cfg), s3d.SonarTo3DMapper(cfg)
+    sa = [_stats3(x) for x in a.process_sonar_images(images, pos, quat)]
+    sb = [_stats3(x) for x in b.process_sonar_images_mono16(img16, pos, quat)]
+    assert sa == sb
+    assert_same_map(*a.octree.voxels.to_arrays(), *b.octree.voxels.to_arrays(), 0.0, "mono16 vs 8-bit")
+
+
 @pytest.mark.parametrize("mode", ["replicate", "route"])
 def test_sharded_single_rank_equals_plain(s3d, mode):
     """The sharded code paths (route: expand -> pack by owner -> merge -> apply) with world = 1

@@ -1,8 +1,9 @@
 #!/bin/bash
-# Round-end style measurements on one B200: tests, bench (ours + reference arm), other workloads,
-# ncu launch list and one full capture (warm caches: --cache-control none) for the traffic figure.
+# Round-end style measurements on one B200: tests, smoke, bench (ours + reference arm), the other
+# single-GPU workloads, ncu launch list and one full capture (warm caches: --cache-control none).
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; tail -c 300 gpurun_out/bench_final.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_final.json 2>/dev/null
 for wl in cfg1 cfg3; do
@@ -19,6 +20,6 @@ import json
 for f in ("bench_final","bench_ref_final","bench_cfg1","bench_cfg3"):
     try:
         d=json.loads(open(f"gpurun_out/{f}.json").read().strip().splitlines()[-1])
-        print(f, round(d["value"]), "e2e", round(d["e2e"]["value"]), "upd/s %.3g"%d["voxel_updates_per_s"], "frac", d.get("roofline",{}).get("frac"), d["config"].get("chunk_retries"), d.get("clocks"))
+        print(f, round(d["value"]), "e2e", round(d["e2e"]["value"]), "upd/s %.3g"%d["voxel_updates_per_s"], "frac", d.get("roofline",{}).get("frac"), d["config"].get("chunk_retries"), d.get("clocks"), d.get("gpu_launches"))
     except Exception as e: print(f,"ERR",e)
 PY
