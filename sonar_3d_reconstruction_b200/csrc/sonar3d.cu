@@ -1,15 +1,16 @@
 // sonar3d.cu -- sm_100a kernels + C-ABI (include/sonar3d.h) of the sonar -> voxel hot path.
 //
 // Reference behaviour: luckkim123/sonar_3d_reconstruction scripts/3d_mapper.py
-//   :387-483 process_sonar_ray   -> k_expand (first-hit scan fused in; K1+K2+K3 of SURVEY 2.2)
+//   :387-483 process_sonar_ray   -> k_expand (first-hit scan, expansion, keys, block combiner; K1+K2+K3 of SURVEY 2.2)
 //   :485-567 process_sonar_image -> chunk dedupe table + k_apply_chunk (K3, K4)
 //   :83-115  update_voxel        -> apply_one()
 //   :117-188 queries / export    -> k_query, k_export (K5, K6)
 //
 // Data layout in HBM (DESIGN.md has the full account):
-//   voxel table    Slot[cap]    16 B {packed key, fp64 log-odds}, open addressing, linear probing
-//   chunk dedupe   u64 keys[C] + u64 counters[C][16]: one entry per voxel touched by a chunk of
-//                  up to 16 consecutive frames, one (n_occ<<32 | n_free) counter lane per frame
+//   voxel table    Slot[cap]    16 B {packed key, fp64 log-odds}, open addressing, probed by 32-byte sector
+//   chunk dedupe   u64 keys[C] + lanes[C][16]: one entry per voxel touched by a chunk of up to 16
+//                  consecutive frames, one {n_occ, n_free} counter lane per frame (u32 = 16+16 bits
+//                  normally, u64 = 32+32 bits after an overflow)
 // No tensor cores: the path has no dense contraction; it is integer/fp64 scatter work.
 #include "../../include/sonar3d.h"
 
