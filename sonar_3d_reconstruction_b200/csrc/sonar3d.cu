@@ -483,8 +483,10 @@ __host__ __device__ inline size_t expand_smem_bytes(int H, int free_step, int oc
 
 // ROUTE: compiled with the routed-map code (records of remote owners go to their inboxes); the
 // single-map instantiation does not carry it
+// (3 blocks per SM: measured 7 % faster than 4 blocks at 64 registers -- the extra registers matter
+// more than the extra warps)
 template <typename CT, bool CHECK, bool ROUTE>
-__global__ void __launch_bounds__(EX_THREADS, ROUTE ? 3 : 4)
+__global__ void __launch_bounds__(EX_THREADS, 3)
 k_expand(ExpandArgs a)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -1717,8 +1719,9 @@ u64 *trace_slot(s3d_map *m, int which)
 
 void launch_apply(s3d_map *m, u64 *skeys, void *scnt, int g, ChunkCtr *cc, DevStats *st, cudaStream_t stream)
 {
-    // as many blocks as stay resident, every block with the same number of tiles
-    const u64 tiles = m->scratch_cap / AP_THREADS, resident = (u64)m->n_sm * 4;
+    // two blocks per SM, every block with the same number of tiles (measured: 4 tiles per block at
+    // cfg2 -- denser update steps, and fewer apply warps competing with k_expand -- beats 2 and 1)
+    const u64 tiles = m->scratch_cap / AP_THREADS, resident = (u64)m->n_sm * 2;
     const int blocks = (int)(tiles / ((tiles + resident - 1) / resident));
     if (m->wide)
         k_apply_chunk<u64><<<blocks, AP_THREADS, apply_smem_bytes<u64>(), stream>>>(skeys, static_cast<u64 *>(scnt), (u32)m->scratch_cap, g, cc, st,
@@ -2235,7 +2238,8 @@ int s3d_ingest_batch(s3d_map *m, const uint8_t *images, int64_t n, const double 
     // to be re-run still finds its frames.  Copies go in sub-pieces on a second stream and
     // overlap the kernels of the previous sub-piece.
     const int64_t stage = std::max<int64_t>(GF, std::min<int64_t>(n, (int64_t)((1ull << 30) / std::max<size_t>(1, img_bytes))));
-    const int64_t sub = 2 * GF;
+    // (the first piece is one chunk, so that the first kernel starts after 16 frames' worth of copy)
+    auto piece = [](int64_t s0) -> int64_t { return s0 == 0 ? GF : 2 * GF; };
     if ((rc = m->img_dev.ensure(std::max<size_t>(16, img_bytes * (size_t)stage)))) return rc;
     if ((rc = m->T_dev.ensure(16 * (size_t)stage))) return rc;
     for (int64_t base = 0; base < n; base += stage) {
@@ -2245,8 +2249,8 @@ int s3d_ingest_batch(s3d_map *m, const uint8_t *images, int64_t n, const double 
         // all copies of this stage are queued first (they run back to back on the copy stream),
         // then the frames are submitted piece by piece, each behind the event of its own copy
         size_t ei = 0;
-        for (int64_t s0 = 0; s0 < k; s0 += sub, ++ei) {
-            const int64_t kk = std::min<int64_t>(sub, k - s0);
+        for (int64_t s0 = 0; s0 < k; s0 += piece(s0), ++ei) {
+            const int64_t kk = std::min<int64_t>(piece(s0), k - s0);
             if (ei == m->copy_ev.size()) {
                 cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                 m->copy_ev.push_back(e);
@@ -2257,8 +2261,8 @@ int s3d_ingest_batch(s3d_map *m, const uint8_t *images, int64_t n, const double 
             CU(cudaEventRecord(m->copy_ev[ei], m->copy_stream));
         }
         ei = 0;
-        for (int64_t s0 = 0; s0 < k; s0 += sub, ++ei) {
-            const int64_t kk = std::min<int64_t>(sub, k - s0);
+        for (int64_t s0 = 0; s0 < k; s0 += piece(s0), ++ei) {
+            const int64_t kk = std::min<int64_t>(piece(s0), k - s0);
             CU(cudaStreamWaitEvent(m->xstream, m->copy_ev[ei], 0));
             CU(cudaStreamWaitEvent(m->xstream2, m->copy_ev[ei], 0));
             if ((rc = submit_frames(m, m->img_dev.p + (size_t)s0 * img_bytes, kk, m->T_dev.p + s0 * 16, m->stats.p + base + s0))) return rc;
