@@ -172,6 +172,8 @@ def run_gpu(args, rank, world, local_rank):
     n_total = (args.steps + args.warmup) * fps_step
     images, pos, quat, cfg = make_workload(args.workload, n_total, args.seed, args.distinct_images)
     cfg = dict(cfg, device=local_rank)
+    if args.no_adaptive:
+        cfg["adaptive_update"] = False
     if world > 1:
         return run_sharded(args, rank, world, local_rank, images, pos, quat, cfg, barrier)
 
@@ -466,6 +468,8 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (profiling runs only)")
+    ap.add_argument("--no-adaptive", action="store_true",
+                    help="ablation (BASELINE config 5): adaptive_update off -- every update is applied unscaled")
     ap.add_argument("--shard-mode", default="fused", choices=["fused", "replicate", "route"],
                     help="N > 1: how the sharded map moves data (sonar_3d_reconstruction_b200/sharded.py)")
     args = ap.parse_args()

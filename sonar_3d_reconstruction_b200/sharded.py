@@ -333,17 +333,15 @@ class ShardedSonarMapper:
         return self.ex.all_reduce_sum(stats)
 
     def _finish(self, stats, n: int, t0: float) -> List[Dict[str, Any]]:
-        stats = stats.cpu().numpy()
+        rows = stats.cpu().tolist()
         dt = time.time() - t0
-        out = []
-        for f in range(n):
-            self.frame_count += 1
-            self.processed_frame_count += 1
-            self.total_processing_time += dt / n
-            out.append({'frame_count': self.frame_count, 'processed_count': self.processed_frame_count,
-                        'num_occupied': int(stats[f, 0]), 'num_free': int(stats[f, 1]), 'num_voxels': int(stats[f, 2]),
-                        'num_samples': int(stats[f, 3]), 'processing_time': dt / n,
-                        'avg_processing_time': self.total_processing_time / max(1, self.processed_frame_count)})
+        per = dt / n if n else 0.0
+        fc0, pc0, tot0 = self.frame_count, self.processed_frame_count, self.total_processing_time
+        out = [{'frame_count': fc0 + f + 1, 'processed_count': pc0 + f + 1,
+                'num_occupied': rows[f][0], 'num_free': rows[f][1], 'num_voxels': rows[f][2], 'num_samples': rows[f][3],
+                'processing_time': per, 'avg_processing_time': (tot0 + per * (f + 1)) / (pc0 + f + 1)} for f in range(n)]
+        self.frame_count, self.processed_frame_count = fc0 + n, pc0 + n
+        self.total_processing_time = tot0 + dt
         return out
 
     def process_sonar_image(self, polar_image, robot_position, robot_orientation) -> Dict[str, Any]:

@@ -290,14 +290,16 @@ def test_sharded_single_rank_equals_plain(s3d, mode):
     assert b.num_voxels() == len(ka)
 
 
-def test_routed_map_two_ranks_in_one_process():
+@pytest.mark.parametrize("world", [2, 3])
+def test_routed_map_ranks_in_one_process(world):
     """The fused exchange (records written into the owner's inbox by the expansion kernel,
-    device-side sequence flags, owner-side merge) with two ranks on this one GPU; multi-process
-    runs over CUDA IPC are exercised by tools/sharded_check.py under torchrun."""
+    device-side sequence flags, owner-side merge) with two / three ranks on this one GPU (53 frames:
+    three full chunks and a ragged one); multi-process runs over CUDA IPC are exercised by
+    tools/sharded_check.py under torchrun."""
     import subprocess
     import sys
     root = os.path.dirname(GOLDEN.rstrip("/").rsplit("/", 1)[0])
-    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", S3D_ROUTE_TIMEOUT_MS="20000")
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", S3D_ROUTE_TIMEOUT_MS="20000", S3D_LOCAL_WORLD=str(world))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "route_local_check.py")], env=env,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "route_local_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
