@@ -93,7 +93,6 @@ struct MapCtr {       // device-resident map counters
 };
 
 struct ChunkCtr {     // working counters of the chunk in flight (chunks are serialised on the stream)
-    u64 count0;       // live voxels before the chunk
     u32 n_unique;     // dedupe entries created for the chunk (k_expand, k_shard_merge)
     u32 ticket;       // last-block-out election (k_apply_chunk)
     u32 xticket;      // last-block-out election of k_expand (routed map)
@@ -1191,7 +1190,6 @@ __global__ void k_route_merge(RouteCtx rt, u64 *skeys, CT *scnt, u32 smask, Chun
     if (threadIdx.x == 0) cc->mticket = 0;
 }
 
-__global__ void k_shard_count0(ChunkCtr *cc, const MapCtr *mc) { cc->count0 = mc->count; }
 
 // ------------------------------------------------------------------------------ store kernels
 __global__ void k_fill_slots(Slot *t, u64 n)
@@ -1209,7 +1207,7 @@ __global__ void k_clear_abort(MapCtr *mc, ChunkCtr *cc)
 {
     mc->abort = 0; mc->abort_seq = ~0ull;
     for (int b = 0; b < N_CHUNK_BUF; ++b) {
-        cc[b].count0 = 0; cc[b].n_unique = 0; cc[b].ticket = 0; cc[b].xticket = 0; cc[b].mticket = 0;
+        cc[b].n_unique = 0; cc[b].ticket = 0; cc[b].xticket = 0; cc[b].mticket = 0;
         for (int f = 0; f < GF; ++f) cc[b].neu[f] = 0;
     }
 }
@@ -2531,10 +2529,9 @@ int s3d_shard_apply(s3d_map *m, const void *records_dev, uint64_t n_records, int
         }
         break;
     }
-    k_shard_count0<<<1, 1, 0, m->stream>>>(m->cc, m->mc);
     launch_apply(m, m->skeys, m->scnt, g, m->cc, st, m->stream);
     CU(cudaGetLastError());
-    m->launches += 2;
+    m->launches += 1;
     ++m->chunk_seq; m->snap_floor = m->chunk_seq;
     m->ex_valid = false;
     return sync_counters(m);

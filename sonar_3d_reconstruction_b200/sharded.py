@@ -191,7 +191,7 @@ class CudaShardBackend:
         self.native.shard_config(rank, world)
         self.world = world
 
-    def set_mode(self, mode: str, exchange=None, inbox_records: int = 1 << 20):
+    def set_mode(self, mode: str, exchange=None, inbox_records: int = 1 << 22):
         self.native.route_enable(False)
         self.native.shard_filter(mode == "replicate" and self.world > 1)
         if mode == "fused" and self.world > 1:
@@ -281,7 +281,9 @@ class ShardedSonarMapper:
         else:
             self.mapper, self.backend = backend_factory(config, self.rank, self.world)
         if mode == "fused":
-            self.backend.set_mode(mode, exchange=self.ex)
+            # records per (source, owner, chunk) inbox region; 16 bytes each, 4 regions deep (config key, optional)
+            self.backend.set_mode(mode, exchange=self.ex,
+                                  inbox_records=int((config or {}).get("route_inbox_records", 1 << 22)))
         else:
             self.backend.set_mode(mode)
         self.frame_count = 0
