@@ -104,6 +104,32 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa(gpu_index: int):
+    """Run this process on the CPUs of the NUMA node the GPU hangs off, so that the pinned host
+    frames are allocated next to it (host->device copies from the far socket run at about half the
+    bandwidth).  Returns a short description for the JSON line; any failure leaves the affinity alone."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(gpu_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return f"{bdf}: no NUMA information"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return f"{bdf}: node {node} has no CPU this process may use"
+        os.sched_setaffinity(0, allowed)
+        return f"{bdf}: bound to NUMA node {node} ({len(allowed)} CPUs)"
+    except Exception as e:                                       # not fatal: measure unbound
+        return f"unbound ({type(e).__name__})"
+
+
 def make_workload(name: str, n_frames: int, seed: int, distinct_images: int):
     images, pos, quat, cfg = synthetic.make_sequence(name, n_frames, seed=seed, distinct_images=distinct_images)
     return images, pos, quat, cfg
@@ -158,6 +184,7 @@ def run_gpu(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: sonar_3d_reconstruction_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    args.numa = bind_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -296,7 +323,8 @@ def run_gpu(args, rank, world, local_rank):
                        "parallelism": "1 map per GPU" if world > 1 else "single GPU"},
             "e2e": {"value": frames_all / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": fps_step * (H * W + 128), "d2h_bytes_per_step": fps_step * 32,
-                    "api": "SonarTo3DMapper.process_sonar_images (pinned host images, poses on host)"},
+                    "api": "SonarTo3DMapper.process_sonar_images (pinned host images, poses on host)",
+                    "host": args.numa},
             "gpu_launches": prof["total_launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
@@ -421,7 +449,8 @@ def run_sharded(args, rank, world, local_rank, images, pos, quat, cfg, barrier):
                        "l2": "inputs streamed once: every step reads fresh frames"},
             "e2e": {"value": n_frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": world * fps_step * (H * W + 128),
                     "d2h_bytes_per_step": fps_step * 32,
-                    "api": "ShardedSonarMapper.process_sonar_images (pinned host images on every rank)"},
+                    "api": "ShardedSonarMapper.process_sonar_images (pinned host images on every rank)",
+                    "host": args.numa},
             "gpu_launches": int(launches[0]),
             "roofline": {"bound": "hbm", "achieved": achieved / world, "peak": peak, "unit": "GB/s",
                          "frac": achieved / world / peak, "traffic": None,
