@@ -117,6 +117,13 @@ int s3d_ingest(s3d_map *map, const uint8_t *image, const double T[16], s3d_frame
 int s3d_ingest_batch(s3d_map *map, const uint8_t *images, int64_t n, const double *T,
                      s3d_frame_stats *out);
 
+/* Asynchronous form of s3d_ingest_batch: s3d_ingest_submit queues the copies and kernels of a host
+ * batch and returns at once with a ticket (0 or 1: two batches may be pending, so the upload and the
+ * kernels of one overlap the tail of the one before); s3d_ingest_collect waits for that batch only
+ * and returns its per-frame counters.  `images` and `T` must stay valid and unchanged until the batch
+ * is collected.  Batches are applied in submission order; collect them in that order too. */
+int s3d_ingest_submit(s3d_map *map, const uint8_t *images, int64_t n, const double *T, int *ticket);
+int s3d_ingest_collect(s3d_map *map, int ticket, s3d_frame_stats *out);
 /* 16-bit frames (ROS encodings mono16 / 16UC1): uint16[n][H][W] host images.  The node converts
  * them with `(img / 256).astype(uint8)` before it calls the mapper (scripts/3d_mapper_node.py:308-310);
  * here the raw 16-bit pixels are uploaded and the high byte is taken on the device, then the frames

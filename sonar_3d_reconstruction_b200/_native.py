@@ -20,6 +20,7 @@ SYMBOLS = (
     "s3d_profile_enable", "s3d_profile_read",
     "s3d_shard_config", "s3d_shard_filter", "s3d_shard_owner", "s3d_shard_expand", "s3d_shard_apply",
     "s3d_route_export", "s3d_route_attach", "s3d_route_enable", "s3d_trace_read", "s3d_ingest_batch_mono16",
+    "s3d_ingest_submit", "s3d_ingest_collect",
 )
 
 
@@ -106,6 +107,8 @@ def load_library():
     L.s3d_route_export.argtypes = [vp, C.c_uint64, C.c_char_p]
     L.s3d_route_attach.argtypes = [vp, C.c_char_p, C.c_int]
     L.s3d_route_enable.argtypes = [vp, C.c_int]
+    L.s3d_ingest_submit.argtypes = [vp, vp, C.c_int64, dp, C.POINTER(C.c_int)]
+    L.s3d_ingest_collect.argtypes = [vp, C.c_int, vp]
     L.s3d_ingest_batch_mono16.argtypes = [vp, C.POINTER(C.c_uint16), C.c_int64, dp, vp]
     L.s3d_trace_read.argtypes = [vp, u64p, C.c_uint64, u64p]
     L.s3d_shard_owner.argtypes = [i32p, C.c_int64, C.c_int, i32p]
@@ -185,6 +188,18 @@ class NativeMap:
         T = np.ascontiguousarray(T, dtype=np.float64).reshape(n, 16)
         out = np.zeros(n, dtype=STATS_DTYPE)
         _check(self._lib.s3d_ingest_batch(self._h, images_u8.ctypes.data, n, _ptr(T, C.c_double), out.ctypes.data))
+        return out
+
+    def ingest_submit(self, images_u8: np.ndarray, T: np.ndarray) -> int:
+        """Queue a host batch without waiting; the arrays must stay alive and unchanged until ingest_collect."""
+        n = int(images_u8.shape[0])
+        ticket = C.c_int(-1)
+        _check(self._lib.s3d_ingest_submit(self._h, images_u8.ctypes.data, n, _ptr(T, C.c_double), C.byref(ticket)))
+        return ticket.value
+
+    def ingest_collect(self, ticket: int, n: int) -> np.ndarray:
+        out = np.zeros(n, dtype=STATS_DTYPE)
+        _check(self._lib.s3d_ingest_collect(self._h, int(ticket), out.ctypes.data))
         return out
 
     def ingest_batch_mono16(self, images_u16: np.ndarray, T: np.ndarray) -> np.ndarray:

@@ -1403,6 +1403,16 @@ struct Job {                         // one s3d_ingest_batch* call: frames [0, n
     u64 id = 0;
     const uint8_t *imgs = nullptr; const double *T = nullptr; DevStats *stats = nullptr;
     int64_t n = 0, next = 0;         // frames [0, next) have been enqueued
+    u64 last_seq = ~0ull;            // sequence number of the chunk that holds its last frame (once enqueued)
+    cudaEvent_t done_ev = nullptr;   // recorded behind the apply of that chunk (asynchronous batches)
+};
+
+// staging of one asynchronous host batch (s3d_ingest_submit / s3d_ingest_collect); two of them, so
+// that the copy and the kernels of one batch overlap the tail of the batch before
+struct Staging {
+    uint8_t *img = nullptr; size_t img_n = 0; double *T = nullptr; size_t T_n = 0;
+    DevStats *stats = nullptr, *stats_host = nullptr; size_t stats_n = 0;
+    u64 last_job = 0; int64_t n = 0; bool busy = false;
 };
 
 struct InFlight { u64 seq = ~0ull; u64 job = 0; int64_t base = 0; int g = 0; };
@@ -1468,12 +1478,15 @@ struct s3d_map {
     cudaEvent_t x_ev = nullptr;      // orders work queued on xstream before xstream2
     cudaStream_t snap_stream = nullptr;  // per-chunk counter snapshots (device -> pinned host)
     cudaStream_t mstream = nullptr;      // routed map: owner-side merges
+    cudaStream_t ctl_stream = nullptr;   // small reads for s3d_ingest_collect (never behind queued chunks)
     size_t l2_persist_max = 0, l2_window_max = 0, l2_window = 0;
     DevBuf<double> sum_tab;          // [4][SUMT] running sums of n copies of lo_free / lo_occ, and their means
     ChunkCtr *cc = nullptr;
     DevBuf<DevStats> stats; DevStats *stats_host = nullptr; size_t stats_host_n = 0;
     // staging
     DevBuf<uint8_t> img_dev; DevBuf<double> T_dev; DevBuf<uint16_t> img16_dev;
+    Staging stg[2]; int stg_next = 0;
+    std::vector<cudaEvent_t> job_ev_pool;
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> copy_ev;
     DevBuf<u64> io_keys; DevBuf<double> io_vals; DevBuf<uint8_t> io_flags;
@@ -1911,6 +1924,10 @@ int pump(s3d_map *m, bool drain)
             int rc = enqueue_chunk(m, *job, job->next, g);
             if (rc) return rc;
             job->next += g;
+            if (job->next == job->n) {
+                job->last_seq = m->chunk_seq - 1;
+                if (job->done_ev) CU(cudaEventRecord(job->done_ev, m->stream));
+            }
             continue;
         }
         if (!drain || m->jobs.empty()) return 0;
@@ -1920,13 +1937,15 @@ int pump(s3d_map *m, bool drain)
         m->count_known = m->mc_host->count;
         m->unique_est = std::max<u64>(m->unique_est, m->mc_host->last_unique);
         m->snap_floor = m->chunk_seq;
+        for (Job &j : m->jobs) if (j.done_ev) m->job_ev_pool.push_back(j.done_ev);
         m->jobs.clear();
         return 0;
     }
 }
 
 // queue n frames whose images / transforms sit in device memory
-int submit_frames(s3d_map *m, const uint8_t *imgs_dev, int64_t n, const double *T_dev, DevStats *stats_dev)
+int submit_frames(s3d_map *m, const uint8_t *imgs_dev, int64_t n, const double *T_dev, DevStats *stats_dev,
+                  bool want_done_event = false)
 {
     // zeroed on the expand stream: k_expand is the first writer (num_samples)
     CU(cudaMemsetAsync(stats_dev, 0, sizeof(DevStats) * (size_t)n, m->xstream));
@@ -1942,8 +1961,40 @@ int submit_frames(s3d_map *m, const uint8_t *imgs_dev, int64_t n, const double *
     }
     Job j;
     j.id = ++m->job_seq; j.imgs = imgs_dev; j.T = T_dev; j.stats = stats_dev; j.n = n; j.next = 0;
+    if (want_done_event) {
+        if (m->job_ev_pool.empty()) { CU(cudaEventCreateWithFlags(&j.done_ev, cudaEventDisableTiming)); }
+        else { j.done_ev = m->job_ev_pool.back(); m->job_ev_pool.pop_back(); }
+    }
     m->jobs.push_back(j);
     return pump(m, false);
+}
+
+// Block until every frame of the jobs up to `job_id` is applied (re-running chunks that asked for a
+// retry), without draining what was queued behind them.
+int wait_jobs_through(s3d_map *m, u64 job_id)
+{
+    for (;;) {
+        int rc = pump(m, false); if (rc) return rc;
+        Job *job = nullptr;
+        for (Job &j : m->jobs) if (j.id == job_id) { job = &j; break; }
+        if (!job) return 0;                                  // a full drain has confirmed it already
+        if (job->done_ev) CU(cudaEventSynchronize(job->done_ev));
+        else CU(cudaStreamSynchronize(m->stream));
+        // (its own stream: the snapshot stream may be queued behind chunks of later batches)
+        CU(cudaMemcpyAsync(m->mc_host, m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, m->ctl_stream));
+        CU(cudaStreamSynchronize(m->ctl_stream));
+        if (m->mc_host->abort && m->mc_host->abort_seq <= job->last_seq) {
+            if ((rc = recover(m))) return rc;                // the chunk is queued again; go round
+            continue;
+        }
+        if (m->mc_host->err) return fatal_from_flags(m, m->mc_host->err);
+        break;
+    }
+    while (!m->jobs.empty() && m->jobs.front().id <= job_id) {
+        if (m->jobs.front().done_ev) m->job_ev_pool.push_back(m->jobs.front().done_ev);
+        m->jobs.pop_front();
+    }
+    return 0;
 }
 
 int check_ready(s3d_map *m)
@@ -2024,6 +2075,7 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
     CU(cudaStreamCreateWithFlags(&m->xstream2, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&m->snap_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&m->mstream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&m->ctl_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&m->x_ev, cudaEventDisableTiming));
     { const char *e = getenv("S3D_WIDE_LANES"); m->wide = e && atoi(e) != 0; }
     { const char *e = getenv("S3D_LOOKAHEAD"); if (e) m->lookahead_env = atoi(e); }
@@ -2069,6 +2121,7 @@ int s3d_destroy(s3d_map *m)
         if (m->buf[b].merged) cudaEventDestroy(m->buf[b].merged);
     }
     if (m->mstream) { cudaStreamSynchronize(m->mstream); cudaStreamDestroy(m->mstream); }
+    if (m->ctl_stream) { cudaStreamSynchronize(m->ctl_stream); cudaStreamDestroy(m->ctl_stream); }
     if (m->xstream) { cudaStreamSynchronize(m->xstream); cudaStreamDestroy(m->xstream); }
     if (m->xstream2) { cudaStreamSynchronize(m->xstream2); cudaStreamDestroy(m->xstream2); }
     if (m->x_ev) cudaEventDestroy(m->x_ev);
@@ -2086,7 +2139,15 @@ int s3d_destroy(s3d_map *m)
     m->d_beam_col.release(); m->d_nv_free.release(); m->d_nv_occ.release();
     m->d_cos_b.release(); m->d_sin_b.release(); m->d_range.release(); m->d_cos_va.release(); m->d_sin_va.release();
     m->d_col_to_beam.release(); m->spool.release(); m->sum_tab.release(); m->stats.release();
-    m->img_dev.release(); m->T_dev.release(); m->img16_dev.release(); m->io_keys.release(); m->io_vals.release(); m->io_flags.release();
+    m->img_dev.release(); m->T_dev.release(); m->img16_dev.release();
+    for (Staging &s : m->stg) {
+        if (s.img) cudaFree(s.img);
+        if (s.T) cudaFree(s.T);
+        if (s.stats) cudaFree(s.stats);
+        if (s.stats_host) cudaFreeHost(s.stats_host);
+    }
+    for (Job &j : m->jobs) if (j.done_ev) cudaEventDestroy(j.done_ev);
+    for (cudaEvent_t e : m->job_ev_pool) cudaEventDestroy(e); m->io_keys.release(); m->io_vals.release(); m->io_flags.release();
     m->ex_xyz.release(); m->ex_prob.release(); m->ex_L.release(); m->ex_cls.release(); m->ex_ijk.release(); m->ex_f32.release();
     for (cudaEvent_t e : m->ev_pool) cudaEventDestroy(e);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -2267,6 +2328,82 @@ int s3d_ingest_batch(s3d_map *m, const uint8_t *images, int64_t n, const double 
         }
     }
     return finish_stats(m, m->stats.p, n, out);
+}
+
+int s3d_ingest_submit(s3d_map *m, const uint8_t *images, int64_t n, const double *T, int *ticket)
+{
+    int rc = check_ready(m); if (rc) return rc;
+    if (!images || !T || !ticket) return fail(S3D_EINVAL, "null argument");
+    if (n < 1) return fail(S3D_EINVAL, "n < 1");
+    if ((rc = set_device(m))) return rc;
+    const size_t img_bytes = (size_t)m->tab.H * m->tab.W;
+    if (img_bytes * (size_t)n > (1ull << 30)) return fail(S3D_EINVAL, "an asynchronous batch is limited to 1 GiB of frames; split it");
+    Staging &s = m->stg[m->stg_next];
+    if (s.busy) return fail(S3D_EINVAL, "both staging slots hold uncollected batches: call s3d_ingest_collect first");
+    // (re)size this slot's buffers; nothing of this slot is in flight
+    if (s.img_n < std::max<size_t>(16, img_bytes * (size_t)n)) {
+        if (s.img) cudaFree(s.img);
+        s.img = nullptr; s.img_n = 0;
+        CU(cudaMalloc(&s.img, std::max<size_t>(16, img_bytes * (size_t)n))); s.img_n = std::max<size_t>(16, img_bytes * (size_t)n);
+    }
+    if (s.T_n < 16 * (size_t)n) {
+        if (s.T) cudaFree(s.T);
+        s.T = nullptr; s.T_n = 0;
+        CU(cudaMalloc(&s.T, sizeof(double) * 16 * (size_t)n)); s.T_n = 16 * (size_t)n;
+    }
+    if (s.stats_n < (size_t)n) {
+        if (s.stats) cudaFree(s.stats);
+        if (s.stats_host) cudaFreeHost(s.stats_host);
+        s.stats = nullptr; s.stats_host = nullptr; s.stats_n = 0;
+        CU(cudaMalloc(&s.stats, sizeof(DevStats) * (size_t)n));
+        CU(cudaMallocHost(&s.stats_host, sizeof(DevStats) * (size_t)n));
+        s.stats_n = (size_t)n;
+    }
+    auto piece = [](int64_t s0) -> int64_t { return s0 == 0 ? GF : 2 * GF; };
+    CU(cudaMemcpyAsync(s.T, T, sizeof(double) * 16 * (size_t)n, cudaMemcpyHostToDevice, m->copy_stream));
+    size_t ei = 0;
+    for (int64_t s0 = 0; s0 < n; s0 += piece(s0), ++ei) {
+        const int64_t kk = std::min<int64_t>(piece(s0), n - s0);
+        if (ei == m->copy_ev.size()) {
+            cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            m->copy_ev.push_back(e);
+        }
+        if (img_bytes)
+            CU(cudaMemcpyAsync(s.img + (size_t)s0 * img_bytes, images + (size_t)s0 * img_bytes, img_bytes * (size_t)kk,
+                               cudaMemcpyHostToDevice, m->copy_stream));
+        CU(cudaEventRecord(m->copy_ev[ei], m->copy_stream));
+    }
+    ei = 0;
+    for (int64_t s0 = 0; s0 < n; s0 += piece(s0), ++ei) {
+        const int64_t kk = std::min<int64_t>(piece(s0), n - s0);
+        CU(cudaStreamWaitEvent(m->xstream, m->copy_ev[ei], 0));
+        CU(cudaStreamWaitEvent(m->xstream2, m->copy_ev[ei], 0));
+        if ((rc = submit_frames(m, s.img + (size_t)s0 * img_bytes, kk, s.T + s0 * 16, s.stats + s0, s0 + kk == n))) return rc;
+    }
+    s.last_job = m->job_seq; s.n = n; s.busy = true;
+    *ticket = m->stg_next;
+    m->stg_next ^= 1;
+    return 0;
+}
+
+int s3d_ingest_collect(s3d_map *m, int ticket, s3d_frame_stats *out)
+{
+    if (!m) return fail(S3D_EINVAL, "null map");
+    if (ticket < 0 || ticket > 1 || !m->stg[ticket].busy) return fail(S3D_EINVAL, "no batch is pending under ticket %d", ticket);
+    int rc = set_device(m); if (rc) return rc;
+    Staging &s = m->stg[ticket];
+    if ((rc = wait_jobs_through(m, s.last_job))) { s.busy = false; return rc; }
+    if (out) {
+        CU(cudaMemcpyAsync(s.stats_host, s.stats, sizeof(DevStats) * (size_t)s.n, cudaMemcpyDeviceToHost, m->ctl_stream));
+        CU(cudaStreamSynchronize(m->ctl_stream));
+        for (int64_t f = 0; f < s.n; ++f) {
+            const DevStats &d = s.stats_host[f];
+            out[f].num_occupied = (int64_t)d.n_occ; out[f].num_free = (int64_t)d.n_free;
+            out[f].num_voxels = (int64_t)d.n_voxels; out[f].num_samples = (int64_t)d.n_samples;
+        }
+    }
+    s.busy = false;
+    return 0;
 }
 
 int s3d_ingest_batch_mono16(s3d_map *m, const uint16_t *images, int64_t n, const double *T, s3d_frame_stats *out)

@@ -258,6 +258,21 @@ class SimpleOctree:
         self._pt_max = np.array([-float("inf")] * 3)
 
 
+class PendingBatch:
+    """Handle of SonarTo3DMapper.process_sonar_images_async; keeps the host arrays alive until collected."""
+
+    def __init__(self, mapper, ticket: int, n: int, start_time: float, keep):
+        self._mapper, self._ticket, self._n, self._t0, self._keep = mapper, ticket, n, start_time, keep
+        self._out = None
+
+    def result(self) -> List[Dict[str, Any]]:
+        if self._out is None:
+            st = self._mapper.octree._native.ingest_collect(self._ticket, self._n)
+            self._keep = None
+            self._out = self._mapper._batch_stats(st, self._n, time.time() - self._t0)
+        return self._out
+
+
 class SonarTo3DMapper:
     """Sonar image + pose -> probabilistic voxel map (reference: scripts/3d_mapper.py:197-650)."""
 
@@ -458,6 +473,22 @@ class SonarTo3DMapper:
         self._sync_device_config(range_bins, bearing_bins)
         st = self.octree._native.ingest_batch(np.ascontiguousarray(polar_images), T)
         return self._batch_stats(st, n, time.time() - start_time)
+
+    def process_sonar_images_async(self, polar_images: np.ndarray, robot_positions, robot_orientations) -> "PendingBatch":
+        """process_sonar_images without the wait (extension): the frames' upload and kernels are queued and
+        a handle comes back at once; `handle.result()` returns what process_sonar_images would have.  Up to
+        two batches may be pending, so batch k+1 uploads and runs while batch k finishes -- a bag replay or a
+        driver thread keeps the GPU busy across calls.  Collect the results in submission order."""
+        start_time = time.time()
+        polar_images = np.ascontiguousarray(polar_images)
+        n, range_bins, bearing_bins = polar_images.shape
+        if polar_images.dtype != np.uint8:
+            raise TypeError("process_sonar_images_async expects uint8 images")
+        self._check_width(bearing_bins)
+        T = np.ascontiguousarray(self.compose_transforms(robot_positions, robot_orientations), dtype=np.float64).reshape(n, 16)
+        self._sync_device_config(range_bins, bearing_bins)
+        ticket = self.octree._native.ingest_submit(polar_images, T)
+        return PendingBatch(self, ticket, n, start_time, (polar_images, T))
 
     def _batch_stats(self, st, n: int, dt: float) -> List[Dict[str, Any]]:
         """The per-frame dicts of process_sonar_image (:587-595) for a batch (time split evenly)."""

@@ -186,6 +186,27 @@ def test_batch_equals_sequential_and_growth(s3d):
     assert b.frame_count == a.frame_count == 40
 
 
+def test_async_batches_equal_the_blocking_call_and_survive_growth(s3d):
+    """Two batches pending at a time (submit k+1 before collecting k), tiny initial table so that chunks
+    of pending batches are re-run after rehash-grows: same counters and map as one blocking call."""
+    from sonar_3d_reconstruction_b200 import synthetic
+    spec = dict(H=160, W=200, config=dict(voxel_resolution=0.06, intensity_threshold=45, max_range=8.0), step_m=0.03)
+    images, pos, quat, cfg = synthetic.make_sequence(spec, 150, seed=8)
+    a = s3d.SonarTo3DMapper(cfg)
+    sa = [_stats3(x) for x in a.process_sonar_images(images, pos, quat)]
+    b = s3d.SonarTo3DMapper(dict(cfg, table_capacity=1024))
+    sb, pending = [], None
+    for f0 in range(0, 150, 37):                                   # ragged batch sizes
+        h = b.process_sonar_images_async(images[f0:f0 + 37], pos[f0:f0 + 37], quat[f0:f0 + 37])
+        if pending is not None:
+            sb += [_stats3(x) for x in pending.result()]
+        pending = h
+    sb += [_stats3(x) for x in pending.result()]
+    assert sa == sb
+    assert_same_map(*a.octree.voxels.to_arrays(), *b.octree.voxels.to_arrays(), 0.0, "async vs blocking")
+    assert b.frame_count == 150
+
+
 def test_dump_load_roundtrip_and_xyzi32(s3d):
     from sonar_3d_reconstruction_b200 import synthetic
     images, pos, quat, cfg = synthetic.make_sequence(dict(H=120, W=96, config=dict(voxel_resolution=0.1)), 5, seed=9)
