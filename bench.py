@@ -475,9 +475,10 @@ def run_sharded(args, rank, world, local_rank, images, pos, quat, cfg, barrier):
                        if sh.mode == "fused" else f"shard{world} ({sh.mode})",
                        "exchange_bytes_sent_per_rank_last_step": exch,
                        "l2": "inputs streamed once: every step reads fresh frames"},
-            "e2e": {"value": n_frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": world * fps_step * (H * W + 128),
+            "e2e": {"value": n_frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": fps_step * H * W + world * fps_step * 128,
                     "d2h_bytes_per_step": fps_step * 32,
-                    "api": "ShardedSonarMapper.process_sonar_images (pinned host images on every rank)",
+                    "api": "ShardedSonarMapper.process_sonar_images (pinned host images on every rank; each rank "
+                           "uploads 1/N of the frames and the ranks all-gather them over NVLink)",
                     "host": args.numa},
             "gpu_launches": int(launches[0]),
             "roofline": {"bound": "hbm", "achieved": achieved / world, "peak": peak, "unit": "GB/s",

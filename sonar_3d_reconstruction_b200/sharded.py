@@ -219,6 +219,30 @@ class CudaShardBackend:
         arr = np.stack([st["num_occupied"], st["num_free"], st["num_voxels"], st["num_samples"]], axis=1)
         return self.torch.from_numpy(arr.astype(np.int64)).to(self.device)
 
+    def ingest_owned_shared_upload(self, images: np.ndarray, T: np.ndarray, ex):
+        """Host frames that every rank holds (fused / replicate modes): each rank uploads 1/world of
+        them over its own PCIe link and the ranks all-gather the rest over NVLink, instead of every
+        rank pulling every frame from host memory.  Returns the per-shard counters int64[n, 4]."""
+        t = self.torch
+        dist = _dist()
+        n, H, W = images.shape
+        w = ex.world
+        part = (n + w - 1) // w
+        if getattr(self, "_gather_buf", None) is None or tuple(self._gather_buf.shape) != (part * w, H, W):
+            self._gather_buf = t.empty((part * w, H, W), dtype=t.uint8, device=self.device)
+        buf = self._gather_buf
+        lo, hi = min(ex.rank * part, n), min((ex.rank + 1) * part, n)
+        mine = buf[ex.rank * part: (ex.rank + 1) * part]
+        if hi > lo:
+            mine[: hi - lo].copy_(t.from_numpy(images[lo:hi]), non_blocking=True)
+        dist.all_gather_into_tensor(buf.view(-1), mine.reshape(-1), group=ex.group)
+        d_T = t.from_numpy(np.ascontiguousarray(T, dtype=np.float64).reshape(-1, 16)).to(self.device, non_blocking=True)
+        st = t.empty((n, 4), dtype=t.int64, device=self.device)
+        t.cuda.current_stream(self.device).synchronize()          # the map's kernels run on the library's own streams
+        self.native.ingest_batch_dev(buf.data_ptr(), n, d_T.data_ptr(), want_stats=False, stats_dev_ptr=st.data_ptr())
+        self.native.sync()
+        return st
+
     def upload(self, images: np.ndarray, T: np.ndarray):
         t = self.torch
         return (t.from_numpy(np.ascontiguousarray(images)).to(self.device, non_blocking=False),
@@ -307,7 +331,10 @@ class ShardedSonarMapper:
         T = m.compose_transforms(robot_positions, robot_orientations)
         m._sync_device_config(H, W)
         if self.mode in ("replicate", "fused"):
-            stats = self.ex.all_reduce_sum(self.backend.ingest_owned_host(polar_images, T))
+            if self.world > 1 and hasattr(self.backend, "ingest_owned_shared_upload"):
+                stats = self.ex.all_reduce_sum(self.backend.ingest_owned_shared_upload(polar_images, T, self.ex))
+            else:
+                stats = self.ex.all_reduce_sum(self.backend.ingest_owned_host(polar_images, T))
             self.last_exchange_bytes = 0
             return self._finish(stats, n, t0)
         d_img, d_T = self.backend.upload(polar_images, T)
