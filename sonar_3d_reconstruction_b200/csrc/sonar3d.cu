@@ -79,7 +79,6 @@ struct DevTables {
     const double *cos_b, *sin_b, *range_m;
     const int *nv_free, *nv_occ;
     const double *cos_va, *sin_va;
-    const short *col_to_beam;  // [W] processed-beam index of a column, -1 = not processed
 };
 
 struct MapCtr {       // device-resident map counters
@@ -1451,14 +1450,12 @@ struct s3d_map {
     DevBuf<u64> trace; static constexpr u64 TRACE_CHUNKS = 4096; static constexpr int TRACE_W = 10;
     DevBuf<u64> send_buf; DevBuf<u32> owner_ctr;      // owner_ctr: [3][64] count / base / fill
     u32 *owner_host = nullptr;                        // pinned [64]
-    int l2_policy = 0;               // S3D_L2_POLICY: 0 = no window, 1 = persisting + streaming misses, 2 = persisting + normal
     // params / tables
     bool have_params = false, have_tables = false;
     DevParams p{};
     DevTables tab{};
     DevBuf<int> d_beam_col, d_nv_free, d_nv_occ;
     DevBuf<double> d_cos_b, d_sin_b, d_range, d_cos_va, d_sin_va;
-    DevBuf<short> d_col_to_beam;
     u64 samples_max = 0;             // worst-case samples per frame for these tables
     // chunk working set
     // chunk dedupe table: one allocation {counters[C][GF], keys[C], list[C]} so that a single L2
@@ -1479,7 +1476,6 @@ struct s3d_map {
     cudaStream_t snap_stream = nullptr;  // per-chunk counter snapshots (device -> pinned host)
     cudaStream_t mstream = nullptr;      // routed map: owner-side merges
     cudaStream_t ctl_stream = nullptr;   // small reads for s3d_ingest_collect (never behind queued chunks)
-    size_t l2_persist_max = 0, l2_window_max = 0, l2_window = 0;
     DevBuf<double> sum_tab;          // [4][SUMT] running sums of n copies of lo_free / lo_occ, and their means
     ChunkCtr *cc = nullptr;
     DevBuf<DevStats> stats; DevStats *stats_host = nullptr; size_t stats_host_n = 0;
@@ -2062,9 +2058,6 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     m->n_sm = prop.multiProcessorCount;
-    { const char *e = getenv("S3D_L2_POLICY"); if (e) m->l2_policy = atoi(e); }
-    m->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
-    m->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&m->mc, sizeof(MapCtr)));
     CU(cudaMallocHost(&m->mc_host, sizeof(MapCtr)));
@@ -2138,7 +2131,7 @@ int s3d_destroy(s3d_map *m)
     if (m->stats_host) cudaFreeHost(m->stats_host);
     m->d_beam_col.release(); m->d_nv_free.release(); m->d_nv_occ.release();
     m->d_cos_b.release(); m->d_sin_b.release(); m->d_range.release(); m->d_cos_va.release(); m->d_sin_va.release();
-    m->d_col_to_beam.release(); m->spool.release(); m->sum_tab.release(); m->stats.release();
+    m->spool.release(); m->sum_tab.release(); m->stats.release();
     m->img_dev.release(); m->T_dev.release(); m->img16_dev.release();
     for (Staging &s : m->stg) {
         if (s.img) cudaFree(s.img);
@@ -2209,11 +2202,9 @@ int s3d_set_tables(s3d_map *m, const s3d_tables *t)
     if ((rc = sync_counters(m))) return rc;
     const size_t nb = (size_t)t->n_beams, H = (size_t)t->H;
     const size_t nfan = (size_t)t->nv_max * ((size_t)t->nv_max + 2);
-    std::vector<short> c2b((size_t)t->W, (short)-1);
     for (size_t b = 0; b < nb; ++b) {
         const int col = t->beam_col[b];
         if (col < 0 || col >= t->W) return fail(S3D_EINVAL, "beam_col[%zu]=%d out of range", b, col);
-        c2b[(size_t)col] = (short)b;
     }
     if (nb > 32767) return fail(S3D_EINVAL, "too many processed beams");
     u64 free_sum = 0, occ_best = 0, occ_run = 0;
@@ -2237,14 +2228,12 @@ int s3d_set_tables(s3d_map *m, const s3d_tables *t)
     if ((rc = upload(m->d_nv_occ, t->nv_occ, H, m->stream))) return rc;
     if ((rc = upload(m->d_cos_va, t->cos_va, nfan, m->stream))) return rc;
     if ((rc = upload(m->d_sin_va, t->sin_va, nfan, m->stream))) return rc;
-    if ((rc = upload(m->d_col_to_beam, c2b.data(), c2b.size(), m->stream))) return rc;
     CU(cudaStreamSynchronize(m->stream));     // host vectors go out of scope
     DevTables &d = m->tab;
     d.H = t->H; d.W = t->W; d.n_beams = t->n_beams; d.nv_max = t->nv_max;
     d.free_step = t->free_step; d.occ_window = t->occ_window;
     d.beam_col = m->d_beam_col.p; d.cos_b = m->d_cos_b.p; d.sin_b = m->d_sin_b.p; d.range_m = m->d_range.p;
     d.nv_free = m->d_nv_free.p; d.nv_occ = m->d_nv_occ.p; d.cos_va = m->d_cos_va.p; d.sin_va = m->d_sin_va.p;
-    d.col_to_beam = m->d_col_to_beam.p;
     m->have_tables = true;
     CU(cudaFuncSetAttribute(k_expand<u32, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
     CU(cudaFuncSetAttribute(k_expand<u32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
