@@ -161,3 +161,21 @@ def test_vectorised_pose_composition_is_bit_identical_or_disabled():
     assert np.array_equal(got, want)                 # whichever path was chosen, the result is the scalar one
     one = h.compose_transforms(pos[:1], quat[:1])
     assert np.array_equal(one[0], want[0])
+
+
+def test_reference_arm_of_the_bench_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours) runs without a GPU and
+    keeps the line contract: impl, metric/unit of our arm, cpu_baseline and a zero-copy e2e object."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--ref-frames-per-step", "4"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "sonar_frames_per_s" and d["unit"] == "frames/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
