@@ -170,6 +170,13 @@ class Exchange:
         return t
 
 
+def upload_partition(n: int, world: int, rank: int) -> Tuple[int, int, int]:
+    """Frames [lo, hi) of a batch of n that `rank` uploads itself (the rest arrives by all-gather):
+    equal parts of ceil(n / world) frames, the last ranks may get fewer or none.  -> (part, lo, hi)"""
+    part = (n + world - 1) // world
+    return part, min(rank * part, n), min((rank + 1) * part, n)
+
+
 # ---------------------------------------------------------------------------- CUDA backend
 class _DevView:
     """Zero-copy torch view of a raw device pointer (CUDA array interface)."""
@@ -227,11 +234,10 @@ class CudaShardBackend:
         dist = _dist()
         n, H, W = images.shape
         w = ex.world
-        part = (n + w - 1) // w
+        part, lo, hi = upload_partition(n, w, ex.rank)
         if getattr(self, "_gather_buf", None) is None or tuple(self._gather_buf.shape) != (part * w, H, W):
             self._gather_buf = t.empty((part * w, H, W), dtype=t.uint8, device=self.device)
         buf = self._gather_buf
-        lo, hi = min(ex.rank * part, n), min((ex.rank + 1) * part, n)
         mine = buf[ex.rank * part: (ex.rank + 1) * part]
         if hi > lo:
             mine[: hi - lo].copy_(t.from_numpy(images[lo:hi]), non_blocking=True)

@@ -253,3 +253,19 @@ def test_beam_slices_cover_all_beams_once():
                 lo, hi = beam_slice(n, r, world)
                 cover += list(range(lo, hi))
             assert cover == list(range(n))
+
+
+def test_upload_partition_covers_every_frame_once():
+    """Shared upload of host frames: the ranks' pieces tile [0, n) in rank order, equal padded parts."""
+    from sonar_3d_reconstruction_b200.sharded import upload_partition
+    for n in (1, 2, 7, 16, 250, 256, 1000):
+        for world in (1, 2, 3, 4, 8):
+            pieces = [upload_partition(n, world, r) for r in range(world)]
+            part = pieces[0][0]
+            assert all(p[0] == part for p in pieces) and part * world >= n
+            covered = []
+            for r, (_, lo, hi) in enumerate(pieces):
+                assert 0 <= lo <= hi <= n and hi - lo <= part
+                assert lo == min(r * part, n)              # where the all-gather puts rank r's part
+                covered += list(range(lo, hi))
+            assert covered == list(range(n))
