@@ -212,7 +212,7 @@ def run_gpu(args, rank, world, local_rank):
     T_all = mapper.compose_transforms(pos, quat).reshape(n_total, 16)
     d_img = torch.from_numpy(images).to(f"cuda:{local_rank}")
     d_T = torch.from_numpy(T_all).to(f"cuda:{local_rank}")
-    d_stats = torch.zeros((n_total, 4), dtype=torch.int64, device=f"cuda:{local_rank}")
+    d_stats = torch.zeros((n_total, 8), dtype=torch.int64, device=f"cuda:{local_rank}")
     torch.cuda.synchronize()
     stream = torch.cuda.ExternalStream(native.stream, device=local_rank)
     img_bytes = H * W
@@ -220,7 +220,7 @@ def run_gpu(args, rank, world, local_rank):
     def step_dev(s):
         f0 = s * fps_step
         native.ingest_batch_dev(d_img.data_ptr() + f0 * img_bytes, fps_step, d_T.data_ptr() + f0 * 128,
-                                want_stats=False, stats_dev_ptr=d_stats.data_ptr() + f0 * 32)
+                                want_stats=False, stats_dev_ptr=d_stats.data_ptr() + f0 * 64)
 
     for s in range(args.warmup):
         step_dev(s)
@@ -346,7 +346,7 @@ def run_gpu(args, rank, world, local_rank):
                              f"{n_frames * H * W / 2**20:.0f} MiB > L2), table {cap * 16 / 2**20:.0f} MiB",
                        "parallelism": "1 map per GPU" if world > 1 else "single GPU"},
             "e2e": {"value": frames_all / e2e_s, "unit": UNIT,
-                    "h2d_bytes_per_step": fps_step * (H * W + 128), "d2h_bytes_per_step": fps_step * 32,
+                    "h2d_bytes_per_step": fps_step * (H * W + 128), "d2h_bytes_per_step": fps_step * 64,
                     "api": "SonarTo3DMapper.process_sonar_images_async, two 250-frame steps pending at a time "
                            "(pinned host images, poses on host; H2D of every frame and D2H of every step's "
                            "per-frame counters inside the timed region)",
@@ -406,7 +406,7 @@ def run_sharded(args, rank, world, local_rank, images, pos, quat, cfg, barrier):
     sampler.start()                       # before the barrier: spawning nvidia-smi must not skew the ranks' start
     stream = torch.cuda.ExternalStream(native.stream, device=local_rank)
     fused_like = sh.mode in ("fused", "replicate")
-    d_stats = torch.zeros((n_frames, 4), dtype=torch.int64, device=dev)
+    d_stats = torch.zeros((n_frames, 8), dtype=torch.int64, device=dev)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if fused_like:
@@ -476,7 +476,7 @@ def run_sharded(args, rank, world, local_rank, images, pos, quat, cfg, barrier):
                        "exchange_bytes_sent_per_rank_last_step": exch,
                        "l2": "inputs streamed once: every step reads fresh frames"},
             "e2e": {"value": n_frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": fps_step * H * W + world * fps_step * 128,
-                    "d2h_bytes_per_step": fps_step * 32,
+                    "d2h_bytes_per_step": fps_step * 64,
                     "api": "ShardedSonarMapper.process_sonar_images (pinned host images on every rank; each rank "
                            "uploads 1/N of the frames and the ranks all-gather them over NVLink)",
                     "host": args.numa},

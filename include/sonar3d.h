@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define S3D_ABI_VERSION 1
+#define S3D_ABI_VERSION 2
 #define S3D_KEY_LIMIT (1 << 20)
 
 enum {
@@ -88,6 +88,12 @@ typedef struct s3d_frame_stats {
     int64_t num_free;      /* voxels updated with type 'free' (:567) */
     int64_t num_voxels;    /* len(octree.voxels) after the frame (:592) */
     int64_t num_samples;   /* samples emitted by all rays after the z filter (len of the :542 loop) */
+    /* the reference's every-10th-frame [DEBUG] statistics (:575-585); filled only while
+     * s3d_debug_counters is on, 0 otherwise */
+    int64_t max_samples_per_voxel; /* max(frame_update_counts.values()) (:576) */
+    int64_t num_voxels_gt10;       /* voxels with more than 10 samples this frame (:585) */
+    int64_t max_total_samples;     /* max(voxel_update_counts.values()) after the frame (:578) */
+    int64_t reserved;
 } s3d_frame_stats;
 
 /* ---- lifetime -------------------------------------------------------------------------- */
@@ -162,6 +168,25 @@ int s3d_clear(s3d_map *map);
  * (k + 0.5) * resolution.  empty map: kmin > kmax. */
 int s3d_bounds(s3d_map *map, int32_t kmin[3], int32_t kmax[3]);
 uint64_t s3d_capacity(s3d_map *map);
+/* Restore of a checkpoint (s3d_dump + s3d_bounds -> s3d_load + s3d_extend_bounds): widen the key
+ * bounding box.  s3d_load and s3d_apply_updates themselves never touch it -- the reference extends
+ * min/max_bounds only inside update_voxel, with the caller's point (:113-115), and not at all for
+ * direct writes into `voxels`. */
+int s3d_extend_bounds(s3d_map *map, const int32_t kmin[3], const int32_t kmax[3]);
+/* Forget the box (the reference lets callers assign min_bounds / max_bounds, :38-40; the host
+ * mirror folds the device's box into its own pair and restarts the device's). */
+int s3d_reset_bounds(s3d_map *map);
+
+/* ---- debug counters: voxel_update_counts / frame_update_counts (:307-308, :549-551, :575-585) ---- */
+
+/* While on, the update kernel also keeps a lifetime sample count per voxel key (a second table
+ * of the voxel table's size; it survives s3d_clear like voxel_update_counts survives reset_map,
+ * :644-650) and fills the three debug fields of s3d_frame_stats.  Off by default. */
+int s3d_debug_counters(s3d_map *map, int on);
+/* frame_update_counts after the last ingested frame: (key, samples) pairs, any order. */
+int s3d_debug_last_frame(s3d_map *map, int32_t *ijk, uint64_t *counts, uint64_t cap, uint64_t *n_out);
+/* voxel_update_counts: (key, lifetime samples) pairs, any order. */
+int s3d_debug_totals(s3d_map *map, int32_t *ijk, uint64_t *counts, uint64_t cap, uint64_t *n_out);
 
 /* ---- export: get_occupied_voxels / get_all_voxels_classified (:127-188) ------------------ */
 

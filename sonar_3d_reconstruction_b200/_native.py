@@ -21,6 +21,7 @@ SYMBOLS = (
     "s3d_shard_config", "s3d_shard_filter", "s3d_shard_owner", "s3d_shard_expand", "s3d_shard_apply",
     "s3d_route_export", "s3d_route_attach", "s3d_route_enable", "s3d_trace_read", "s3d_ingest_batch_mono16",
     "s3d_ingest_submit", "s3d_ingest_collect",
+    "s3d_extend_bounds", "s3d_reset_bounds", "s3d_debug_counters", "s3d_debug_last_frame", "s3d_debug_totals",
 )
 
 
@@ -47,7 +48,12 @@ class Tables(C.Structure):
 
 class FrameStats(C.Structure):
     _fields_ = [("num_occupied", C.c_int64), ("num_free", C.c_int64), ("num_voxels", C.c_int64),
-                ("num_samples", C.c_int64)]
+                ("num_samples", C.c_int64), ("max_samples_per_voxel", C.c_int64), ("num_voxels_gt10", C.c_int64),
+                ("max_total_samples", C.c_int64), ("reserved", C.c_int64)]
+
+
+STATS_WORDS = 8          # int64 words per s3d_frame_stats
+STATS_BYTES = 8 * STATS_WORDS
 
 
 class Profile(C.Structure):
@@ -57,7 +63,9 @@ class Profile(C.Structure):
 
 KERNEL_NAMES = ("k_first_hit", "k_expand", "k_apply")
 
-STATS_DTYPE = np.dtype([("num_occupied", "<i8"), ("num_free", "<i8"), ("num_voxels", "<i8"), ("num_samples", "<i8")])
+STATS_DTYPE = np.dtype([("num_occupied", "<i8"), ("num_free", "<i8"), ("num_voxels", "<i8"), ("num_samples", "<i8"),
+                        ("max_samples_per_voxel", "<i8"), ("num_voxels_gt10", "<i8"), ("max_total_samples", "<i8"),
+                        ("reserved", "<i8")])
 
 _lib = None
 
@@ -114,6 +122,11 @@ def load_library():
     L.s3d_shard_owner.argtypes = [i32p, C.c_int64, C.c_int, i32p]
     L.s3d_shard_expand.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(vp), u64p]
     L.s3d_shard_apply.argtypes = [vp, vp, C.c_uint64, C.c_int, vp]
+    L.s3d_extend_bounds.argtypes = [vp, i32p, i32p]
+    L.s3d_reset_bounds.argtypes = [vp]
+    L.s3d_debug_counters.argtypes = [vp, C.c_int]
+    L.s3d_debug_last_frame.argtypes = [vp, i32p, u64p, C.c_uint64, u64p]
+    L.s3d_debug_totals.argtypes = [vp, i32p, u64p, C.c_uint64, u64p]
     for name in SYMBOLS:
         getattr(L, name)          # AttributeError here = header / library mismatch
     _lib = L
@@ -177,11 +190,11 @@ class NativeMap:
         _check(self._lib.s3d_set_tables(self._h, C.byref(s)))
 
     # -- ingest -------------------------------------------------------------------------
-    def ingest(self, image_u8: np.ndarray, T: np.ndarray) -> Tuple[int, int, int, int]:
+    def ingest(self, image_u8: np.ndarray, T: np.ndarray) -> FrameStats:
         st = FrameStats()
         T = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
         _check(self._lib.s3d_ingest(self._h, image_u8.ctypes.data, _ptr(T, C.c_double), C.byref(st)))
-        return st.num_occupied, st.num_free, st.num_voxels, st.num_samples
+        return st
 
     def ingest_batch(self, images_u8: np.ndarray, T: np.ndarray) -> np.ndarray:
         n = int(images_u8.shape[0])
@@ -324,6 +337,37 @@ class NativeMap:
 
     def clear(self):
         _check(self._lib.s3d_clear(self._h))
+
+    def extend_bounds(self, kmin: np.ndarray, kmax: np.ndarray):
+        kmin = np.ascontiguousarray(kmin, dtype=np.int32).reshape(3)
+        kmax = np.ascontiguousarray(kmax, dtype=np.int32).reshape(3)
+        _check(self._lib.s3d_extend_bounds(self._h, _ptr(kmin, C.c_int32), _ptr(kmax, C.c_int32)))
+
+    def reset_bounds(self):
+        _check(self._lib.s3d_reset_bounds(self._h))
+
+    # -- debug counters -------------------------------------------------------------------
+    def debug_counters(self, on: bool = True):
+        _check(self._lib.s3d_debug_counters(self._h, int(bool(on))))
+
+    def _debug_pairs(self, fn) -> Tuple[np.ndarray, np.ndarray]:
+        n = C.c_uint64()
+        _check(fn(self._h, None, None, 0, C.byref(n)))
+        cap = int(n.value)
+        ijk = np.empty((cap, 3), dtype=np.int32)
+        cnt = np.empty(cap, dtype=np.uint64)
+        if cap:
+            _check(fn(self._h, _ptr(ijk, C.c_int32), _ptr(cnt, C.c_uint64), cap, C.byref(n)))
+        k = min(cap, int(n.value))
+        return ijk[:k], cnt[:k]
+
+    def debug_last_frame(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(keys int32[n,3], samples uint64[n]) of the last ingested frame (frame_update_counts)."""
+        return self._debug_pairs(self._lib.s3d_debug_last_frame)
+
+    def debug_totals(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(keys int32[n,3], lifetime samples uint64[n]) (voxel_update_counts)."""
+        return self._debug_pairs(self._lib.s3d_debug_totals)
 
     def bounds(self) -> Tuple[np.ndarray, np.ndarray]:
         kmin = np.zeros(3, dtype=np.int32)

@@ -86,9 +86,12 @@ struct MapCtr {       // device-resident map counters
     u64 abort_seq;    // first chunk (sequence number) that asked for a retry; ~0 = none
     int kmin[3], kmax[3];
     u32 err;          // fatal flags
-    u32 abort;        // retry flags; while set, every pipeline kernel returns without side effects
+    u32 abort;        // retry flags; while set, the kernels of chunk abort_seq and of every later chunk
+                      // return without side effects (earlier chunks run to completion)
     u32 last_new;     // voxels inserted by the last applied chunk
     u32 last_unique;  // voxels touched by the last applied chunk
+    u64 life_count;   // debug counters: keys in the lifetime sample-count table
+    u64 life_max;     // debug counters: largest lifetime sample count of any voxel (3d_mapper.py:578)
 };
 
 struct ChunkCtr {     // working counters of the chunk in flight (chunks are serialised on the stream)
@@ -97,9 +100,16 @@ struct ChunkCtr {     // working counters of the chunk in flight (chunks are ser
     u32 xticket;      // last-block-out election of k_expand (routed map)
     u32 mticket;      // last-block-out election of k_route_merge (routed map)
     u32 neu[GF];      // voxels first inserted at frame f of the chunk
+    // debug counters (3d_mapper.py:549-551, :575-585), only written when they are enabled
+    u32 dmax[GF];     // largest per-voxel sample count of frame f
+    u32 dgt10[GF];    // voxels with more than 10 samples in frame f
+    u32 life_new;     // keys first inserted into the lifetime table by this chunk
+    u32 pad_;
+    u64 dlife[GF];    // largest lifetime sample count reached by a voxel touched in frame f
 };
 
-struct DevStats { u64 n_occ, n_free, n_voxels, n_samples; };  // == s3d_frame_stats
+// == s3d_frame_stats
+struct DevStats { u64 n_occ, n_free, n_voxels, n_samples, max_in_frame, n_gt10, max_total, reserved; };
 static_assert(sizeof(DevStats) == sizeof(s3d_frame_stats), "stats layout");
 
 __host__ __device__ __forceinline__ u64 mix64(u64 x)
@@ -505,7 +515,8 @@ k_expand(ExpandArgs a)
     const u32 lt_mask = (1u << lane) - 1;
     const int g = blockIdx.y;
     const uint8_t *img = a.imgs + (size_t)g * a.img_stride;
-    if (tid == 0) { s_abort = __ldcg(&a.mc->abort); s_count = 0; }
+    // (a retry asked for by this chunk or an earlier one; a later chunk's flag does not stop this one)
+    if (tid == 0) { s_abort = (__ldcg(&a.mc->abort) != 0u && a.seq >= __ldcg(&a.mc->abort_seq)) ? 1u : 0u; s_count = 0; }
     trace_begin(a.trace);
     if (tid < 12) s_T[tid] = a.T[g * 16 + tid];
     if (tid == 32) {
@@ -809,8 +820,17 @@ __device__ __forceinline__ void acc_publish(LocalAcc &a, MapCtr *mc, bool add_co
     }
 }
 
-constexpr int AP_THREADS = 256;    // = dedupe slots per tile
-constexpr int SUMT = 64;           // entries of the sequential-sum tables
+constexpr int AP_THREADS = 256;
+constexpr int AP_WARPS = AP_THREADS / 32;
+constexpr int AP_SCAN = 4;                   // dedupe slots per lane per scan step (independent loads)
+constexpr int AP_STRIP = 32 * AP_SCAN;       // dedupe slots a warp scans per step
+constexpr int AP_QCAP = 256;                 // per-warp queue of live entries (ring; < 32 left + one strip)
+constexpr int SUMT = 64;                     // entries of the sequential-sum tables
+static_assert(AP_QCAP >= 32 + AP_STRIP && (AP_QCAP & (AP_QCAP - 1)) == 0, "queue holds a leftover round plus one strip");
+// staged counter lanes of the 32 entries a warp is processing: one padded row per lane (stride
+// of 5 / 9 sixteen-byte words: conflict-free 128-bit stores)
+template <typename CT> __host__ __device__ constexpr int ap_row_words() { return (int)(sizeof(CT) * GF / 4) + 4; }
+template <typename CT> __host__ __device__ constexpr size_t apply_smem_bytes() { return (size_t)AP_WARPS * 32 * ap_row_words<CT>() * 4; }
 
 // sum of n_free copies of lo_free followed by n_occ copies of lo_occ, added one by one as the
 // reference's `sum += log_odds` does (3d_mapper.py:546).  tab[0][n] / tab[1][n] hold the
@@ -830,189 +850,263 @@ __device__ __forceinline__ double seq_avg(u32 n_free, u32 n_occ, const double (*
     return sum / (double)(n_occ + n_free);                       // :559
 }
 
-// The chunk's dedupe table is walked in tiles of AP_THREADS slots:
-//   1. one thread per slot: a live entry is read into registers and wiped, its voxel is found or
-//      inserted in the table (one probe per voxel per chunk), the per-frame num_occupied /
-//      num_free / new-voxel counts are taken from the counter lanes (they do not depend on L),
-//      and lanes + L are appended to a ring of staged entries in shared memory;
-//   2. whenever the ring holds AP_THREADS entries, they are listed -- those that can take the
-//      adaptive path (some frame saw the voxel occupied) first, so that warps are homogeneous --
-//   3. and one thread per listed entry walks only the frames that touched the voxel, in order:
-//      per-voxel mean of the sample deltas (3d_mapper.py:557-559), then update_voxel (:562-567);
-//      L goes back to the table with one 8-byte store.  Every thread has an entry, whatever the
-//      load of the dedupe table.
-// Frames stay strictly ordered per voxel, which is all the reference's sequential semantics
-// require (voxels are independent of each other).
-constexpr int AP_Q = 2 * AP_THREADS;        // ring capacity: a full window plus one more tile
-constexpr int AP_ROW = GF + 1;              // padded row of counter lanes: conflict-free column access
-
-template <typename CT> __host__ __device__ constexpr size_t apply_smem_bytes()
+// find-or-insert with the home pair already loaded (the loads were issued together with the
+// entry's counter lanes, so a warp has all of its table sectors in flight at once)
+__device__ __forceinline__ u64 table_resolve(Slot *table, u64 mask, u64 key, u64 pair, ulonglong2 s0, ulonglong2 s1,
+                                             bool &fresh, double &val)
 {
-    return (size_t)AP_Q * (AP_ROW * sizeof(CT) + sizeof(double) + sizeof(u64) + sizeof(unsigned short) + 1);
+    fresh = false;
+    for (u32 probe = 0; probe < (1u << 20); ++probe) {
+        if (s0.x == key) { val = __longlong_as_double((long long)s0.y); return pair; }
+        if (s1.x == key) { val = __longlong_as_double((long long)s1.y); return pair + 1; }
+        if (s0.x == EMPTY_KEY || s1.x == EMPTY_KEY) {
+            const u64 slot = s0.x == EMPTY_KEY ? pair : pair + 1;
+            const u64 cur = atomicCAS(&table[slot].key, EMPTY_KEY, key);
+            if (cur == EMPTY_KEY) { fresh = true; val = 0.0; return slot; }                       // :105-106
+            if (cur == key) { val = __ldcg(&table[slot].val); return slot; }
+        } else {
+            pair = (pair + 2) & mask;
+        }
+        s0 = __ldcg(reinterpret_cast<const ulonglong2 *>(&table[pair]));
+        s1 = __ldcg(reinterpret_cast<const ulonglong2 *>(&table[pair + 1]));
+    }
+    return ~0ull;
 }
 
-template <typename CT>
-__global__ void __launch_bounds__(AP_THREADS)
-k_apply_chunk(u64 *__restrict__ skeys, CT *__restrict__ scnt, u32 n_slots, int g, ChunkCtr *cc, DevStats *st,
-              Slot *table, u64 tmask, DevParams p, const double *__restrict__ sum_tab, MapCtr *mc, u64 table_limit,
-              u64 seq, u64 *trace)
+// spread the low 4 bits of x into the low bits of the 4 bytes of a word
+__device__ __forceinline__ u32 spread4(u32 x) { return ((x & 0xFu) * 0x00204081u) & 0x01010101u; }
+
+struct ApplyArgs {
+    u64 *skeys; void *scnt; u32 n_slots; int g;
+    ChunkCtr *cc; DevStats *st;
+    Slot *table; u64 tmask;
+    DevParams p; const double *sum_tab;
+    MapCtr *mc; u64 table_limit; u64 seq; u64 *trace;
+    // debug counters (DEBUG instantiation only)
+    Slot *life;                 // lifetime sample counts: same geometry as the voxel table, val = u64 count
+    ulonglong2 *last; u32 *last_n; u32 last_cap;   // {key, samples} of the chunk's last frame
+};
+
+// K4.  The chunk's dedupe table is walked by autonomous warps (no block barrier in the loop):
+//   scan     a warp reads AP_STRIP slots' keys (AP_SCAN independent loads per lane) and appends
+//            the live ones to its own shared-memory queue;
+//   process  whenever the queue holds 32 entries, every lane takes one: the entry's counter
+//            lanes and the home sector of its voxel in the table are requested together (six
+//            independent 16-byte loads per lane, a warp keeps 192 in flight), the entry is wiped
+//            for the next chunk, the voxel is found or inserted (one probe per voxel per chunk),
+//            and the frames that touched the voxel are applied in order: per-voxel mean of the
+//            sample deltas (3d_mapper.py:557-559), then update_voxel (:562-567); L goes back with
+//            one 8-byte store.  The frame loop is unrolled over the 16 lanes (registers, no staging).
+// num_occupied / num_free per frame are kept as packed byte counters in registers (one add per
+// entry per 4 frames) and reduced per warp when they could overflow and at the end.
+// Frames stay strictly ordered per voxel, which is all the reference's sequential semantics
+// require (voxels are independent of each other).
+template <typename CT, bool DEBUG>
+__global__ void __launch_bounds__(AP_THREADS, 3)
+k_apply_chunk(const ApplyArgs a)
 {
-    extern __shared__ __align__(16) unsigned char s_dyn[];
-    trace_begin(trace);
+    static_assert(GF == 16, "the packed per-frame counters assume 16 frames per chunk");
+    trace_begin(a.trace);
+    MapCtr *mc = a.mc; ChunkCtr *cc = a.cc;
+    // a retry was asked for by this chunk or an earlier one: stay side-effect free.  (An older
+    // chunk keeps running when a later chunk -- expanded concurrently -- raises the flag.)
+    if (__ldcg(&mc->abort) != 0u && a.seq >= __ldcg(&mc->abort_seq)) return;
     // The gate: the chunk may be applied only if the table keeps its load bound even when every
     // voxel of the chunk is new; otherwise nothing of it touches the table and the host grows the
-    // table and re-runs the chunk.  Every block takes the same decision from the same two numbers
+    // table and re-runs the chunk.  Every block takes the same decision from the same numbers
     // (the previous chunk has finished on this stream, so `count` is final until our last block).
     const u64 count0 = __ldcg(&mc->count);
-    if (count0 + __ldcg(&cc->n_unique) > table_limit) {
-        if (blockIdx.x == 0 && threadIdx.x == 0 && !__ldcg(&mc->abort)) raise_abort(mc, ABORT_TABLE, seq);
-        return;
+    {
+        u64 load = count0;
+        if (DEBUG) load = max(load, __ldcg(&mc->life_count));
+        if (load + __ldcg(&cc->n_unique) > a.table_limit) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) raise_abort(mc, ABORT_TABLE, a.seq);
+            return;
+        }
     }
-    CT *s_lane = reinterpret_cast<CT *>(s_dyn);
-    double *s_L = reinterpret_cast<double *>(s_lane + AP_Q * AP_ROW);
-    u64 *s_slot = reinterpret_cast<u64 *>(s_L + AP_Q);
-    unsigned short *s_mask = reinterpret_cast<unsigned short *>(s_slot + AP_Q);
-    unsigned char *s_cls = reinterpret_cast<unsigned char *>(s_mask + AP_Q);
-    __shared__ unsigned short s_ordA[AP_THREADS], s_ordB[AP_THREADS];
-    __shared__ u32 s_occ[GF], s_free[GF], s_new[GF], s_nA, s_nB, s_qn;
-    __shared__ u32 s_hist[AP_THREADS / 32][2 * GF];   // per warp: voxels updated as free / occupied in frame f
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    __shared__ u64 s_qkey[AP_WARPS][AP_QCAP];
+    __shared__ u32 s_qslot[AP_WARPS][AP_QCAP];
+    __shared__ u32 s_occ[GF], s_free[GF], s_new[GF];
+    __shared__ u32 s_dmax[GF], s_dgt10[GF], s_lifenew;
+    __shared__ u64 s_dlife[GF];
     __shared__ double s_sum[4][SUMT];
     __shared__ bool s_last;
-    static_assert(GF <= 16, "s_mask holds one bit per frame");
-    static_assert((AP_Q * AP_ROW * sizeof(CT)) % 8 == 0, "staging alignment");
-    if (__ldcg(&mc->abort)) return;
-    const u32 tid = threadIdx.x, lane = tid & 31;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 lt_mask = (1u << lane) - 1;
-    if (tid < GF) { s_occ[tid] = 0; s_free[tid] = 0; s_new[tid] = 0; }
-    if (tid == 0) { s_qn = 0; s_nA = 0; s_nB = 0; }
-    for (int q = tid; q < 4 * SUMT; q += AP_THREADS) (&s_sum[0][0])[q] = sum_tab[q];
-    for (int q = tid; q < (AP_THREADS / 32) * 2 * GF; q += AP_THREADS) (&s_hist[0][0])[q] = 0;
+    const DevParams &p = a.p;
+    if (tid < GF) { s_occ[tid] = 0; s_free[tid] = 0; s_new[tid] = 0; s_dmax[tid] = 0; s_dgt10[tid] = 0; s_dlife[tid] = 0; }
+    if (tid == 0) s_lifenew = 0;
+    for (int q = tid; q < 4 * SUMT; q += AP_THREADS) (&s_sum[0][0])[q] = a.sum_tab[q];
     __syncthreads();
-    u32 *hist = s_hist[tid >> 5];
-    u32 consumed = 0;                           // ring entries already applied (block-uniform)
+    u64 *qkey = s_qkey[warp]; u32 *qslot = s_qslot[warp];
+    constexpr int ROWW = ap_row_words<CT>();
+    constexpr int NV = (int)(sizeof(CT) * GF / 16);
+    u32 *my_row = reinterpret_cast<u32 *>(s_dyn) + ((size_t)warp * 32 + lane) * ROWW;   // this lane's staged counter lanes
+    CT *scnt = static_cast<CT *>(a.scnt);
     LocalAcc acc; acc_init(acc);
+    u32 pk_occ[4] = {0, 0, 0, 0}, pk_free[4] = {0, 0, 0, 0};     // byte f%4 of word f/4: voxels updated as occupied / free in frame f
+    u32 pk_rounds = 0;
+    u32 q_head = 0, q_tail = 0;                                   // warp-uniform ring positions
 
-    // steps 2 + 3 on ring entries [consumed, consumed + n_win); all threads call it
-    auto drain = [&](u32 n_win) {
-        {
-            const bool have = tid < n_win;
-            const u32 pos = (consumed + tid) & (AP_Q - 1);
-            const bool isA = have && s_cls[pos] != 0;
-            const u32 mA = __ballot_sync(0xffffffffu, isA), mB = __ballot_sync(0xffffffffu, have && !isA);
-            u32 bA = 0, bB = 0;
-            if (lane == 0) { if (mA) bA = atomicAdd(&s_nA, (u32)__popc(mA)); if (mB) bB = atomicAdd(&s_nB, (u32)__popc(mB)); }
-            bA = __shfl_sync(0xffffffffu, bA, 0); bB = __shfl_sync(0xffffffffu, bB, 0);
-            if (isA) s_ordA[bA + __popc(mA & lt_mask)] = (unsigned short)pos;
-            else if (have) s_ordB[bB + __popc(mB & lt_mask)] = (unsigned short)pos;
-        }
-        __syncthreads();
-        if (tid < n_win) {
-            const u32 nA = s_nA;
-            const u32 e = tid < nA ? s_ordA[tid] : s_ordB[tid - nA];
-            u32 todo = s_mask[e];
-            double Lv = s_L[e];
-            const CT *row = s_lane + e * AP_ROW;
-            while (todo) {
-                const int f = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const CT cf = row[f];
-                const u32 n_occ = Lane<CT>::n_occ(cf), n_free = Lane<CT>::n_free(cf);
-                Lv = apply_one(Lv, seq_avg(n_free, n_occ, s_sum, p), n_occ > 0, p);
-                // num_occupied / num_free of frame f (:562-567); lanes on the same (frame, kind) add once
-                const u32 bin = 2u * (u32)f + (n_occ > 0 ? 1u : 0u);
-                const u32 peers = __match_any_sync(__activemask(), bin);
-                if (lane == (u32)__ffs(peers) - 1) atomicAdd(&hist[bin], (u32)__popc(peers));
+    auto flush_packed = [&]() {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const u32 so = __reduce_add_sync(0xffffffffu, (pk_occ[w] >> (8 * b)) & 0xffu);
+                const u32 sf = __reduce_add_sync(0xffffffffu, (pk_free[w] >> (8 * b)) & 0xffu);
+                if (lane == 0) { if (so) atomicAdd(&s_occ[4 * w + b], so); if (sf) atomicAdd(&s_free[4 * w + b], sf); }
             }
-            table[s_slot[e]].val = Lv;
+            pk_occ[w] = 0; pk_free[w] = 0;
         }
-        consumed += n_win;
-        __syncthreads();
-        if (tid == 0) { s_nA = 0; s_nB = 0; }
+        pk_rounds = 0;
     };
 
-    const u32 n_tiles = n_slots / AP_THREADS;
-    for (u32 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const u32 s = tile * AP_THREADS + tid;
-        const u64 key = __ldcg(&skeys[s]);
-        bool live = key != EMPTY_KEY;
-        if (!__syncthreads_or(live)) continue;
-        // ---- 1. entry -> registers, wipe, probe, per-frame counts, stage
-        CT c[GF];
-#pragma unroll
-        for (int f = 0; f < GF; ++f) c[f] = 0;
-        u64 slot = ~0ull; bool fresh = false; double L = 0.0;
-        if (live) {
+    // one round: lanes < n take the entries at the head of the queue
+    auto process = [&](u32 n) {
+        const bool have = lane < n;
+        const u32 qi = (q_head + lane) & (AP_QCAP - 1);
+        const u64 key = have ? qkey[qi] : 0ull;
+        const u32 s = have ? qslot[qi] : 0u;
+        q_head += n;
+        if (have) {
+            // ---- all loads of the entry first: counter lanes + home sector of the voxel (+ lifetime table)
             uint4 *cp = reinterpret_cast<uint4 *>(scnt + (size_t)s * GF);
-            constexpr int NV = (int)(sizeof(CT) * GF / 16);
             uint4 raw[NV];
 #pragma unroll
             for (int q = 0; q < NV; ++q) raw[q] = __ldcg(cp + q);
-            slot = table_find_or_insert(table, tmask, key, fresh, L);
-            if (slot == ~0ull) { atomicOr(&mc->err, ERR_TABLEFULL); live = false; }
-            skeys[s] = EMPTY_KEY;                                   // entry is ready for the next chunk
+            const u64 pair = table_home(key, a.tmask);
+            const ulonglong2 t0 = __ldcg(reinterpret_cast<const ulonglong2 *>(&a.table[pair]));
+            const ulonglong2 t1 = __ldcg(reinterpret_cast<const ulonglong2 *>(&a.table[pair + 1]));
+            ulonglong2 l0 = make_ulonglong2(0ull, 0ull), l1 = l0;
+            if (DEBUG) {
+                l0 = __ldcg(reinterpret_cast<const ulonglong2 *>(&a.life[pair]));
+                l1 = __ldcg(reinterpret_cast<const ulonglong2 *>(&a.life[pair + 1]));
+            }
+            // ---- the entry is ready for the next chunk
+            a.skeys[s] = EMPTY_KEY;
 #pragma unroll
             for (int q = 0; q < NV; ++q) cp[q] = make_uint4(0u, 0u, 0u, 0u);
+            // ---- frames that saw the voxel at all / occupied (occupied has priority, :544-545); stage the lanes
+            u32 m_occ = 0, m_any = 0;
 #pragma unroll
             for (int q = 0; q < NV; ++q) {
+                reinterpret_cast<uint4 *>(my_row)[q] = raw[q];
+                const u32 w[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
                 if (sizeof(CT) == 4) {
-                    c[4 * q] = (CT)raw[q].x; c[4 * q + 1] = (CT)raw[q].y; c[4 * q + 2] = (CT)raw[q].z; c[4 * q + 3] = (CT)raw[q].w;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        m_any |= (w[j] != 0u ? 1u : 0u) << (4 * q + j);
+                        m_occ |= ((w[j] >> 16) != 0u ? 1u : 0u) << (4 * q + j);
+                    }
                 } else {
-                    c[2 * q] = (CT)(((u64)raw[q].y << 32) | raw[q].x); c[2 * q + 1] = (CT)(((u64)raw[q].w << 32) | raw[q].z);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        m_any |= ((w[2 * j] | w[2 * j + 1]) != 0u ? 1u : 0u) << (2 * q + j);
+                        m_occ |= (w[2 * j + 1] != 0u ? 1u : 0u) << (2 * q + j);
+                    }
+                }
+            }
+            if (m_any) {
+                bool fresh; double L;
+                const u64 slot = table_resolve(a.table, a.tmask, key, pair, t0, t1, fresh, L);
+                if (slot == ~0ull) atomicOr(&mc->err, ERR_TABLEFULL);
+                else {
+                    if (fresh) atomicAdd(&s_new[__ffs(m_any) - 1], 1u);       // len(voxels) grows at the first frame that touched it
+                    u64 life = 0, lslot = 0;
+                    if (DEBUG) {
+                        bool lfresh; double lv;
+                        lslot = table_resolve(a.life, a.tmask, key, pair, l0, l1, lfresh, lv);
+                        if (lslot == ~0ull) atomicOr(&mc->err, ERR_TABLEFULL);
+                        else { life = lfresh ? 0ull : (u64)__double_as_longlong(lv); if (lfresh) atomicAdd(&s_lifenew, 1u); }
+                    }
+                    const CT *row = reinterpret_cast<const CT *>(my_row);
+                    u32 todo = m_any;
+                    while (todo) {                                              // only the frames that touched the voxel, in order
+                        const int f = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const CT cf = row[f];
+                        const u32 n_occ = Lane<CT>::n_occ(cf), n_free = Lane<CT>::n_free(cf);
+                        L = apply_one(L, seq_avg(n_free, n_occ, s_sum, p), n_occ > 0, p);
+                        if (DEBUG) {
+                            const u32 nn = n_occ + n_free;                      // frame_update_counts[key] (:550)
+                            life += nn;                                         // voxel_update_counts[key] (:551)
+                            atomicMax(&s_dmax[f], nn);
+                            if (nn > 10u) atomicAdd(&s_dgt10[f], 1u);
+                            atomicMax(&s_dlife[f], life);
+                        }
+                    }
+                    a.table[slot].val = L;
+                    if (DEBUG) {
+                        if (lslot != ~0ull) a.life[lslot].val = __longlong_as_double((long long)life);
+                        const CT last = row[a.g - 1];                           // frame_update_counts of the chunk's last frame
+                        if (last != 0) {
+                            const u32 at = atomicAdd(a.last_n, 1u);
+                            if (at < a.last_cap) a.last[at] = make_ulonglong2(key, (u64)(Lane<CT>::n_occ(last) + Lane<CT>::n_free(last)));
+                        }
+                    }
+                    acc_key(acc, key);
+                    // num_occupied / num_free of every frame that touched the voxel (:562-567)
+                    const u32 m_free = m_any & ~m_occ;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) { pk_occ[w] += spread4(m_occ >> (4 * w)); pk_free[w] += spread4(m_free >> (4 * w)); }
                 }
             }
         }
-        u32 mask = 0; bool any_occ = false;
-        if (live) {
+        if (++pk_rounds == 255u) flush_packed();
+    };
+
+    const u32 n_strips = a.n_slots / AP_STRIP;
+    u32 strip = blockIdx.x * AP_WARPS + warp;
+    bool more = strip < n_strips;
+    for (;;) {
+        if (more) {
+            const u32 s0 = strip * AP_STRIP;
+            u64 k[AP_SCAN];
 #pragma unroll
-            for (int f = 0; f < GF; ++f) {
-                if (f < g && c[f] != 0) {
-                    mask |= 1u << f;
-                    any_occ |= Lane<CT>::n_occ(c[f]) > 0;               // occupied has priority (:544-545)
+            for (int j = 0; j < AP_SCAN; ++j) k[j] = __ldcg(&a.skeys[s0 + j * 32 + lane]);
+#pragma unroll
+            for (int j = 0; j < AP_SCAN; ++j) {
+                const bool live = k[j] != EMPTY_KEY;
+                const u32 m = __ballot_sync(0xffffffffu, live);
+                if (live) {
+                    const u32 qi = (q_tail + __popc(m & lt_mask)) & (AP_QCAP - 1);
+                    qkey[qi] = k[j]; qslot[qi] = s0 + j * 32 + lane;
                 }
+                q_tail += __popc(m);
             }
+            strip += gridDim.x * AP_WARPS;
+            more = strip < n_strips;
+            __syncwarp();
         }
-        live = live && mask != 0;
-        {
-            const u32 m_live = __ballot_sync(0xffffffffu, live);
-            u32 at = 0;
-            if (lane == 0 && m_live) at = atomicAdd(&s_qn, (u32)__popc(m_live));
-            at = __shfl_sync(0xffffffffu, at, 0);
-            if (live) {
-                const u32 pos = (at + __popc(m_live & lt_mask)) & (AP_Q - 1);
-#pragma unroll
-                for (int f = 0; f < GF; ++f) s_lane[pos * AP_ROW + f] = c[f];
-                s_L[pos] = L; s_slot[pos] = slot; s_mask[pos] = (unsigned short)mask;
-                s_cls[pos] = (any_occ && p.adaptive) ? 1 : 0;
-                if (fresh) atomicAdd(&s_new[__ffs(mask) - 1], 1u);   // len(voxels) grows at the first frame that touched it
-                acc_key(acc, key);
-            }
+        u32 avail = q_tail - q_head;
+        while (avail >= 32u || (!more && avail > 0u)) {          // full rounds; the last one may be ragged
+            const u32 n = min(avail, 32u);
+            process(n);
+            avail -= n;
         }
-        __syncthreads();
-        // every thread reads the fill before the next barrier, and nobody appends before that barrier
-        if (*(volatile u32 *)&s_qn - consumed >= (u32)AP_THREADS) drain(AP_THREADS);
+        __syncwarp();
+        if (!more) break;
     }
-    __syncthreads();
-    {
-        const u32 left = *(volatile u32 *)&s_qn - consumed;
-        if (left) drain(left);
-    }
+    flush_packed();
     acc_publish(acc, mc, false);
     __syncthreads();
-    if (tid < 2 * GF) {
-        u32 sum = 0;
-        for (int w = 0; w < AP_THREADS / 32; ++w) sum += s_hist[w][tid];
-        if (tid & 1) s_occ[tid >> 1] = sum; else s_free[tid >> 1] = sum;
-    }
-    __syncthreads();
-    if (tid < (u32)g) {
+    if (tid < (u32)a.g) {
         const int f = tid;
-        if (s_occ[f]) atomicAdd(&st[f].n_occ, (u64)s_occ[f]);
-        if (s_free[f]) atomicAdd(&st[f].n_free, (u64)s_free[f]);
+        if (s_occ[f]) atomicAdd(&a.st[f].n_occ, (u64)s_occ[f]);
+        if (s_free[f]) atomicAdd(&a.st[f].n_free, (u64)s_free[f]);
         if (s_new[f]) atomicAdd(&cc->neu[f], s_new[f]);
+        if (DEBUG) {
+            if (s_dmax[f]) atomicMax(&cc->dmax[f], s_dmax[f]);
+            if (s_dgt10[f]) atomicAdd(&cc->dgt10[f], s_dgt10[f]);
+            if (s_dlife[f]) atomicMax(&cc->dlife[f], s_dlife[f]);
+        }
     }
+    if (DEBUG && tid == 0 && s_lifenew) atomicAdd(&cc->life_new, s_lifenew);
     // last block out: len(voxels) after each frame (:592), publish the new count, re-arm the chunk
     __syncthreads();
-    trace_end(trace);
+    trace_end(a.trace);
     if (tid == 0) {
         __threadfence();
         const u32 t = atomicAdd(&cc->ticket, 1u);
@@ -1022,10 +1116,23 @@ k_apply_chunk(u64 *__restrict__ skeys, CT *__restrict__ scnt, u32 n_slots, int g
     if (s_last && tid == 0) {
         __threadfence();
         u64 run = count0;
-        for (int f = 0; f < g; ++f) {
+        u64 lmax = DEBUG ? __ldcg(&mc->life_max) : 0ull;
+        for (int f = 0; f < a.g; ++f) {
             run += atomicAdd(&cc->neu[f], 0u);
-            st[f].n_voxels = run;
+            a.st[f].n_voxels = run;
             cc->neu[f] = 0;
+            if (DEBUG) {
+                lmax = max(lmax, (u64)atomicMax(&cc->dlife[f], 0ull));
+                a.st[f].max_in_frame = atomicMax(&cc->dmax[f], 0u);
+                a.st[f].n_gt10 = atomicAdd(&cc->dgt10[f], 0u);
+                a.st[f].max_total = lmax;                               // max(voxel_update_counts.values()) (:578)
+                cc->dmax[f] = 0; cc->dgt10[f] = 0; cc->dlife[f] = 0;
+            }
+        }
+        if (DEBUG) {
+            mc->life_max = lmax;
+            mc->life_count = __ldcg(&mc->life_count) + atomicAdd(&cc->life_new, 0u);
+            cc->life_new = 0;
         }
         mc->last_new = (u32)(run - count0);
         mc->last_unique = atomicAdd(&cc->n_unique, 0u);
@@ -1207,7 +1314,8 @@ __global__ void k_clear_abort(MapCtr *mc, ChunkCtr *cc)
     mc->abort = 0; mc->abort_seq = ~0ull;
     for (int b = 0; b < N_CHUNK_BUF; ++b) {
         cc[b].n_unique = 0; cc[b].ticket = 0; cc[b].xticket = 0; cc[b].mticket = 0;
-        for (int f = 0; f < GF; ++f) cc[b].neu[f] = 0;
+        cc[b].life_new = 0;
+        for (int f = 0; f < GF; ++f) { cc[b].neu[f] = 0; cc[b].dmax[f] = 0; cc[b].dgt10[f] = 0; cc[b].dlife[f] = 0; }
     }
 }
 
@@ -1236,9 +1344,9 @@ __global__ void k_apply_direct(const u64 *__restrict__ keys, const double *__res
         const u64 slot = table_find_or_insert(table, tmask, key, fresh, L);
         if (slot == ~0ull) atomicOr(&mc->err, ERR_TABLEFULL);
         else {
+            // (bounds: the reference extends them with the caller's raw point, :113-115 -- the host keeps those)
             table[slot].val = apply_one(L, delta[i], adaptive[i] != 0, p);
             if (fresh) ++acc.n_new;
-            acc_key(acc, key);
         }
     }
     acc_publish(acc, mc, true);
@@ -1255,9 +1363,8 @@ __global__ void k_load(const u64 *__restrict__ keys, const double *__restrict__ 
         const u64 slot = table_find_or_insert(table, tmask, key, fresh, L);
         if (slot == ~0ull) atomicOr(&mc->err, ERR_TABLEFULL);
         else {
-            table[slot].val = vals[i];
+            table[slot].val = vals[i];                     // a direct dict write: no bounds (:113-115 are update_voxel only)
             if (fresh) ++acc.n_new;
-            acc_key(acc, key);
         }
     }
     acc_publish(acc, mc, true);
@@ -1356,8 +1463,22 @@ __global__ void k_mono16_to_u8(const uint16_t *__restrict__ in, uint8_t *__restr
 
 __global__ void k_reset_ctr(MapCtr *mc)
 {
+    // (life_count / life_max stay: reset_map does not clear voxel_update_counts, 3d_mapper.py:644-650)
     mc->count = 0; mc->err = 0; mc->abort = 0; mc->abort_seq = ~0ull; mc->last_new = 0; mc->last_unique = 0;
     for (int q = 0; q < 3; ++q) { mc->kmin[q] = INT_MAX; mc->kmax[q] = INT_MIN; }
+}
+
+__global__ void k_init_life_ctr(MapCtr *mc) { mc->life_count = 0; mc->life_max = 0; }
+
+// compact the lifetime table into {key, count} pairs (debug view voxel_update_counts)
+__global__ void k_dump_life(const Slot *__restrict__ life, u64 n_slots, ulonglong2 *out, u64 out_cap, u64 *cursor)
+{
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n_slots; i += (u64)gridDim.x * blockDim.x) {
+        const ulonglong2 raw = *reinterpret_cast<const ulonglong2 *>(&life[i]);
+        if (raw.x == EMPTY_KEY) continue;
+        const u64 at = atomicAdd(cursor, 1ull);
+        if (at < out_cap) out[at] = raw;
+    }
 }
 
 // ------------------------------------------------------------------------------------ host
@@ -1445,6 +1566,7 @@ struct s3d_map {
     u64 route_seq = 0;               // chunks routed so far (the same on every rank)
     u64 route_timeout_ns = 30000000000ull;   // S3D_ROUTE_TIMEOUT_MS
     int lookahead_env = 0;           // S3D_LOOKAHEAD (experiments)
+    u64 scratch_env = 0;             // S3D_SCRATCH_CAP: first size of the chunk dedupe tables (tests force retries with a tiny one)
     int bpb_env = 0;                 // S3D_BEAMS_PER_BLOCK (experiments)
     // S3D_TRACE: per chunk 5 x {start, end}: ack wait, expand, flag wait, merge, apply
     DevBuf<u64> trace; static constexpr u64 TRACE_CHUNKS = 4096; static constexpr int TRACE_W = 10;
@@ -1489,6 +1611,11 @@ struct s3d_map {
     // export staging
     DevBuf<double> ex_xyz, ex_prob, ex_L; DevBuf<int8_t> ex_cls; DevBuf<int> ex_ijk; DevBuf<float4> ex_f32;
     u64 *ex_counts = nullptr; u64 *ex_counts_host = nullptr; u64 ex_n = 0; bool ex_valid = false;
+    // debug counters: lifetime sample counts per voxel key + the last frame's per-key counts
+    bool debug_on = false;
+    Slot *life = nullptr;            // same capacity / probing as the voxel table; val holds a u64 count
+    DevBuf<ulonglong2> dbg_last; u32 *dbg_last_n = nullptr;
+    int apply_bps = 3;               // k_apply_chunk blocks per SM (S3D_APPLY_BPS)
     // measurement
     bool prof_on = false;
     std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
@@ -1511,7 +1638,7 @@ int preload_pipeline_kernels()
     int rc;
     if ((rc = preload(k_expand<u32, false, true>)) || (rc = preload(k_expand<u32, true, true>)) ||
         (rc = preload(k_expand<u64, false, true>)) || (rc = preload(k_expand<u32, false, false>)) ||
-        (rc = preload(k_apply_chunk<u32>)) || (rc = preload(k_apply_chunk<u64>)) ||
+        (rc = preload(k_apply_chunk<u32, false>)) || (rc = preload(k_apply_chunk<u64, false>)) ||
         (rc = preload(k_route_signal)) || (rc = preload(k_route_wait)) ||
         (rc = preload(k_route_merge<u32, true>)) || (rc = preload(k_route_merge<u32, false>)) ||
         (rc = preload(k_route_merge<u64, false>)) ||
@@ -1601,6 +1728,22 @@ int grow_table(s3d_map *m, u64 new_cap)
         CU(cudaStreamSynchronize(m->stream));
         CU(cudaFree(m->table));
         ++m->n_grows;
+    }
+    if (m->debug_on) {
+        // the lifetime table keeps the voxel table's geometry
+        Slot *nl = nullptr;
+        e = cudaMalloc(&nl, new_cap * sizeof(Slot));
+        if (e != cudaSuccess) { cudaFree(nt); return fail(S3D_ETABLEFULL, "cannot grow the debug-counter table to %llu slots: %s",
+                                                          (unsigned long long)new_cap, cudaGetErrorString(e)); }
+        if ((rc = launch_fill_table(m, nl, new_cap))) return rc;
+        if (m->life) {
+            const int blocks = (int)std::min<u64>((m->cap + 255) / 256, (u64)m->n_sm * 16);
+            k_rehash<<<blocks, 256, 0, m->stream>>>(m->life, m->cap, nl, new_cap - 1, m->mc);
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(m->stream));
+            CU(cudaFree(m->life));
+        }
+        m->life = nl;
     }
     m->table = nt; m->cap = new_cap;
     m->ex_valid = false;
@@ -1726,18 +1869,22 @@ u64 *trace_slot(s3d_map *m, int which)
 
 void launch_apply(s3d_map *m, u64 *skeys, void *scnt, int g, ChunkCtr *cc, DevStats *st, cudaStream_t stream)
 {
-    // up to three blocks per SM, every block with the same number of tiles (measured at cfg2: 3 tiles
-    // per block -- dense update steps, few apply warps competing with k_expand -- beats 4, 2 and 1)
-    const u64 tiles = m->scratch_cap / AP_THREADS, resident = (u64)m->n_sm * 3;
-    const int blocks = (int)(tiles / ((tiles + resident - 1) / resident));
-    if (m->wide)
-        k_apply_chunk<u64><<<blocks, AP_THREADS, apply_smem_bytes<u64>(), stream>>>(skeys, static_cast<u64 *>(scnt), (u32)m->scratch_cap, g, cc, st,
-                                                             m->table, m->cap - 1, m->p, m->sum_tab.p, m->mc, table_limit(m),
-                                                             m->chunk_seq, trace_slot(m, 4));
-    else
-        k_apply_chunk<u32><<<blocks, AP_THREADS, apply_smem_bytes<u32>(), stream>>>(skeys, static_cast<u32 *>(scnt), (u32)m->scratch_cap, g, cc, st,
-                                                             m->table, m->cap - 1, m->p, m->sum_tab.p, m->mc, table_limit(m),
-                                                             m->chunk_seq, trace_slot(m, 4));
+    // autonomous warps, AP_STRIP slots per scan step; up to `apply_bps` blocks per SM
+    const u64 strips = m->scratch_cap / AP_STRIP;
+    const int blocks = (int)std::max<u64>(1, std::min<u64>((strips + AP_WARPS - 1) / AP_WARPS, (u64)m->n_sm * (u64)m->apply_bps));
+    ApplyArgs a;
+    a.skeys = skeys; a.scnt = scnt; a.n_slots = (u32)m->scratch_cap; a.g = g; a.cc = cc; a.st = st;
+    a.table = m->table; a.tmask = m->cap - 1; a.p = m->p; a.sum_tab = m->sum_tab.p; a.mc = m->mc;
+    a.table_limit = table_limit(m); a.seq = m->chunk_seq; a.trace = trace_slot(m, 4);
+    a.life = m->life; a.last = m->dbg_last.p; a.last_n = m->dbg_last_n; a.last_cap = (u32)std::min<size_t>(m->dbg_last.n, 0xffffffffu);
+    if (m->debug_on) {
+        cudaMemsetAsync(m->dbg_last_n, 0, sizeof(u32), stream);      // the list restarts with every chunk: it ends up holding the last frame
+        if (m->wide) k_apply_chunk<u64, true><<<blocks, AP_THREADS, apply_smem_bytes<u64>(), stream>>>(a);
+        else k_apply_chunk<u32, true><<<blocks, AP_THREADS, apply_smem_bytes<u32>(), stream>>>(a);
+    } else {
+        if (m->wide) k_apply_chunk<u64, false><<<blocks, AP_THREADS, apply_smem_bytes<u64>(), stream>>>(a);
+        else k_apply_chunk<u32, false><<<blocks, AP_THREADS, apply_smem_bytes<u32>(), stream>>>(a);
+    }
     m->launches += 1;
 }
 
@@ -2006,24 +2153,49 @@ int check_ready(s3d_map *m)
     return 0;
 }
 
+void stats_to_abi(const DevStats &s, s3d_frame_stats &o)
+{
+    o.num_occupied = (int64_t)s.n_occ; o.num_free = (int64_t)s.n_free;
+    o.num_voxels = (int64_t)s.n_voxels; o.num_samples = (int64_t)s.n_samples;
+    o.max_samples_per_voxel = (int64_t)s.max_in_frame; o.num_voxels_gt10 = (int64_t)s.n_gt10;
+    o.max_total_samples = (int64_t)s.max_total; o.reserved = 0;
+}
+
 int finish_stats(s3d_map *m, const DevStats *stats_dev, int64_t n, s3d_frame_stats *out)
 {
-    int rc = sync_counters(m);
-    if (rc) return rc;
-    if (!out) return 0;
-    if (m->stats_host_n < (size_t)n) {
+    if (out && m->stats_host_n < (size_t)n) {
         if (m->stats_host) cudaFreeHost(m->stats_host);
         m->stats_host = nullptr; m->stats_host_n = 0;
         CU(cudaMallocHost(&m->stats_host, sizeof(DevStats) * (size_t)n));
         m->stats_host_n = (size_t)n;
     }
+    // Fast path (every single-frame call takes it): all frames are enqueued, so the map counters
+    // and the per-frame counters are copied behind the last apply and one synchronisation ends the
+    // call.  Only a chunk that asked for a retry falls through to the general drain.
+    bool all_enqueued = !m->jobs.empty();
+    for (const Job &j : m->jobs) if (j.next < j.n) all_enqueued = false;
+    if (all_enqueued) {
+        CU(cudaMemcpyAsync(m->mc_host, m->mc, sizeof(MapCtr), cudaMemcpyDeviceToHost, m->stream));
+        if (out) CU(cudaMemcpyAsync(m->stats_host, stats_dev, sizeof(DevStats) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+        CU(cudaStreamSynchronize(m->stream));
+        if (!m->mc_host->abort) {
+            m->count_known = m->mc_host->count;
+            m->unique_est = std::max<u64>(m->unique_est, m->mc_host->last_unique);
+            m->snap_floor = m->chunk_seq;
+            for (Job &j : m->jobs) if (j.done_ev) m->job_ev_pool.push_back(j.done_ev);
+            m->jobs.clear();
+            int rc = fatal_from_flags(m, m->mc_host->err);
+            if (rc) return rc;
+            if (out) for (int64_t f = 0; f < n; ++f) stats_to_abi(m->stats_host[f], out[f]);
+            return 0;
+        }
+    }
+    int rc = sync_counters(m);
+    if (rc) return rc;
+    if (!out) return 0;
     CU(cudaMemcpyAsync(m->stats_host, stats_dev, sizeof(DevStats) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
     CU(cudaStreamSynchronize(m->stream));
-    for (int64_t f = 0; f < n; ++f) {
-        const DevStats &s = m->stats_host[f];
-        out[f].num_occupied = (int64_t)s.n_occ; out[f].num_free = (int64_t)s.n_free;
-        out[f].num_voxels = (int64_t)s.n_voxels; out[f].num_samples = (int64_t)s.n_samples;
-    }
+    for (int64_t f = 0; f < n; ++f) stats_to_abi(m->stats_host[f], out[f]);
     return 0;
 }
 
@@ -2078,6 +2250,8 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
     { const char *e = getenv("S3D_WIDE_LANES"); m->wide = e && atoi(e) != 0; }
     { const char *e = getenv("S3D_LOOKAHEAD"); if (e) m->lookahead_env = atoi(e); }
     { const char *e = getenv("S3D_BEAMS_PER_BLOCK"); if (e) m->bpb_env = atoi(e); }
+    { const char *e = getenv("S3D_APPLY_BPS"); if (e && atoi(e) > 0) m->apply_bps = std::min(atoi(e), 8); }
+    { const char *e = getenv("S3D_SCRATCH_CAP"); if (e && atoll(e) > 0) m->scratch_env = (u64)atoll(e); }
     if (const char *e = getenv("S3D_TRACE")) if (atoi(e) != 0) {
         if (m->trace.ensure(s3d_map::TRACE_CHUNKS * s3d_map::TRACE_W)) return S3D_ENOMEM;
         std::vector<u64> init(s3d_map::TRACE_CHUNKS * s3d_map::TRACE_W);
@@ -2095,6 +2269,9 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
     CU(cudaMalloc(&m->ex_counts, sizeof(u64) * 4));
     CU(cudaMallocHost(&m->ex_counts_host, sizeof(u64) * 4));
     k_reset_ctr<<<1, 1, 0, m->stream>>>(m->mc);
+    k_init_life_ctr<<<1, 1, 0, m->stream>>>(m->mc);
+    CU(cudaMalloc(&m->dbg_last_n, sizeof(u32)));
+    CU(cudaMemsetAsync(m->dbg_last_n, 0, sizeof(u32), m->stream));
     int rc = grow_table(m, initial_capacity ? initial_capacity : (1ull << 22));
     if (rc) { s3d_destroy(m); return rc; }
     CU(cudaStreamSynchronize(m->stream));
@@ -2108,6 +2285,9 @@ int s3d_destroy(s3d_map *m)
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->table) cudaFree(m->table);
+    if (m->life) cudaFree(m->life);
+    if (m->dbg_last_n) cudaFree(m->dbg_last_n);
+    m->dbg_last.release();
     if (m->mc) cudaFree(m->mc);
     if (m->mc_host) cudaFreeHost(m->mc_host);
     if (m->snap_host) cudaFreeHost(m->snap_host);
@@ -2246,8 +2426,8 @@ int s3d_set_tables(s3d_map *m, const s3d_tables *t)
     CU(cudaFuncSetAttribute(k_expand<u32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
     CU(cudaFuncSetAttribute(k_expand<u32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
     CU(cudaFuncSetAttribute(k_expand<u64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
-    CU(cudaFuncSetAttribute(k_apply_chunk<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes<u64>()));
-    CU(cudaFuncSetAttribute(k_apply_chunk<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes<u32>()));
+    CU(cudaFuncSetAttribute(k_apply_chunk<u64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes<u64>()));
+    CU(cudaFuncSetAttribute(k_apply_chunk<u64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes<u64>()));
     m->h_range.assign(t->range_m, t->range_m + H);
     m->h_nv_free.assign(t->nv_free, t->nv_free + H);
     m->h_nv_occ.assign(t->nv_occ, t->nv_occ + H);
@@ -2256,7 +2436,7 @@ int s3d_set_tables(s3d_map *m, const s3d_tables *t)
     // first guess for the chunk dedupe table; it doubles on demand (retry) from here
     // (a rank of a sharded map holds about 1/world of the entries; 1.5x margin, it doubles on demand)
     const u64 share = m->shard_world > 1 ? (m->samples_max / 4) * 3 / (2 * (u64)m->shard_world) : m->samples_max / 4;
-    return ensure_scratch(m, std::min<u64>(1u << 20, std::max<u64>(1u << 14, share)), false);
+    return ensure_scratch(m, m->scratch_env ? m->scratch_env : std::min<u64>(1u << 20, std::max<u64>(1u << 14, share)), false);
 }
 
 int s3d_ingest_batch_dev(s3d_map *m, const uint8_t *images_dev, int64_t n, const double *T_dev,
@@ -2390,11 +2570,7 @@ int s3d_ingest_collect(s3d_map *m, int ticket, s3d_frame_stats *out)
     if (out) {
         CU(cudaMemcpyAsync(s.stats_host, s.stats, sizeof(DevStats) * (size_t)s.n, cudaMemcpyDeviceToHost, m->ctl_stream));
         CU(cudaStreamSynchronize(m->ctl_stream));
-        for (int64_t f = 0; f < s.n; ++f) {
-            const DevStats &d = s.stats_host[f];
-            out[f].num_occupied = (int64_t)d.n_occ; out[f].num_free = (int64_t)d.n_free;
-            out[f].num_voxels = (int64_t)d.n_voxels; out[f].num_samples = (int64_t)d.n_samples;
-        }
+        for (int64_t f = 0; f < s.n; ++f) stats_to_abi(s.stats_host[f], out[f]);
     }
     s.busy = false;
     return 0;
@@ -2756,6 +2932,7 @@ int s3d_query(s3d_map *m, const int32_t *ijk, int64_t n, double *log_odds, uint8
     if (!m) return fail(S3D_EINVAL, "null map");
     if (n <= 0) return n == 0 ? 0 : fail(S3D_EINVAL, "n < 0");
     int rc = set_device(m); if (rc) return rc;
+    if ((rc = pump(m, true))) return rc;                 // a queued chunk may be waiting for a retry
     std::vector<u64> keys((size_t)n);
     std::vector<uint8_t> in_range((size_t)n, 1);
     for (int64_t i = 0; i < n; ++i) {
@@ -2802,6 +2979,7 @@ int s3d_clear(s3d_map *m)
 {
     if (!m) return fail(S3D_EINVAL, "null map");
     int rc = set_device(m); if (rc) return rc;
+    if ((rc = sync_counters(m))) return rc;              // queued frames (and pending retries) belong to the map being cleared
     if ((rc = launch_fill_table(m, m->table, m->cap))) return rc;
     k_reset_ctr<<<1, 1, 0, m->stream>>>(m->mc);
     CU(cudaGetLastError());
@@ -2857,6 +3035,100 @@ int s3d_export_read_xyzi32(s3d_map *m, float *xyzi, uint64_t n)
     CU(cudaMemcpyAsync(xyzi, m->ex_f32.p, sizeof(float4) * n, cudaMemcpyDeviceToHost, m->stream));
     CU(cudaStreamSynchronize(m->stream));
     return 0;
+}
+
+int s3d_extend_bounds(s3d_map *m, const int32_t kmin[3], const int32_t kmax[3])
+{
+    if (!m || !kmin || !kmax) return fail(S3D_EINVAL, "null argument");
+    int rc = set_device(m); if (rc) return rc;
+    if ((rc = sync_counters(m))) return rc;
+    MapCtr h = *m->mc_host;
+    for (int q = 0; q < 3; ++q) { h.kmin[q] = std::min(h.kmin[q], (int)kmin[q]); h.kmax[q] = std::max(h.kmax[q], (int)kmax[q]); }
+    CU(cudaMemcpyAsync(m->mc->kmin, h.kmin, sizeof h.kmin, cudaMemcpyHostToDevice, m->stream));
+    CU(cudaMemcpyAsync(m->mc->kmax, h.kmax, sizeof h.kmax, cudaMemcpyHostToDevice, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int s3d_reset_bounds(s3d_map *m)
+{
+    if (!m) return fail(S3D_EINVAL, "null map");
+    int rc = set_device(m); if (rc) return rc;
+    if ((rc = sync_counters(m))) return rc;
+    const int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+    CU(cudaMemcpyAsync(m->mc->kmin, lo, sizeof lo, cudaMemcpyHostToDevice, m->stream));
+    CU(cudaMemcpyAsync(m->mc->kmax, hi, sizeof hi, cudaMemcpyHostToDevice, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int s3d_debug_counters(s3d_map *m, int on)
+{
+    if (!m) return fail(S3D_EINVAL, "null map");
+    int rc = set_device(m); if (rc) return rc;
+    if ((rc = sync_counters(m))) return rc;
+    if (on && m->route_on) return fail(S3D_EINVAL, "debug counters are not available on a routed map");
+    if (on && !m->life) {
+        cudaError_t e = cudaMalloc(&m->life, m->cap * sizeof(Slot));
+        if (e != cudaSuccess) return fail(S3D_ENOMEM, "debug-counter table of %llu slots: %s", (unsigned long long)m->cap, cudaGetErrorString(e));
+        if ((rc = launch_fill_table(m, m->life, m->cap))) return rc;
+        CU(cudaStreamSynchronize(m->stream));
+    }
+    if (on && (rc = m->dbg_last.ensure(std::max<size_t>(m->scratch_cap, 1u << 12)))) return rc;
+    m->debug_on = on != 0;
+    return 0;
+}
+
+namespace {
+int unpack_pairs(s3d_map *m, const ulonglong2 *dev, u64 k, int32_t *ijk, uint64_t *counts)
+{
+    std::vector<ulonglong2> h((size_t)k);
+    CU(cudaMemcpyAsync(h.data(), dev, sizeof(ulonglong2) * (size_t)k, cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    for (u64 i = 0; i < k; ++i) {
+        int a, b, c; unpack_key(h[(size_t)i].x, a, b, c);
+        if (ijk) { ijk[3 * i] = a; ijk[3 * i + 1] = b; ijk[3 * i + 2] = c; }
+        if (counts) counts[i] = h[(size_t)i].y;
+    }
+    return 0;
+}
+}
+
+int s3d_debug_last_frame(s3d_map *m, int32_t *ijk, uint64_t *counts, uint64_t cap, uint64_t *n_out)
+{
+    if (!m || !n_out) return fail(S3D_EINVAL, "null argument");
+    *n_out = 0;
+    if (!m->debug_on) return 0;
+    int rc = set_device(m); if (rc) return rc;
+    if ((rc = sync_counters(m))) return rc;
+    u32 n = 0;
+    CU(cudaMemcpyAsync(&n, m->dbg_last_n, sizeof n, cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    n = (u32)std::min<u64>(n, m->dbg_last.n);
+    *n_out = n;
+    const u64 k = std::min<u64>(n, cap);
+    return k ? unpack_pairs(m, m->dbg_last.p, k, ijk, counts) : 0;
+}
+
+int s3d_debug_totals(s3d_map *m, int32_t *ijk, uint64_t *counts, uint64_t cap, uint64_t *n_out)
+{
+    if (!m || !n_out) return fail(S3D_EINVAL, "null argument");
+    *n_out = 0;
+    if (!m->life) return 0;
+    int rc = set_device(m); if (rc) return rc;
+    if ((rc = sync_counters(m))) return rc;
+    const u64 n = m->mc_host->life_count;
+    *n_out = n;
+    const u64 k = std::min<u64>(n, cap);
+    if (!k) return 0;
+    DevBuf<ulonglong2> outb; DevBuf<u64> cur;
+    if ((rc = outb.ensure((size_t)k)) || (rc = cur.ensure(1))) { outb.release(); cur.release(); return rc; }
+    cudaMemsetAsync(cur.p, 0, sizeof(u64), m->stream);
+    const int blocks = (int)std::min<u64>((m->cap + 255) / 256, (u64)m->n_sm * 8);
+    k_dump_life<<<blocks, 256, 0, m->stream>>>(m->life, m->cap, outb.p, k, cur.p);
+    rc = unpack_pairs(m, outb.p, k, ijk, counts);
+    outb.release(); cur.release();
+    return rc;
 }
 
 int s3d_trace_read(s3d_map *m, uint64_t *out, uint64_t max_chunks, uint64_t *n_chunks)

@@ -15,7 +15,6 @@ from __future__ import annotations
 
 import time
 from collections import defaultdict
-from collections.abc import Sequence
 from typing import Any, Dict, Iterator, List, Optional, Tuple
 
 import numpy as np
@@ -37,31 +36,72 @@ def _threshold_to_int(thr) -> int:
     return int(min(255.0, max(-1.0, np.floor(t))))
 
 
-class _PointProbSeq(Sequence):
-    """Read-only sequence of (point ndarray[3], probability) pairs over two device-exported
-    arrays: what get_occupied_voxels / get_all_voxels_classified return as Python lists in the
-    reference (:151, :178-182), without materialising one tuple per voxel up front."""
-
-    __slots__ = ("points", "probabilities")
+class _PointProbList(list):
+    """What get_occupied_voxels / get_all_voxels_classified return in the reference (:151,
+    :178-182): a real Python list of (point ndarray[3], probability) tuples -- `+`, `.append`,
+    slicing and iteration behave as there.  The device-exported arrays the tuples were cut from
+    stay reachable as `.points` (float64[n,3]) and `.probabilities` (float64[n]) for callers
+    that want them without the per-voxel objects."""
 
     def __init__(self, points: np.ndarray, probabilities: np.ndarray):
+        super().__init__(zip(points, probabilities.tolist()))
         self.points = points
         self.probabilities = probabilities
 
-    def __len__(self) -> int:
-        return len(self.probabilities)
 
-    def __getitem__(self, i):
-        if isinstance(i, slice):
-            return _PointProbSeq(self.points[i], self.probabilities[i])
-        return (self.points[i], float(self.probabilities[i]))
+class _CountView(defaultdict):
+    """voxel_update_counts / frame_update_counts (:307-308): a defaultdict(int) keyed by (i, j, k).
+    With `debug_counters` on it is refilled from the device's counters the first time it is read
+    after an ingest; otherwise it stays empty."""
 
-    def __iter__(self) -> Iterator[Tuple[np.ndarray, float]]:
-        for p, q in zip(self.points, self.probabilities.tolist()):
-            yield (p, q)
+    def __init__(self, fetch):
+        super().__init__(int)
+        self._fetch = fetch
+        self._stale = False
+
+    def _mark_stale(self):
+        self._stale = True
+
+    def _refresh(self):
+        if self._stale:
+            self._stale = False
+            ijk, cnt = self._fetch()
+            dict.clear(self)
+            dict.update(self, zip(map(tuple, ijk.tolist()), cnt.tolist()))
+
+    def __len__(self):
+        self._refresh(); return dict.__len__(self)
+
+    def __iter__(self):
+        self._refresh(); return dict.__iter__(self)
+
+    def __contains__(self, key):
+        self._refresh(); return dict.__contains__(self, key)
+
+    def __getitem__(self, key):
+        self._refresh(); return defaultdict.__getitem__(self, key)
 
     def __eq__(self, other):
-        return list(self) == list(other)
+        self._refresh(); return dict.__eq__(self, other)
+
+    def __repr__(self):
+        self._refresh(); return defaultdict.__repr__(self)
+
+    def get(self, key, default=None):
+        self._refresh(); return dict.get(self, key, default)
+
+    def items(self):
+        self._refresh(); return dict.items(self)
+
+    def keys(self):
+        self._refresh(); return dict.keys(self)
+
+    def values(self):
+        self._refresh(); return dict.values(self)
+
+    def clear(self):
+        self._stale = False
+        dict.clear(self)
 
 
 class _VoxelView:
@@ -215,13 +255,29 @@ class SimpleOctree:
                 mx = np.maximum(mx, (kmax.astype(np.float64) + 0.5) * self.resolution)
         return mn, mx
 
+    # public and assignable as in the reference (:38-40); an assigned value replaces the bounds
+    # seen so far, later updates extend it again
     @property
     def min_bounds(self) -> np.ndarray:
         return self._bounds()[0]
 
+    @min_bounds.setter
+    def min_bounds(self, value):
+        self._assign_bounds(np.asarray(value, dtype=np.float64).reshape(3).copy(), None)
+
     @property
     def max_bounds(self) -> np.ndarray:
         return self._bounds()[1]
+
+    @max_bounds.setter
+    def max_bounds(self, value):
+        self._assign_bounds(None, np.asarray(value, dtype=np.float64).reshape(3).copy())
+
+    def _assign_bounds(self, mn, mx):
+        cur_mn, cur_mx = self._bounds()
+        self._pt_min = cur_mn if mn is None else mn
+        self._pt_max = cur_mx if mx is None else mx
+        self._native.reset_bounds()        # what the device has seen so far is folded into the host pair
 
     # -- export (:127-188) ----------------------------------------------------------------
     def _occupied_threshold(self, min_probability: float) -> float:
@@ -236,11 +292,11 @@ class SimpleOctree:
         thr = self._occupied_threshold(min_probability)
         return self._native.export(thr, -float("inf"), 1 << NativeMap.CLASS_OCCUPIED, want=want)
 
-    def get_occupied_voxels(self, min_probability: float = 0.5) -> Sequence:
+    def get_occupied_voxels(self, min_probability: float = 0.5) -> List[Tuple[np.ndarray, float]]:
         r = self._export_occupied(min_probability)
-        return _PointProbSeq(r["xyz"], r["prob"])
+        return _PointProbList(r["xyz"], r["prob"])
 
-    def get_all_voxels_classified(self, min_probability: float = 0.7) -> Dict[str, Sequence]:
+    def get_all_voxels_classified(self, min_probability: float = 0.7) -> Dict[str, List[Tuple[np.ndarray, float]]]:
         self._push_params()
         free_threshold = float(np.log(0.3 / 0.7))
         occupied_threshold = float(np.log(min_probability / (1.0 - min_probability)))
@@ -249,7 +305,7 @@ class SimpleOctree:
         for name, c in (("free", NativeMap.CLASS_FREE), ("unknown", NativeMap.CLASS_UNKNOWN),
                         ("occupied", NativeMap.CLASS_OCCUPIED)):
             sel = r["cls"] == c
-            out[name] = _PointProbSeq(r["xyz"][sel], r["prob"][sel])
+            out[name] = _PointProbList(r["xyz"][sel], r["prob"][sel])
         return out
 
     def clear(self):
@@ -320,9 +376,16 @@ class SonarTo3DMapper:
 
         self.frame_count = 0
         self.processed_frame_count = 0
-        # debug-only counters of the reference (:307-308); kept as (empty) attributes
-        self.voxel_update_counts = defaultdict(int)
-        self.frame_update_counts = defaultdict(int)
+        # debug counters of the reference (:307-308, :549-551, :575-585).  Extension key
+        # `debug_counters` (default False): when True the update kernel also counts
+        # samples per voxel, the two dicts below are served from the device, and the reference's
+        # every-10th-frame [DEBUG] text is printed; when False they stay empty and nothing is printed.
+        self.debug_counters = bool(c.get('debug_counters', False))
+        nat = self.octree._native
+        self.voxel_update_counts = _CountView(nat.debug_totals)
+        self.frame_update_counts = _CountView(nat.debug_last_frame)
+        if self.debug_counters:
+            nat.debug_counters(True)
         self.last_processing_time = 0.0
         self.total_processing_time = 0.0
         self.last_num_samples = 0
@@ -379,7 +442,8 @@ class SonarTo3DMapper:
         """uint8, C-contiguous image whose `> threshold` mask equals the input's (:407, :452)."""
         if polar_image.dtype == np.uint8:
             return np.ascontiguousarray(polar_image)
-        # other dtypes (the node always sends uint8): keep only what the algorithm reads
+        # other dtypes (the node always sends uint8): keep only what the algorithm reads -- a 0/255
+        # mask of `> threshold`, which the device's integer threshold t (0 <= t <= 255) reproduces
         return np.ascontiguousarray(np.where(polar_image > self.intensity_threshold, 255, 0).astype(np.uint8))
 
     def _check_width(self, bearing_bins: int):
@@ -401,26 +465,42 @@ class SonarTo3DMapper:
         T_sonar_to_world = T_base_to_world @ self.T_sonar_to_base
         self._sync_device_config(range_bins, bearing_bins)
         img = self._as_device_image(polar_image)
-        if img.dtype != polar_image.dtype:
+        if img.dtype != polar_image.dtype and _threshold_to_int(self.intensity_threshold) < 0:
+            # a negative threshold on a non-uint8 image: the 0/255 mask needs its own device threshold
             saved, self.octree._intensity_threshold = self.octree._intensity_threshold, 0
             self.octree._push_params()
-            n_occ, n_free, n_vox, n_samp = self.octree._native.ingest(img, T_sonar_to_world)
+            st = self.octree._native.ingest(img, T_sonar_to_world)
             self.octree._intensity_threshold = saved
         else:
-            n_occ, n_free, n_vox, n_samp = self.octree._native.ingest(img, T_sonar_to_world)
-        self.last_num_samples = n_samp
+            st = self.octree._native.ingest(img, T_sonar_to_world)
+        self.last_num_samples = st.num_samples
         processing_time = time.time() - start_time
         self.last_processing_time = processing_time
         self.total_processing_time += processing_time
+        if self.debug_counters:
+            self._debug_report(self.frame_count, st.num_samples, st.num_occupied + st.num_free,
+                               st.max_samples_per_voxel, st.max_total_samples, st.num_voxels_gt10)
         return {
             'frame_count': self.frame_count,
             'processed_count': self.processed_frame_count,
-            'num_occupied': n_occ,
-            'num_free': n_free,
-            'num_voxels': n_vox,
+            'num_occupied': st.num_occupied,
+            'num_free': st.num_free,
+            'num_voxels': st.num_voxels,
             'processing_time': processing_time,
             'avg_processing_time': self.total_processing_time / max(1, self.processed_frame_count),
         }
+
+    def _debug_report(self, frame_count: int, n_samples: int, n_keys: int, max_frame: int, max_total: int, n_gt10: int):
+        """The reference's debug statistics (:574-585).  frame_update_counts holds one entry per voxel
+        key of the frame, so its length is num_occupied + num_free and its sum the sample count."""
+        self.frame_update_counts._mark_stale()
+        self.voxel_update_counts._mark_stale()
+        if n_keys and frame_count % 10 == 0:
+            print(f"[DEBUG] Frame {frame_count}:")
+            print(f"  Max updates in frame: {max_frame}")
+            print(f"  Avg updates in frame: {n_samples / n_keys:.1f}")
+            print(f"  Max total updates: {max_total}")
+            print(f"  Voxels with >10 updates in frame: {n_gt10}")
 
     def _compose_scalar(self, positions, orientations) -> np.ndarray:
         out = np.empty((len(positions), 4, 4))
@@ -504,6 +584,11 @@ class SonarTo3DMapper:
         if n:
             self.last_processing_time = per
             self.last_num_samples = int(st['num_samples'][-1])
+            if self.debug_counters:
+                for f in range(n):
+                    self._debug_report(fc0 + f + 1, int(st['num_samples'][f]), occ[f] + fre[f],
+                                       int(st['max_samples_per_voxel'][f]), int(st['max_total_samples'][f]),
+                                       int(st['num_voxels_gt10'][f]))
         return out
 
     def process_sonar_images_mono16(self, polar_images_u16: np.ndarray, robot_positions, robot_orientations

@@ -36,6 +36,7 @@ import numpy as np
 RECORD_WORDS = 17      # include/sonar3d.h S3D_RECORD_WORDS: packed key + 16 frame counters
 CHUNK_FRAMES = 16      # include/sonar3d.h S3D_CHUNK_FRAMES
 KEY_BIAS = 1 << 20
+STATS_WORDS = 8       # int64 words per s3d_frame_stats (include/sonar3d.h)
 
 
 def pack_keys(ijk: np.ndarray) -> np.ndarray:
@@ -215,10 +216,10 @@ class CudaShardBackend:
         """replicate mode, inputs on the device: per-shard counters int64[n, 4] (device tensor)."""
         t = self.torch
         n = int(d_img.shape[0])
-        st = t.empty((n, 4), dtype=t.int64, device=self.device)
+        st = t.empty((n, STATS_WORDS), dtype=t.int64, device=self.device)
         self.native.ingest_batch_dev(d_img.data_ptr(), n, d_T.data_ptr(), want_stats=False, stats_dev_ptr=st.data_ptr())
         self.native.sync()
-        return st
+        return st[:, :4].contiguous()
 
     def ingest_owned_host(self, images: np.ndarray, T: np.ndarray):
         """replicate mode, host inputs (copies overlap the kernels inside the library)."""
@@ -243,11 +244,11 @@ class CudaShardBackend:
             mine[: hi - lo].copy_(t.from_numpy(images[lo:hi]), non_blocking=True)
         dist.all_gather_into_tensor(buf.view(-1), mine.reshape(-1), group=ex.group)
         d_T = t.from_numpy(np.ascontiguousarray(T, dtype=np.float64).reshape(-1, 16)).to(self.device, non_blocking=True)
-        st = t.empty((n, 4), dtype=t.int64, device=self.device)
+        st = t.empty((n, STATS_WORDS), dtype=t.int64, device=self.device)
         t.cuda.current_stream(self.device).synchronize()          # the map's kernels run on the library's own streams
         self.native.ingest_batch_dev(buf.data_ptr(), n, d_T.data_ptr(), want_stats=False, stats_dev_ptr=st.data_ptr())
         self.native.sync()
-        return st
+        return st[:, :4].contiguous()
 
     def upload(self, images: np.ndarray, T: np.ndarray):
         t = self.torch
@@ -257,7 +258,9 @@ class CudaShardBackend:
     def expand(self, d_img, d_T, f0: int, g: int):
         t = self.torch
         H, W = d_img.shape[1], d_img.shape[2]
-        st = t.zeros((g, 4), dtype=t.int64, device=self.device)
+        # (the library zeroes the buffer itself, on its own stream: torch must not race it with a fill)
+        st = t.empty((g, STATS_WORDS), dtype=t.int64, device=self.device)
+        t.cuda.current_stream(self.device).synchronize()
         ptr, counts = self.native.shard_expand(d_img.data_ptr() + f0 * H * W, d_T.data_ptr() + f0 * 128, g, st.data_ptr())
         n = sum(counts)
         if n:
@@ -268,7 +271,7 @@ class CudaShardBackend:
 
     def apply(self, recv, g: int):
         t = self.torch
-        st = t.zeros((g, 4), dtype=t.int64, device=self.device)
+        st = t.empty((g, STATS_WORDS), dtype=t.int64, device=self.device)
         t.cuda.current_stream(self.device).synchronize()          # the exchange wrote `recv` on torch's stream
         self.native.shard_apply(recv.data_ptr() if recv.shape[0] else 0, int(recv.shape[0]), g, st.data_ptr())
         return st[:, :3].clone()

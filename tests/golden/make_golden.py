@@ -249,6 +249,57 @@ def case_store(ref):
     print("store", len(keys), "voxels", edge_thr)
 
 
+def case_debug(ref):
+    """stdout of the reference ([DEBUG] block every 10th frame, :574-585; "Map reset", :650) and its two
+    debug dicts over 25 frames + reset_map + 12 frames (voxel_update_counts survives the reset)."""
+    cfg = dict(voxel_resolution=0.25, intensity_threshold=45, max_range=8.0)
+    images, pos, quat = seq_inputs(120, 96, 37, 31, cfg, step_m=0.04)
+    mapper = ref.SonarTo3DMapper(dict(cfg))
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        for f in range(25):
+            mapper.process_sonar_image(images[f], list(pos[f]), list(quat[f]))
+        mapper.reset_map()
+        for f in range(25, 37):
+            mapper.process_sonar_image(images[f], list(pos[f]), list(quat[f]))
+    fk = np.array(list(mapper.frame_update_counts.keys()), dtype=np.int32).reshape(-1, 3)
+    fv = np.array(list(mapper.frame_update_counts.values()), dtype=np.int64)
+    vk = np.array(list(mapper.voxel_update_counts.keys()), dtype=np.int32).reshape(-1, 3)
+    vv = np.array(list(mapper.voxel_update_counts.values()), dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "debug_counters.npz"), images=images, positions=pos, quaternions=quat,
+                        config_json=np.array(json.dumps(cfg)), stdout=np.array(buf.getvalue()),
+                        frame_keys=fk, frame_counts=fv, total_keys=vk, total_counts=vv, reset_after=np.array(25))
+    print("debug", len(buf.getvalue().splitlines()), "stdout lines;", len(fk), "frame keys,", len(vk), "total keys")
+
+
+def case_node(ref):
+    """Transcripts of the fake node (tests/fake_node.py: the node's exact call sequence) on the reference:
+    one session publishing PointCloud2, one publishing the classified CUBE_LIST markers."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import fake_node
+    cls = fake_node.load_mapper_class(REF_PATH)
+    cfg = fake_node.node_config(fake_node.NODE_PARAMS)
+    images, pos, quat = seq_inputs(160, 128, 23, 41, cfg, step_m=0.05)
+    rng = np.random.default_rng(7)
+    images16 = {f: (images[f].astype(np.uint16) << 8) | rng.integers(0, 256, size=images[f].shape, dtype=np.uint16)
+                for f in (3, 11)}
+    out = dict(images=images, positions=pos, quaternions=quat,
+               frames16=np.array(sorted(images16)), images16=np.stack([images16[f] for f in sorted(images16)]))
+    for name, free in (("cloud", False), ("markers", True)):
+        tr = quiet(fake_node.run_session, cls, images, images16, pos, quat, free)
+        out[f"{name}__log"] = np.array(json.dumps(tr["log"]))
+        out[f"{name}__n_clouds"] = np.array(len(tr["clouds"]))
+        for i, c in enumerate(tr["clouds"]):
+            out[f"{name}__cloud{i}"] = c
+        out[f"{name}__n_markers"] = np.array(len(tr["markers"]))
+        for i, m in enumerate(tr["markers"]):
+            out[f"{name}__marker{i}_meta"] = np.array(json.dumps({k: {"scale": v["scale"], "rgba": v["rgba"]} for k, v in m.items()}))
+            for k, v in m.items():
+                out[f"{name}__marker{i}_{k}"] = v["points"]
+        print("node", name, tr["log"][-1])
+    np.savez_compressed(os.path.join(HERE, "node_sessions.npz"), **out)
+
+
 if __name__ == "__main__":
     ref = load_reference()
     if len(sys.argv) > 1:
@@ -260,4 +311,6 @@ if __name__ == "__main__":
     case_store(ref)
     case_edges(ref)
     case_sequences(ref)
+    case_debug(ref)
+    case_node(ref)
     print("numpy", np.__version__)

@@ -324,3 +324,127 @@ def test_routed_map_ranks_in_one_process(world):
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "route_local_check.py")], env=env,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "route_local_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_cfg1_100_frames_single_and_batched_calls(s3d):
+    """north_star's parity target: BASELINE configs[0] (512 beams x 500 bins, library defaults) x 100
+    posed frames -- once through process_sonar_image (the reference's own call, one frame per
+    C-ABI call) and once through process_sonar_images (16-frame chunks, three in flight) -- against
+    the CPU oracle: per-frame counters exact, key set exact, |dL| <= 1e-5 (observed ~1e-15).
+    Spec: scripts/3d_mapper.py:485-595."""
+    from oracle.oracle import OracleMapper
+    from sonar_3d_reconstruction_b200 import synthetic
+    n = 100
+    images, pos, quat, cfg = synthetic.make_sequence("cfg1", n, seed=0)
+    cpu = OracleMapper(cfg)
+    want = [cpu.process_sonar_image(images[f], pos[f], quat[f]) for f in range(n)]
+    kc, vc = cpu.dump()
+    one = s3d.SonarTo3DMapper(cfg)
+    for f in range(n):
+        a = one.process_sonar_image(images[f], list(pos[f]), list(quat[f]))
+        assert _stats3(a) == _stats3(want[f]), f"single-frame call, frame {f}"
+        assert one.last_num_samples == want[f]["num_samples"]
+    assert assert_same_map(*one.octree.voxels.to_arrays(), kc, vc, LOGODDS_ATOL, "cfg1 x 100, single-frame calls") <= 1e-9
+    batch = s3d.SonarTo3DMapper(cfg)
+    got = batch.process_sonar_images(images, pos, quat)
+    assert [_stats3(x) for x in got] == [_stats3(x) for x in want]
+    assert assert_same_map(*batch.octree.voxels.to_arrays(), kc, vc, LOGODDS_ATOL, "cfg1 x 100, batched call") <= 1e-9
+    assert batch.get_point_cloud()["num_occupied"] == cpu.get_point_cloud()["num_occupied"]
+
+
+def test_retry_of_a_later_chunk_leaves_earlier_chunks_whole(s3d, monkeypatch):
+    """A chunk that asks for a retry (here: its dedupe table, forced tiny, overflows during k_expand) must
+    not stop the chunks before it, which are still being applied on the other streams: chunk 0 is small
+    and fits, chunks 1..3 overflow the 4096-entry table (twice: 4096 -> 8192 -> 16384) while chunk 0 is
+    in flight.  Counters and map must still equal the oracle's."""
+    from oracle.oracle import OracleMapper
+    from sonar_3d_reconstruction_b200 import synthetic
+    monkeypatch.setenv("S3D_SCRATCH_CAP", "4096")
+    spec = dict(H=200, W=128, seabed_depth=3.0, config=dict(voxel_resolution=0.1, intensity_threshold=40), step_m=0.05)
+    images, pos, quat, cfg = synthetic.make_sequence(spec, 64, seed=17)
+    images = images.copy()
+    images[:16] = 0
+    images[:16, 12, :] = 255                        # first hit at 0.6 m: a few hundred voxels per frame
+    for rep in range(3):                            # the race is timing dependent: a few tries
+        gpu, cpu = s3d.SonarTo3DMapper(cfg), OracleMapper(cfg)
+        got = gpu.process_sonar_images(images, pos, quat)
+        want = [cpu.process_sonar_image(images[f], pos[f], quat[f]) for f in range(len(images))]
+        assert [_stats3(x) for x in got] == [_stats3(x) for x in want], f"try {rep}"
+        assert assert_same_map(*gpu.octree.voxels.to_arrays(), *cpu.dump(), LOGODDS_ATOL, "retry") <= 1e-9
+        # the same through two pending asynchronous batches
+        gpu2 = s3d.SonarTo3DMapper(cfg)
+        h1 = gpu2.process_sonar_images_async(images[:40], pos[:40], quat[:40])
+        h2 = gpu2.process_sonar_images_async(images[40:], pos[40:], quat[40:])
+        got2 = h1.result() + h2.result()
+        assert [_stats3(x) for x in got2] == [_stats3(x) for x in want], f"async try {rep}"
+        assert assert_same_map(*gpu2.octree.voxels.to_arrays(), *cpu.dump(), LOGODDS_ATOL, "retry async") <= 1e-9
+
+
+def test_debug_counters_reproduce_the_reference_stdout(s3d, capsys):
+    """with debug_counters=True the every-10th-frame [DEBUG] block (scripts/3d_mapper.py:574-585),
+    "Map reset" (:650) and the two debug dicts equal the unmodified reference's, frame by frame and as one batch."""
+    g = load_golden("debug_counters")
+    cfg = dict(golden_config(g), debug_counters=True)
+    cut = int(g["reset_after"])
+    img, pos, quat = g["images"], g["positions"], g["quaternions"]
+    m = s3d.SonarTo3DMapper(cfg)
+    capsys.readouterr()
+    for f in range(cut):
+        m.process_sonar_image(img[f], list(pos[f]), list(quat[f]))
+    m.reset_map()
+    for f in range(cut, len(img)):
+        m.process_sonar_image(img[f], list(pos[f]), list(quat[f]))
+    assert capsys.readouterr().out == str(g["stdout"])
+    want_frame = dict(zip(map(tuple, g["frame_keys"].tolist()), g["frame_counts"].tolist()))
+    want_total = dict(zip(map(tuple, g["total_keys"].tolist()), g["total_counts"].tolist()))
+    assert dict(m.frame_update_counts) == want_frame
+    assert dict(m.voxel_update_counts) == want_total
+    assert max(m.voxel_update_counts.values()) == max(want_total.values()) and len(m.frame_update_counts) == len(want_frame)
+    # the batched call prints the same text
+    b = s3d.SonarTo3DMapper(cfg)
+    b.process_sonar_images(img[:cut], pos[:cut], quat[:cut])
+    b.reset_map()
+    b.process_sonar_images(img[cut:], pos[cut:], quat[cut:])
+    assert capsys.readouterr().out == str(g["stdout"])
+    assert dict(b.voxel_update_counts) == want_total and dict(b.frame_update_counts) == want_frame
+    # off by default: silent, dicts empty
+    q = s3d.SonarTo3DMapper(golden_config(g))
+    for f in range(10):
+        q.process_sonar_image(img[f], list(pos[f]), list(quat[f]))
+    assert capsys.readouterr().out == "" and len(q.voxel_update_counts) == 0 and not q.frame_update_counts
+
+
+def test_api_fidelity_lists_bounds_and_float_images(s3d):
+    """Return types and attribute behaviour of the reference: exports are real lists (:151, :178-182),
+    min/max_bounds are assignable (:38-40) and extended by later updates (:113-115), update_voxel bounds
+    follow the raw point, non-uint8 images are thresholded like uint8 ones (:407)."""
+    from sonar_3d_reconstruction_b200 import synthetic
+    images, pos, quat, cfg = synthetic.make_sequence(dict(H=120, W=96, config=dict(voxel_resolution=0.1)), 3, seed=2)
+    m = s3d.SonarTo3DMapper(cfg)
+    m.process_sonar_images(images[:2], pos[:2], quat[:2])
+    occ = m.octree.get_occupied_voxels(0.6)
+    assert type(occ + occ) is list and len(occ + occ) == 2 * len(occ)
+    occ.append((np.zeros(3), 0.5))
+    p0, q0 = occ[0]
+    assert isinstance(p0, np.ndarray) and p0.shape == (3,) and isinstance(q0, float)
+    cls = m.octree.get_all_voxels_classified(0.7)
+    assert isinstance(cls["free"], list) and isinstance(cls["unknown"] + cls["occupied"], list)
+    # bounds: assign, then extend
+    mn0, mx0 = m.octree.min_bounds.copy(), m.octree.max_bounds.copy()
+    m.octree.min_bounds = np.array([1e6, 1e6, 1e6])
+    m.octree.max_bounds = np.array([-1e6, -1e6, -1e6])
+    assert np.array_equal(m.octree.min_bounds, [1e6] * 3) and np.array_equal(m.octree.max_bounds, [-1e6] * 3)
+    m.octree.update_voxel(np.array([0.06, 0.06, 0.06]), 0.4)
+    assert np.array_equal(m.octree.max_bounds, [0.06] * 3) and np.array_equal(m.octree.min_bounds, [0.06] * 3)
+    m.process_sonar_image(images[2], list(pos[2]), list(quat[2]))
+    only = s3d.SonarTo3DMapper(cfg)
+    only.process_sonar_image(images[2], list(pos[2]), list(quat[2]))
+    assert np.array_equal(m.octree.min_bounds, np.minimum(0.06, only.octree.min_bounds))
+    assert np.array_equal(m.octree.max_bounds, np.maximum(0.06, only.octree.max_bounds))
+    assert (mn0 < mx0).all()
+    # float image == the uint8 image it came from
+    a, b = s3d.SonarTo3DMapper(cfg), s3d.SonarTo3DMapper(cfg)
+    sa = a.process_sonar_image(images[0], list(pos[0]), list(quat[0]))
+    sb = b.process_sonar_image(images[0].astype(np.float32) + 0.25, list(pos[0]), list(quat[0]))
+    assert _stats3(sa) == _stats3(sb)
+    assert_same_map(*a.octree.voxels.to_arrays(), *b.octree.voxels.to_arrays(), 0.0, "float image")

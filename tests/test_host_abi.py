@@ -33,15 +33,15 @@ def test_library_exports_every_declared_symbol():
     assert declared == exported, (declared ^ exported)
     assert set(_native.SYMBOLS) == declared
     lib = _native.load_library()                  # dlopen + argtypes; needs no GPU
-    assert lib.s3d_abi_version() == 1
-    assert "S3D_ABI_VERSION 1" in header
+    assert lib.s3d_abi_version() == 2
+    assert "S3D_ABI_VERSION 2" in header
 
 
 def test_struct_layouts_match_header():
     import ctypes as C
     from sonar_3d_reconstruction_b200 import _native
     assert C.sizeof(_native.Params) == 8 * 8 + 4 * 4
-    assert C.sizeof(_native.FrameStats) == 32 and _native.STATS_DTYPE.itemsize == 32
+    assert C.sizeof(_native.FrameStats) == 64 and _native.STATS_DTYPE.itemsize == 64
     assert C.sizeof(_native.Tables) == 6 * 4 + 8 * 8
     assert C.sizeof(_native.Profile) == 3 * 8 + 3 * 8 + 4 * 8
 

@@ -31,7 +31,7 @@ def main():
     T = maps[0].compose_transforms(pos, quat).reshape(n, 16)
     d_img = torch.from_numpy(images).cuda()
     d_T = torch.from_numpy(np.ascontiguousarray(T)).cuda()
-    stats = [torch.zeros((n, 4), dtype=torch.int64, device="cuda") for _ in range(world)]
+    stats = [torch.zeros((n, 8), dtype=torch.int64, device="cuda") for _ in range(world)]
     handles = []
     for r, m in enumerate(maps):
         m._check_width(W)
@@ -49,7 +49,7 @@ def main():
         g = min(16, n - f0)
         for r, m in enumerate(maps):
             m.octree._native.ingest_batch_dev(d_img.data_ptr() + f0 * H * W, g, d_T.data_ptr() + f0 * 128,
-                                              want_stats=False, stats_dev_ptr=stats[r].data_ptr() + f0 * 32)
+                                              want_stats=False, stats_dev_ptr=stats[r].data_ptr() + f0 * 64)
     for m in maps:
         m.octree._native.sync()
     tot = sum(s.cpu().numpy() for s in stats)

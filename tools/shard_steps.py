@@ -24,7 +24,7 @@ for s in range(steps):
     f0 = s * n_step
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
-    st = torch.empty((n_step, 4), dtype=torch.int64, device="cuda")
+    st = torch.empty((n_step, 8), dtype=torch.int64, device="cuda")
     nat.ingest_batch_dev(d_img[f0:f0 + n_step].data_ptr(), n_step, d_T[f0:f0 + n_step].data_ptr(), want_stats=False, stats_dev_ptr=st.data_ptr())
     t1 = time.perf_counter()
     nat.sync()

@@ -38,7 +38,7 @@ def main():
     m._check_width(W); m._sync_device_config(H, W)
     T = m.compose_transforms(pos, quat).reshape(n, 16)
     d_img = torch.from_numpy(images).cuda(); d_T = torch.from_numpy(np.ascontiguousarray(T)).cuda()
-    st = torch.zeros((n, 4), dtype=torch.int64, device="cuda")
+    st = torch.zeros((n, 8), dtype=torch.int64, device="cuda")
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
