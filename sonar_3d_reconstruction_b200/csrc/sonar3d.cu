@@ -14,6 +14,7 @@
 // No tensor cores: the path has no dense contraction; it is integer/fp64 scatter work.
 #include "../../include/sonar3d.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -40,6 +41,7 @@ constexpr int GF = 16;                                      // frames per chunk 
 constexpr int N_CHUNK_BUF = 4;                              // chunk dedupe buffers (a single map cycles through 3 of them)
 constexpr u32 ERR_KEYRANGE = 1u, ERR_TABLEFULL = 2u;        // fatal
 constexpr u32 ERR_ROUTE_FULL = 4u, ERR_ROUTE_TIMEOUT = 8u;  // fatal (routed map): a peer inbox overflowed / a peer never signalled
+constexpr u32 ERR_VERIFY = 16u;                             // S3D_VERIFY_FAST: an accepted fp32 estimate differed from the fp64 key
 constexpr u32 ABORT_SCRATCH = 1u, ABORT_TABLE = 2u;         // retryable: the host enlarges and re-runs the chunk
 constexpr u32 ABORT_NARROW = 4u;                            // retryable: a 16-bit sample count overflowed -> wide lanes
 
@@ -79,6 +81,8 @@ struct DevTables {
     const double *cos_b, *sin_b, *range_m;
     const int *nv_free, *nv_occ;
     const double *cos_va, *sin_va;
+    const float2 *csva32;     // {cos, sin}(va) rounded to fp32 (fast path)
+    int col_step;             // beam_col[b] == b * col_step for every beam (0 = irregular: no strip staging)
 };
 
 struct MapCtr {       // device-resident map counters
@@ -170,8 +174,10 @@ __device__ __forceinline__ u32 mix32(u64 key)
 //      to ~1 k entries at shared-memory atomic cost;
 //   2. the combiner is flushed, entry by entry, into the chunk's dedupe table in global memory
 //      (one entry per voxel touched by the chunk, one counter lane per frame).
-constexpr int EX_WARPS = 8;                  // beams per block
+constexpr int EX_WARPS = 8;                  // warps per block
+constexpr int EX_MAXB = 16;                  // beams per tile at most (a 16-byte image strip at bearing step 1)
 constexpr int EX_THREADS = EX_WARPS * 32;
+constexpr int EX_BPS = 4;                    // resident blocks per SM the kernel is compiled for
 constexpr int EX_ILP = 2;                    // samples per lane per pass
 constexpr int EX_PASS = 32 * EX_ILP;         // samples per warp per pass
 constexpr int EX_ROUND = 6;                  // passes between two block-wide flush votes
@@ -187,7 +193,10 @@ constexpr int FL_ILP = 4;                    // combiner entries per thread per 
 constexpr u32 SCRATCH_PROBE_LIMIT = 512;
 static_assert(EX_ROUND_SAMPLES <= LT_LIMIT, "a round must fit the combiner");
 
-struct __align__(16) Fan { int off; u32 code; double range; };   // code = r | nv << 16 | occupied << 31
+struct __align__(16) Fan { int off; u32 code; float rho; u32 pad_; };   // code = r | nv << 16 | occupied << 31; rho = range / res
+constexpr int TMA_BOX_ROWS = 256;            // rows per TMA box (the hardware limit of a box dimension)
+constexpr int TMA_STRIP_BYTES = 16;          // bytes per image row a tile stages: its beams' columns
+constexpr float MAGICF = 12582912.0f;        // 1.5 * 2^23: adding it (round down) leaves floor(q) in the low mantissa bits
 
 // ---- routed map (one process per GPU): a rank expands its slice of the beams and its combiner
 // flush writes the entries of voxels it does not own straight into the owner's inbox over
@@ -272,7 +281,11 @@ struct ExpandArgs {
     DevStats *stats;             // [g]
     MapCtr *mc;
     int beam_lo, beam_hi;        // processed beams [beam_lo, beam_hi) are expanded (a rank's slice when sharded)
-    int bpb;                     // beams per block, 1..EX_WARPS: fewer beams = shorter blocks, more of them
+    int bpb;                     // beams per tile, 1..EX_MAXB
+    int n_frames;                // frames of the chunk covered by this launch
+    int use_tma;                 // the tile's image strip is staged with one 2-D TMA box per 256 rows (else plain loads)
+    int fast32_ok;               // 0: every sample takes the fp64 path (S3D_NO_FAST32)
+    int box_rows;                // rows per TMA box: min(256, H)
     u32 own_rank, own_world;     // own_world > 1: keep only the voxels this rank owns (replicated expansion)
     RouteCtx rt;                 // rt.world > 1: voxels of other owners are routed to them (routed map)
     u64 seq;                     // chunk sequence number (for abort bookkeeping)
@@ -482,22 +495,77 @@ __device__ __forceinline__ void expand_finish(const ExpandArgs &a)
     if (threadIdx.x == 0) a.cc->xticket = 0;
 }
 
-__host__ __device__ inline size_t expand_smem_bytes(int H, int free_step, int occ_window)
+// dynamic shared memory of k_expand: the combiner (keys, counts, live list) -- whose first bytes double
+// as the landing zone of the tile's image strip while the fans are listed -- and the fan lists
+__host__ __device__ inline size_t expand_smem_bytes(int H, int free_step, int occ_window, int bpb)
 {
     const int max_f = (H + free_step - 1) / free_step;
     return sizeof(u32) * 2 * LT_CAP + sizeof(unsigned short) * LT_CAP +
-           sizeof(Fan) * (size_t)EX_WARPS * (size_t)(max_f + occ_window + 1);
+           sizeof(Fan) * (size_t)bpb * (size_t)(max_f + occ_window + 1);
+}
+__host__ __device__ inline int strip_box_rows(int H) { return H < TMA_BOX_ROWS ? (H > 0 ? H : 1) : TMA_BOX_ROWS; }
+__host__ __device__ inline size_t strip_smem_bytes(int H)
+{
+    const int br = strip_box_rows(H);
+    return (size_t)((H + br - 1) / br) * br * TMA_STRIP_BYTES;
 }
 
-// ROUTE: compiled with the routed-map code (records of remote owners go to their inboxes); the
-// single-map instantiation does not carry it
-// (3 blocks per SM: measured 7 % faster than 4 blocks at 64 registers -- the extra registers matter
-// more than the extra warps)
-template <typename CT, bool CHECK, bool ROUTE>
-__global__ void __launch_bounds__(EX_THREADS, 3)
-k_expand(ExpandArgs a)
+// ---- mbarrier / TMA (sm_100a PTX)
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count)
 {
-    extern __shared__ __align__(16) unsigned char s_raw[];
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one 2-D box {TMA_STRIP_BYTES x TMA_BOX_ROWS} of the chunk's frames (a [rows][W] byte tensor) -> shared memory
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, u64 *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+// K1 + K2 + K3.  A *tile* is (up to EX_MAXB adjacent processed beams, one frame); blocks walk the
+// launch's tiles with a grid stride.  Per tile:
+//   stage    the tile's 16-byte-wide image strip [H rows] is brought into shared memory with one
+//            2-D TMA box per 256 rows (cp.async.bulk.tensor + mbarrier; the strip lands on the
+//            combiner's memory, which is idle until the walk) -- the frames are read here, once,
+//            in full sectors.  Shapes that cannot be described as a strip fall back to plain loads;
+//   list     warp w finds its beam's first above-threshold bin (:406-409) and lists the beam's
+//            fans in walking order;
+//   walk     the flattened (fan, vertical step) space of the tile's beams is cut into passes dealt
+//            round-robin to the warps.  Per sample the voxel index relative to the voxel of the sonar
+//            origin is first estimated in fp32: q = rho * (a_b * cos(va) + c * sin(va)) + f0 per axis
+//            (rho = range / res; a_b, c, f0 are per-beam / per-frame constants prepared in fp64).  The
+//            estimate is accepted when its fractional part is further than a proven error band from
+//            both neighbouring integers (and the z filter's threshold, if any); the rare rest, and
+//            every sample of a frame whose transform does not satisfy the bound's premises, is
+//            evaluated in fp64 in numpy's operation order (:434-440, :63-65), which is what decides
+//            in the reference.  So every key is the reference's key; the fp32 path only skips work;
+//   combine / flush  as described above.
+// ROUTE: compiled with the routed-map code (records of remote owners go to their inboxes); the
+// single-map instantiation does not carry it.  VERIFY (tests): every sample also takes the fp64
+// path and a fast-path key that differs from it raises ERR_VERIFY.
+template <typename CT, bool CHECK, bool ROUTE, bool VERIFY>
+__global__ void __launch_bounds__(EX_THREADS, EX_BPS)
+k_expand(const ExpandArgs a, const __grid_constant__ CUtensorMap tmap)
+{
+    extern __shared__ __align__(128) unsigned char s_raw[];
     u32 *tkey = reinterpret_cast<u32 *>(s_raw);
     u32 *tcnt = tkey + LT_CAP;
     unsigned short *live = reinterpret_cast<unsigned short *>(tcnt + LT_CAP);
@@ -507,234 +575,335 @@ k_expand(ExpandArgs a)
     const int max_f = (H + tab.free_step - 1) / tab.free_step;        // free candidates per beam
     const int nf_max = max_f + tab.occ_window;                        // fans per beam
     __shared__ __align__(16) double s_T[12];
-    __shared__ int s_o[3], s_fast, s_tot[EX_WARPS], s_nfan[EX_WARPS], s_pfirst[EX_WARPS + 1];
-    __shared__ double s_cb[EX_WARPS], s_sb[EX_WARPS];
+    __shared__ __align__(8) u64 s_bar;
+    __shared__ int s_o[3], s_fast, s_fast32, s_tot[EX_MAXB], s_nfan[EX_MAXB], s_pfirst[EX_MAXB + 1];
+    __shared__ double s_cb[EX_MAXB], s_sb[EX_MAXB];
+    __shared__ float s_ab[EX_MAXB][4], s_c[3], s_f0[3], s_kband, s_zq, s_zslack;
     __shared__ u32 s_count, s_abort;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const u32 lt_mask = (1u << lane) - 1;
-    const int g = blockIdx.y;
-    const uint8_t *img = a.imgs + (size_t)g * a.img_stride;
     // (a retry asked for by this chunk or an earlier one; a later chunk's flag does not stop this one)
-    if (tid == 0) { s_abort = (__ldcg(&a.mc->abort) != 0u && a.seq >= __ldcg(&a.mc->abort_seq)) ? 1u : 0u; s_count = 0; }
-    trace_begin(a.trace);
-    if (tid < 12) s_T[tid] = a.T[g * 16 + tid];
-    if (tid == 32) {
-        // voxel of the sonar origin (the combiner's key origin), and whether every sample of this
-        // frame is certain to stay below 2^30 voxels from zero (then the fast quantiser is exact)
-        const double *T = a.T + g * 16;
-        const double reach = H > 0 ? tab.range_m[H - 1] : 0.0;
-        bool fast = true;
-        int o[3] = {0, 0, 0};
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const double bound = (fabs(T[4 * q]) + fabs(T[4 * q + 1]) + fabs(T[4 * q + 2])) * reach + fabs(T[4 * q + 3]);
-            if (!(bound * a.p.inv_res < 1073741824.0)) fast = false;
-            if (!voxel_index(T[4 * q + 3], a.p.res, a.p.inv_res, o[q])) fast = false;
-        }
-        s_o[0] = o[0]; s_o[1] = o[1]; s_o[2] = o[2];
-        s_fast = fast;
+    if (tid == 0) {
+        s_abort = (__ldcg(&a.mc->abort) != 0u && a.seq >= __ldcg(&a.mc->abort_seq)) ? 1u : 0u;
+        s_count = 0;
+        if (a.use_tma) mbar_init(&s_bar, 1);
     }
+    trace_begin(a.trace);
     for (int i = tid; i < LT_CAP / 4; i += EX_THREADS) {
         reinterpret_cast<uint4 *>(tkey)[i] = make_uint4(LT_EMPTY, LT_EMPTY, LT_EMPTY, LT_EMPTY);
         reinterpret_cast<uint4 *>(tcnt)[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
-    if (s_abort) {                      // a chunk must be retried first: stay side-effect free (block-uniform)
+    if (s_abort) {                      // stay side-effect free (block-uniform)
         expand_finish<ROUTE>(a);
         return;
     }
-
-    // ---- per warp: first hit and fan list of its beam
-    Fan *fans = fans_all + (size_t)warp * (nf_max + 1);
-    const int beam = a.beam_lo + blockIdx.x * a.bpb + warp;
-    int total = 0, nfan = 0;
-    double cb = 0.0, sb = 0.0;
-    if (warp < a.bpb && beam < a.beam_hi) {
-        const int col = tab.beam_col[beam];
-        cb = tab.cos_b[beam]; sb = tab.sin_b[beam];
-        // first above-threshold range bin of this beam (:406-409): 128 rows per step, lanes = rows
-        int fh = H;                                                    // no hit -> whole ray is free (:412-413)
-        for (int r0 = 0; r0 < H && fh == H; r0 += 128) {
-            bool hit[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int r = r0 + q * 32 + lane;
-                hit[q] = r < H && (int)__ldg(&img[(size_t)r * W + col]) > a.p.thr;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const u32 mk = __ballot_sync(0xffffffffu, hit[q]);
-                if (mk && fh == H) fh = r0 + q * 32 + __ffs(mk) - 1;
-            }
-        }
-        const int nfc = (fh + tab.free_step - 1) / tab.free_step;      // range(0, fh, free_step) (:420)
-        const int noc = fh < H ? min(tab.occ_window, H - fh) : 0;      // range(fh, min(fh+50, H)) (:451)
-        // fans in walking order, empty ones dropped: free = every free_step-th bin before the first
-        // hit (:420; bins below min_range have nv == 0), then occupied = above-threshold bins in
-        // the window from the first hit (:451-452)
-        int run = 0;
-        const int nfc32 = (nfc + 31) & ~31;
-        for (int base = 0; base < nfc32 + noc; base += 32) {
-            int r = 0, nv = 0;
-            u32 occ_bit = 0u;
-            if (base < nfc32) {                                         // warp-uniform
-                const int c = base + lane;
-                if (c < nfc) { r = c * tab.free_step; nv = tab.nv_free[r]; }
-            } else {
-                const int c = base - nfc32 + lane;
-                if (c < noc) {
-                    r = fh + c;
-                    nv = ((int)__ldg(&img[(size_t)r * W + col]) > a.p.thr) ? tab.nv_occ[r] : 0;   // :452, :456
-                }
-                occ_bit = 0x80000000u;
-            }
-            const u32 m = __ballot_sync(0xffffffffu, nv > 0);
-            const int v = nv > 0 ? 2 * nv + 1 : 0;
-            int incl = v;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
-            }
-            if (nv > 0) {
-                Fan f; f.off = run + incl - v; f.code = (u32)r | ((u32)nv << 16) | occ_bit; f.range = tab.range_m[r];
-                fans[nfan + __popc(m & lt_mask)] = f;
-            }
-            nfan += __popc(m);
-            run += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (lane == 0) fans[nfan].off = run;
-        total = run;
-    }
-    if (lane == 0) { s_tot[warp] = total; s_nfan[warp] = nfan; s_cb[warp] = cb; s_sb[warp] = sb; }
-    __syncthreads();
-    const bool fast = s_fast != 0;
-    const int o[3] = {s_o[0], s_o[1], s_o[2]};
+    const int n_slice = a.beam_hi - a.beam_lo;
+    const int tiles_x = (n_slice + a.bpb - 1) / a.bpb;
+    const int n_tiles = tiles_x * a.n_frames;
+    const int n_box = (H + a.box_rows - 1) / a.box_rows;
+    u32 tma_parity = 0;
     volatile u32 *v_count = &s_count;
     volatile u32 *v_tkey = tkey;
 
-    // ---- the flattened (fan, vertical step) space of each beam is cut into passes of EX_PASS
-    // consecutive samples; the passes of the block's beams, in beam order, are dealt to the warps
-    // round-robin, so the warps finish together whatever the beams hold.  The block walks in rounds
-    // of EX_ROUND passes per warp; between rounds it votes on flushing the combiner, until what is
-    // left certainly fits (then the warps run free to the end).
-    u32 emitted = 0;
-    if (tid == 0) {                  // first pass of each beam (exclusive prefix of the pass counts)
-        int run = 0;
-        for (int b = 0; b < EX_WARPS; ++b) { s_pfirst[b] = run; run += (s_tot[b] + EX_PASS - 1) / EX_PASS; }
-        s_pfirst[EX_WARPS] = run;
-    }
-    __syncthreads();
-    const int n_pass = s_pfirst[EX_WARPS];       // passes of the whole block
-    const int my_pfirst = lane < EX_WARPS ? s_pfirst[lane] : INT_MAX;
-    int since = 0;                   // samples the block has walked since the last flush (>= combiner entries)
-    for (int p_lo = 0; p_lo < n_pass; p_lo += EX_WARPS * EX_ROUND) {
-        int rem = (n_pass - p_lo) * EX_PASS;                            // samples still to walk (upper bound)
-        const bool free_run = since + rem <= LT_LIMIT;                  // block-uniform
-        const int p_hi = free_run ? n_pass : min(n_pass, p_lo + EX_WARPS * EX_ROUND);
-        for (int p = p_lo + warp; p < p_hi; p += EX_WARPS) {
-            // which beam, and where in it
-            const int b = __popc(__ballot_sync(0xffffffffu, my_pfirst <= p)) - 1;     // last beam that starts at or before p
-            const int base = (p - s_pfirst[b]) * EX_PASS;               // first sample of the pass, in its beam
-            const int total = s_tot[b], nfan = s_nfan[b];
-            const double cb = s_cb[b], sb = s_sb[b];
-            const Fan *fans = fans_all + (size_t)b * (nf_max + 1);
-            // fan that holds sample `base`: two-level search over the beam's fan offsets (32 probes each)
-            int c0;
-            {
-                const int S = (nfan + 31) / 32;
-                const int i1 = min(lane * S, nfan);
-                const int seg = __popc(__ballot_sync(0xffffffffu, fans[i1].off <= base && lane * S < nfan)) - 1;
-                const int i2 = seg * S + lane;
-                c0 = seg * S + __popc(__ballot_sync(0xffffffffu, lane < S && i2 < nfan && fans[min(i2, nfan)].off <= base)) - 1;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int g = tile / tiles_x;
+        const int beam0 = a.beam_lo + (tile - g * tiles_x) * a.bpb;
+        const int nb = min(a.bpb, a.beam_hi - beam0);                 // beams of this tile
+        const uint8_t *img = a.imgs + (size_t)g * a.img_stride;
+        // ---- stage: image strip by TMA, frame constants
+        if (tid == 0 && a.use_tma) {
+            // (the combiner region was last touched through the generic proxy: order it before the async proxy's writes)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&s_bar, (u32)(n_box * a.box_rows * TMA_STRIP_BYTES));
+            for (int q = 0; q < n_box; ++q)
+                tma_load_2d(s_raw + (size_t)q * a.box_rows * TMA_STRIP_BYTES, &tmap, (beam0 * tab.col_step) & ~(TMA_STRIP_BYTES - 1),
+                            g * H + q * a.box_rows, &s_bar);
+        }
+        if (tid < 12) s_T[tid] = a.T[g * 16 + tid];
+        if (tid == 32) {
+            // voxel of the sonar origin (the combiner's key origin); whether every sample of this frame
+            // is certain to stay below 2^30 voxels from zero (then the fp64 quantiser's reciprocal
+            // shortcut is exact); and whether the fp32 estimate's premises hold: finite transform,
+            // every sample within the combiner's +-2^9 voxels of the origin
+            const double *T = a.T + g * 16;
+            const double reach = H > 0 ? tab.range_m[H - 1] : 0.0;
+            bool fast = true;
+            int o[3] = {0, 0, 0};
+            double l2max = 0.0, l1max = 0.0;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const double l1 = fabs(T[4 * q]) + fabs(T[4 * q + 1]) + fabs(T[4 * q + 2]);
+                const double bound = l1 * reach + fabs(T[4 * q + 3]);
+                if (!(bound * a.p.inv_res < 1073741824.0)) fast = false;
+                if (!voxel_index(T[4 * q + 3], a.p.res, a.p.inv_res, o[q])) fast = false;
+                l1max = fmax(l1max, l1);
+                l2max = fmax(l2max, sqrt(T[4 * q] * T[4 * q] + T[4 * q + 1] * T[4 * q + 1] + T[4 * q + 2] * T[4 * q + 2]));
             }
-            // fans that start inside this pass: bit (start - base) of a 64-bit mask (a fan has >= 3 samples)
-            const int kf = c0 + 1 + lane;
-            const int rel = (kf <= nfan ? fans[kf].off : INT_MAX) - base;
-            const u32 m_lo = __reduce_or_sync(0xffffffffu, (rel > 0 && rel < 32) ? 1u << rel : 0u);
-            const u32 m_hi = __reduce_or_sync(0xffffffffu, (rel >= 32 && rel < 64) ? 1u << (rel - 32) : 0u);
-            const u32 upto = 0xffffffffu >> (31 - lane);                // bits 0..lane
-            bool made[EX_ILP]; u32 made_at[EX_ILP];
+            s_o[0] = o[0]; s_o[1] = o[1]; s_o[2] = o[2];
+            s_fast = fast;
+            const bool fast32 = fast && (reach * a.p.inv_res * l2max + 2.0 < (double)(LK_HALF - 1)) && a.fast32_ok;
 #pragma unroll
-            for (int j = 0; j < EX_ILP; ++j) {
-                made[j] = false; made_at[j] = 0;
-                const int w = base + j * 32 + lane;
-                if (w >= total) continue;
-                const Fan f = fans[c0 + (j == 0 ? __popc(m_lo & upto) : __popc(m_lo) + __popc(m_hi & upto))];
-                const int nv = (int)((f.code >> 16) & 0x7fffu);
-                const bool occ = (f.code >> 31) != 0u;
-                const int ti = nv * nv - 1 + (w - f.off);               // row nv, entry v_step + nv
-                const double cv = __ldg(&tab.cos_va[ti]), sv = __ldg(&tab.sin_va[ti]);
-                // sonar frame, X fwd / Y right / Z down, products rounded left to right (:434-436)
-                const double rc = __dmul_rn(f.range, cv);
-                const double xs = __dmul_rn(rc, cb);
-                const double ys = -__dmul_rn(rc, sb);
-                const double zs = __dmul_rn(f.range, sv);
-                // T @ [x,y,z,1] as numpy evaluates it: (t0*x + t2*z) + (t1*y + t3) (:440)
-                double wv[3];
+            for (int q = 0; q < 3; ++q) {
+                s_c[q] = (float)T[4 * q + 2];
+                s_f0[q] = (float)(T[4 * q + 3] * a.p.inv_res - (double)o[q]);
+            }
+            // error band of the estimate, per unit of rho (derivation in DESIGN.md): every rounding is
+            // <= 2^-24 relative, five of them act on the rotated term and one on the result
+            s_kband = (float)(l1max * 7.5e-7);
+            const double zq = a.p.zmin * a.p.inv_res - (double)o[2];
+            s_zq = (float)zq;
+            s_zslack = (float)(fabs(zq) * 1.3e-7);
+            s_fast32 = (fast32 && (!a.p.zfilter || fabs(zq) < 1e9)) ? 1 : 0;
+        }
+        if (a.use_tma) { mbar_wait(&s_bar, tma_parity); tma_parity ^= 1u; }
+        __syncthreads();
+
+        // ---- list: per warp, first hit and fan list of its beams
+        for (int b = warp; b < nb; b += EX_WARPS) {
+            Fan *fans = fans_all + (size_t)b * (nf_max + 1);
+            const int beam = beam0 + b;
+            const int col = tab.beam_col[beam];
+            const double cb = tab.cos_b[beam], sb = tab.sin_b[beam];
+            const unsigned char *strip = s_raw + (((beam0 + b) * tab.col_step) & (TMA_STRIP_BYTES - 1));   // this beam's column of the staged strip
+            auto pix = [&](int r) -> int {
+                return a.use_tma ? (int)strip[r * TMA_STRIP_BYTES] : (int)__ldg(&img[(size_t)r * W + col]);
+            };
+            // first above-threshold range bin of this beam (:406-409): 128 rows per step, lanes = rows
+            int fh = H;                                                    // no hit -> whole ray is free (:412-413)
+            for (int r0 = 0; r0 < H && fh == H; r0 += 128) {
+                bool hit[4];
 #pragma unroll
-                for (int q = 0; q < 3; ++q)
-                    wv[q] = __dadd_rn(__dadd_rn(__dmul_rn(s_T[4 * q], xs), __dmul_rn(s_T[4 * q + 2], zs)),
-                                      __dadd_rn(__dmul_rn(s_T[4 * q + 1], ys), s_T[4 * q + 3]));
-                if (a.p.zfilter && wv[2] < a.p.zmin) continue;          // :443, :478
-                int ki, kj, kk;
-                if (!(quantise(a.p, wv[0], fast, ki) && quantise(a.p, wv[1], fast, kj) && quantise(a.p, wv[2], fast, kk))) {
-                    atomicOr(&a.mc->err, ERR_KEYRANGE);
-                    continue;
+                for (int q = 0; q < 4; ++q) {
+                    const int r = r0 + q * 32 + lane;
+                    hit[q] = r < H && pix(r) > a.p.thr;
                 }
-                const u32 d0 = (u32)(ki - o[0] + LK_HALF), d1 = (u32)(kj - o[1] + LK_HALF), d2 = (u32)(kk - o[2] + LK_HALF);
-                if (fast && (d0 | d1 | d2) < (u32)(2 * LK_HALF)) {
-                    // block combiner: find-or-insert the 30-bit local key, bump its 16+16-bit counts
-                    const u32 lk = d0 | (d1 << LK_BITS) | (d2 << (2 * LK_BITS));
-                    u32 h = (lk * 0x9E3779B1u) >> (32 - LT_BITS);
-                    for (;;) {
-                        u32 cur = v_tkey[h];
-                        if (cur == lk) break;
-                        if (cur == LT_EMPTY) {
-                            cur = atomicCAS(&tkey[h], LT_EMPTY, lk);
-                            if (cur == LT_EMPTY) { made[j] = true; made_at[j] = h; break; }
-                            if (cur == lk) break;
-                        }
-                        h = (h + 1) & (LT_CAP - 1);
-                    }
-                    atomicAdd(&tcnt[h], occ ? 0x10000u : 1u);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const u32 mk = __ballot_sync(0xffffffffu, hit[q]);
+                    if (mk && fh == H) fh = r0 + q * 32 + __ffs(mk) - 1;
+                }
+            }
+            const int nfc = (fh + tab.free_step - 1) / tab.free_step;      // range(0, fh, free_step) (:420)
+            const int noc = fh < H ? min(tab.occ_window, H - fh) : 0;      // range(fh, min(fh+50, H)) (:451)
+            // fans in walking order, empty ones dropped: free = every free_step-th bin before the first
+            // hit (:420; bins below min_range have nv == 0), then occupied = above-threshold bins in
+            // the window from the first hit (:451-452)
+            int run = 0, nfan = 0;
+            const int nfc32 = (nfc + 31) & ~31;
+            for (int base = 0; base < nfc32 + noc; base += 32) {
+                int r = 0, nv = 0;
+                u32 occ_bit = 0u;
+                if (base < nfc32) {                                         // warp-uniform
+                    const int c = base + lane;
+                    if (c < nfc) { r = c * tab.free_step; nv = tab.nv_free[r]; }
                 } else {
-                    if (!key_in_range(ki, kj, kk)) { atomicOr(&a.mc->err, ERR_KEYRANGE); continue; }
-                    const u64 key = pack_key(ki, kj, kk);
-                    if (a.own_world > 1 && key_owner(key, a.own_world) != a.own_rank) continue;
-                    ++emitted;
-                    commit_direct<CT, CHECK, ROUTE>(a.skeys, static_cast<CT *>(a.scnt), a.smask, a.cc, a.mc, a.seq, key, g, occ, a.rt);
+                    const int c = base - nfc32 + lane;
+                    if (c < noc) {
+                        r = fh + c;
+                        nv = (pix(r) > a.p.thr) ? tab.nv_occ[r] : 0;       // :452, :456
+                    }
+                    occ_bit = 0x80000000u;
+                }
+                const u32 m = __ballot_sync(0xffffffffu, nv > 0);
+                const int v = nv > 0 ? 2 * nv + 1 : 0;
+                int incl = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if (nv > 0) {
+                    Fan f; f.off = run + incl - v; f.code = (u32)r | ((u32)nv << 16) | occ_bit;
+                    f.rho = (float)(tab.range_m[r] * a.p.inv_res); f.pad_ = 0u;
+                    fans[nfan + __popc(m & lt_mask)] = f;
+                }
+                nfan += __popc(m);
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) {
+                fans[nfan].off = run;
+                s_tot[b] = run; s_nfan[b] = nfan; s_cb[b] = cb; s_sb[b] = sb;
+            }
+            if (lane < 3) s_ab[b][lane] = (float)(s_T[4 * lane] * cb - s_T[4 * lane + 1] * sb);
+        }
+        __syncthreads();
+        if (a.use_tma) {                 // the strip sat on the combiner: make it a combiner again
+            for (int i = tid; i < (int)(strip_smem_bytes(H) / 16); i += EX_THREADS) {
+                if (i < LT_CAP / 4) reinterpret_cast<uint4 *>(tkey)[i] = make_uint4(LT_EMPTY, LT_EMPTY, LT_EMPTY, LT_EMPTY);
+                else reinterpret_cast<uint4 *>(tkey)[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        if (tid == 0) {                  // first pass of each beam (exclusive prefix of the pass counts)
+            int run = 0;
+            for (int b = 0; b < nb; ++b) { s_pfirst[b] = run; run += (s_tot[b] + EX_PASS - 1) / EX_PASS; }
+            for (int b = nb; b <= EX_MAXB; ++b) s_pfirst[b] = run;
+        }
+        __syncthreads();
+        const bool fast = s_fast != 0, fast32 = s_fast32 != 0;
+        const int o[3] = {s_o[0], s_o[1], s_o[2]};
+        const float cz[3] = {s_c[0], s_c[1], s_c[2]}, f0[3] = {s_f0[0], s_f0[1], s_f0[2]};
+        const float kband = s_kband, zq = s_zq, zslack = s_zslack;
+
+        // ---- walk: the flattened (fan, vertical step) space of each beam is cut into passes of EX_PASS
+        // consecutive samples; the passes of the tile's beams, in beam order, are dealt to the warps
+        // round-robin, so the warps finish together whatever the beams hold.  The block walks in rounds
+        // of EX_ROUND passes per warp; between rounds it votes on flushing the combiner, until what is
+        // left certainly fits (then the warps run free to the end).
+        u32 emitted = 0;
+        const int n_pass = s_pfirst[EX_MAXB];        // passes of the whole tile
+        const int my_pfirst = lane < nb ? s_pfirst[lane] : INT_MAX;
+        int since = 0;                   // samples the block has walked since the last flush (>= combiner entries)
+        for (int p_lo = 0; p_lo < n_pass; p_lo += EX_WARPS * EX_ROUND) {
+            int rem = (n_pass - p_lo) * EX_PASS;                            // samples still to walk (upper bound)
+            const bool free_run = since + rem <= LT_LIMIT;                  // block-uniform
+            const int p_hi = free_run ? n_pass : min(n_pass, p_lo + EX_WARPS * EX_ROUND);
+            for (int p = p_lo + warp; p < p_hi; p += EX_WARPS) {
+                // which beam, and where in it
+                const int b = __popc(__ballot_sync(0xffffffffu, my_pfirst <= p)) - 1;     // last beam that starts at or before p
+                const int base = (p - s_pfirst[b]) * EX_PASS;               // first sample of the pass, in its beam
+                const int total = s_tot[b], nfan = s_nfan[b];
+                const float ab[3] = {s_ab[b][0], s_ab[b][1], s_ab[b][2]};
+                const Fan *fans = fans_all + (size_t)b * (nf_max + 1);
+                // fan that holds sample `base`: two-level search over the beam's fan offsets (32 probes each)
+                int c0;
+                {
+                    const int S = (nfan + 31) / 32;
+                    const int i1 = min(lane * S, nfan);
+                    const int seg = __popc(__ballot_sync(0xffffffffu, fans[i1].off <= base && lane * S < nfan)) - 1;
+                    const int i2 = seg * S + lane;
+                    c0 = seg * S + __popc(__ballot_sync(0xffffffffu, lane < S && i2 < nfan && fans[min(i2, nfan)].off <= base)) - 1;
+                }
+                // fans that start inside this pass: bit (start - base) of a 64-bit mask (a fan has >= 3 samples)
+                const int kf = c0 + 1 + lane;
+                const int rel = (kf <= nfan ? fans[kf].off : INT_MAX) - base;
+                const u32 m_lo = __reduce_or_sync(0xffffffffu, (rel > 0 && rel < 32) ? 1u << rel : 0u);
+                const u32 m_hi = __reduce_or_sync(0xffffffffu, (rel >= 32 && rel < 64) ? 1u << (rel - 32) : 0u);
+                const u32 upto = 0xffffffffu >> (31 - lane);                // bits 0..lane
+                bool made[EX_ILP]; u32 made_at[EX_ILP];
+#pragma unroll
+                for (int j = 0; j < EX_ILP; ++j) {
+                    made[j] = false; made_at[j] = 0;
+                    const int w = base + j * 32 + lane;
+                    if (w >= total) continue;
+                    const Fan f = fans[c0 + (j == 0 ? __popc(m_lo & upto) : __popc(m_lo) + __popc(m_hi & upto))];
+                    const int nv = (int)((f.code >> 16) & 0x7fffu);
+                    const bool occ = (f.code >> 31) != 0u;
+                    const int ti = nv * nv - 1 + (w - f.off);               // row nv, entry v_step + nv
+                    bool need_exact = true, to_comb = false;
+                    u32 lk = 0;
+                    if (fast32) {
+                        // fp32 estimate of the voxel index relative to the sonar-origin voxel
+                        const float2 cs = __ldg(&tab.csva32[ti]);
+                        const float band = fmaf(f.rho, kband, 3e-7f);
+                        bool ok = true;
+                        u32 tb[3];
+                        float q2 = 0.f;
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            const float v = fmaf(cz[q], cs.y, __fmul_rn(ab[q], cs.x));
+                            const float qq = fmaf(f.rho, v, f0[q]);
+                            const float t = __fadd_rd(qq, MAGICF);                       // floor(qq) + MAGICF, exactly
+                            const float fr = __fadd_rn(qq, -__fadd_rn(t, -MAGICF));      // qq - floor(qq), exact
+                            ok = ok && (fabsf(fr - 0.5f) < 0.5f - band);
+                            tb[q] = __float_as_uint(t);
+                            if (q == 2) q2 = qq;
+                        }
+                        bool drop = false;
+                        if (a.p.zfilter) {                                               // :443, :478
+                            const float dz = q2 - zq;
+                            if (fabsf(dz) < band + zslack) ok = false; else drop = dz < 0.f;
+                        }
+                        constexpr u32 KOFF = (u32)LK_HALF - 0x4B400000u;
+                        lk = ((tb[0] + KOFF) & (2 * LK_HALF - 1)) | (((tb[1] + KOFF) & (2 * LK_HALF - 1)) << LK_BITS) |
+                             (((tb[2] + KOFF) & (2 * LK_HALF - 1)) << (2 * LK_BITS));
+                        need_exact = !ok;
+                        to_comb = ok && !drop;
+                    }
+                    if (need_exact || VERIFY) {
+                        // the reference's arithmetic: sonar frame, X fwd / Y right / Z down, products rounded left to right (:434-436)
+                        const double range = tab.range_m[f.code & 0xffffu];
+                        const double cv = __ldg(&tab.cos_va[ti]), sv = __ldg(&tab.sin_va[ti]);
+                        const double cb = s_cb[b], sb = s_sb[b];
+                        const double rc = __dmul_rn(range, cv);
+                        const double xs = __dmul_rn(rc, cb);
+                        const double ys = -__dmul_rn(rc, sb);
+                        const double zs = __dmul_rn(range, sv);
+                        // T @ [x,y,z,1] as numpy evaluates it: (t0*x + t2*z) + (t1*y + t3) (:440)
+                        double wv[3];
+#pragma unroll
+                        for (int q = 0; q < 3; ++q)
+                            wv[q] = __dadd_rn(__dadd_rn(__dmul_rn(s_T[4 * q], xs), __dmul_rn(s_T[4 * q + 2], zs)),
+                                              __dadd_rn(__dmul_rn(s_T[4 * q + 1], ys), s_T[4 * q + 3]));
+                        bool x_comb = false; u32 x_lk = 0; bool x_direct = false; u64 x_key = 0;
+                        if (!(a.p.zfilter && wv[2] < a.p.zmin)) {           // :443, :478
+                            int ki, kj, kk;
+                            if (!(quantise(a.p, wv[0], fast, ki) && quantise(a.p, wv[1], fast, kj) && quantise(a.p, wv[2], fast, kk))) {
+                                atomicOr(&a.mc->err, ERR_KEYRANGE);
+                            } else {
+                                const u32 d0 = (u32)(ki - o[0] + LK_HALF), d1 = (u32)(kj - o[1] + LK_HALF), d2 = (u32)(kk - o[2] + LK_HALF);
+                                if (fast && (d0 | d1 | d2) < (u32)(2 * LK_HALF)) {
+                                    x_comb = true; x_lk = d0 | (d1 << LK_BITS) | (d2 << (2 * LK_BITS));
+                                } else if (!key_in_range(ki, kj, kk)) atomicOr(&a.mc->err, ERR_KEYRANGE);
+                                else { x_direct = true; x_key = pack_key(ki, kj, kk); }
+                            }
+                        }
+                        if (VERIFY && !need_exact && (to_comb != x_comb || (to_comb && lk != x_lk))) atomicOr(&a.mc->err, ERR_VERIFY);
+                        if (need_exact) {
+                            to_comb = x_comb; lk = x_lk;
+                            if (x_direct && !(a.own_world > 1 && key_owner(x_key, a.own_world) != a.own_rank)) {
+                                ++emitted;
+                                commit_direct<CT, CHECK, ROUTE>(a.skeys, static_cast<CT *>(a.scnt), a.smask, a.cc, a.mc, a.seq, x_key, g, occ, a.rt);
+                            }
+                        }
+                    }
+                    if (to_comb) {
+                        // block combiner: find-or-insert the 30-bit local key, bump its 16+16-bit counts
+                        u32 h = (lk * 0x9E3779B1u) >> (32 - LT_BITS);
+                        for (;;) {
+                            u32 cur = v_tkey[h];
+                            if (cur == lk) break;
+                            if (cur == LT_EMPTY) {
+                                cur = atomicCAS(&tkey[h], LT_EMPTY, lk);
+                                if (cur == LT_EMPTY) { made[j] = true; made_at[j] = h; break; }
+                                if (cur == lk) break;
+                            }
+                            h = (h + 1) & (LT_CAP - 1);
+                        }
+                        atomicAdd(&tcnt[h], occ ? 0x10000u : 1u);
+                    }
+                }
+                // combiner slots created by this pass join the live list: one shared-memory atomic per pass
+                static_assert(EX_ILP == 2, "two ballots below");
+                const u32 mk0 = __ballot_sync(0xffffffffu, made[0]), mk1 = __ballot_sync(0xffffffffu, made[1]);
+                if (mk0 | mk1) {
+                    u32 at = 0;
+                    if (lane == 0) at = atomicAdd(&s_count, (u32)(__popc(mk0) + __popc(mk1)));
+                    at = __shfl_sync(0xffffffffu, at, 0);
+                    if (made[0]) live[at + __popc(mk0 & lt_mask)] = (unsigned short)made_at[0];
+                    if (made[1]) live[at + __popc(mk0) + __popc(mk1 & lt_mask)] = (unsigned short)made_at[1];
                 }
             }
-            // combiner slots created by this pass join the live list: one shared-memory atomic per pass
-            static_assert(EX_ILP == 2, "two ballots below");
-            const u32 mk0 = __ballot_sync(0xffffffffu, made[0]), mk1 = __ballot_sync(0xffffffffu, made[1]);
-            if (mk0 | mk1) {
-                u32 at = 0;
-                if (lane == 0) at = atomicAdd(&s_count, (u32)(__popc(mk0) + __popc(mk1)));
-                at = __shfl_sync(0xffffffffu, at, 0);
-                if (made[0]) live[at + __popc(mk0 & lt_mask)] = (unsigned short)made_at[0];
-                if (made[1]) live[at + __popc(mk0) + __popc(mk1 & lt_mask)] = (unsigned short)made_at[1];
+            if (free_run) break;
+            since += (p_hi - p_lo) * EX_PASS;
+            rem -= (p_hi - p_lo) * EX_PASS;
+            // flush if the next round could overflow the combiner's entries or its 16-bit counts.  Every
+            // thread votes with the entry count it sees on arrival; the last one to arrive sees the final one.
+            const int next = min(rem, EX_ROUND_SAMPLES);
+            const int want = (*v_count + (u32)next > (u32)LT_LIMIT) || (since + next > LT_MAX_SAMPLES);
+            if (__syncthreads_or(want)) {
+                flush_combiner<CT, CHECK, ROUTE>(a, tkey, tcnt, live, v_count, o, g, emitted);
+                since = 0;
             }
         }
-        if (free_run) break;
-        since += (p_hi - p_lo) * EX_PASS;
-        rem -= (p_hi - p_lo) * EX_PASS;
-        // flush if the next round could overflow the combiner's entries or its 16-bit counts.  Every
-        // thread votes with the entry count it sees on arrival; the last one to arrive sees the final one.
-        const int next = min(rem, EX_ROUND_SAMPLES);
-        const int want = (*v_count + (u32)next > (u32)LT_LIMIT) || (since + next > LT_MAX_SAMPLES);
-        if (__syncthreads_or(want)) {
-            flush_combiner<CT, CHECK, ROUTE>(a, tkey, tcnt, live, v_count, o, g, emitted);
-            since = 0;
-        }
-    }
-    __syncthreads();
-    if (*v_count > 0u) flush_combiner<CT, CHECK, ROUTE>(a, tkey, tcnt, live, v_count, o, g, emitted);
+        __syncthreads();
+        if (*v_count > 0u) flush_combiner<CT, CHECK, ROUTE>(a, tkey, tcnt, live, v_count, o, g, emitted);
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
-    if (lane == 0 && emitted) atomicAdd(&a.stats[g].n_samples, (u64)emitted);
+        for (int d = 16; d > 0; d >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
+        if (lane == 0 && emitted) atomicAdd(&a.stats[g].n_samples, (u64)emitted);
+        __syncthreads();                 // the tile's shared state is reused by the next one
+    }
     expand_finish<ROUTE>(a);
 }
 
@@ -820,17 +989,17 @@ __device__ __forceinline__ void acc_publish(LocalAcc &a, MapCtr *mc, bool add_co
     }
 }
 
-constexpr int AP_THREADS = 256;
+constexpr int AP_THREADS = 256;              // = entries per batch
 constexpr int AP_WARPS = AP_THREADS / 32;
-constexpr int AP_SCAN = 4;                   // dedupe slots per lane per scan step (independent loads)
-constexpr int AP_STRIP = 32 * AP_SCAN;       // dedupe slots a warp scans per step
-constexpr int AP_QCAP = 256;                 // per-warp queue of live entries (ring; < 32 left + one strip)
+constexpr int AP_SCAN = 2;                   // dedupe slots per thread per scan step (independent loads)
+constexpr int AP_TILE = AP_THREADS * AP_SCAN;   // dedupe slots a block scans per step
+constexpr int AP_LCAP = 1024;                // live list (ring): less than a batch left over + one tile
 constexpr int SUMT = 64;                     // entries of the sequential-sum tables
-static_assert(AP_QCAP >= 32 + AP_STRIP && (AP_QCAP & (AP_QCAP - 1)) == 0, "queue holds a leftover round plus one strip");
-// staged counter lanes of the 32 entries a warp is processing: one padded row per lane (stride
-// of 5 / 9 sixteen-byte words: conflict-free 128-bit stores)
+static_assert(AP_LCAP >= AP_THREADS + AP_TILE && (AP_LCAP & (AP_LCAP - 1)) == 0, "list holds a leftover batch plus one tile");
+// staged counter lanes of the entries of a batch: one padded row per entry (stride of 5 / 9
+// sixteen-byte words: conflict-free 128-bit stores)
 template <typename CT> __host__ __device__ constexpr int ap_row_words() { return (int)(sizeof(CT) * GF / 4) + 4; }
-template <typename CT> __host__ __device__ constexpr size_t apply_smem_bytes() { return (size_t)AP_WARPS * 32 * ap_row_words<CT>() * 4; }
+template <typename CT> __host__ __device__ constexpr size_t apply_smem_bytes() { return (size_t)AP_THREADS * ap_row_words<CT>() * 4; }
 
 // sum of n_free copies of lo_free followed by n_occ copies of lo_occ, added one by one as the
 // reference's `sum += log_odds` does (3d_mapper.py:546).  tab[0][n] / tab[1][n] hold the
@@ -887,16 +1056,19 @@ struct ApplyArgs {
     ulonglong2 *last; u32 *last_n; u32 last_cap;   // {key, samples} of the chunk's last frame
 };
 
-// K4.  The chunk's dedupe table is walked by autonomous warps (no block barrier in the loop):
-//   scan     a warp reads AP_STRIP slots' keys (AP_SCAN independent loads per lane) and appends
-//            the live ones to its own shared-memory queue;
-//   process  whenever the queue holds 32 entries, every lane takes one: the entry's counter
-//            lanes and the home sector of its voxel in the table are requested together (six
-//            independent 16-byte loads per lane, a warp keeps 192 in flight), the entry is wiped
-//            for the next chunk, the voxel is found or inserted (one probe per voxel per chunk),
-//            and the frames that touched the voxel are applied in order: per-voxel mean of the
-//            sample deltas (3d_mapper.py:557-559), then update_voxel (:562-567); L goes back with
-//            one 8-byte store.  The frame loop is unrolled over the 16 lanes (registers, no staging).
+// K4.  The chunk's dedupe table is walked by blocks in tiles of AP_TILE slots:
+//   scan     every thread reads AP_SCAN slots' keys; live ones are appended to the block's list;
+//   batch    whenever the list holds AP_THREADS entries (and at the end), every thread takes one:
+//            the entry's counter lanes and the home sector of its voxel in the table are requested
+//            together (six independent 16-byte loads per thread -- the whole block's table sectors
+//            are in flight at once), the entry is wiped for the next chunk, the voxel is found or
+//            inserted (one probe per voxel per chunk), lanes + L are staged in shared memory;
+//   sort     the batch is ordered by the number of frames that touched each voxel (counting sort,
+//            16 bins), so that the warps of the update step are homogeneous: the per-voxel frame
+//            chains are sequential, and a warp takes as long as its longest chain;
+//   update   one thread per staged entry walks only the frames that touched the voxel, in order:
+//            per-voxel mean of the sample deltas (3d_mapper.py:557-559), then update_voxel
+//            (:562-567); L goes back to the table with one 8-byte store.
 // num_occupied / num_free per frame are kept as packed byte counters in registers (one add per
 // entry per 4 frames) and reduced per warp when they could overflow and at the end.
 // Frames stay strictly ordered per voxel, which is all the reference's sequential semantics
@@ -924,30 +1096,35 @@ k_apply_chunk(const ApplyArgs a)
             return;
         }
     }
-    extern __shared__ __align__(16) unsigned char s_dyn[];
-    __shared__ u64 s_qkey[AP_WARPS][AP_QCAP];
-    __shared__ u32 s_qslot[AP_WARPS][AP_QCAP];
+    extern __shared__ __align__(16) unsigned char s_dyn[];          // staged counter lanes [AP_THREADS][ROWW]
+    __shared__ u64 s_lkey[AP_LCAP];                                 // live list: key ...
+    __shared__ u32 s_lslot[AP_LCAP];                                // ... and dedupe slot
+    __shared__ double s_L[AP_THREADS];
+    __shared__ u64 s_tslot[AP_THREADS];
+    __shared__ u64 s_life[DEBUG ? AP_THREADS : 1], s_lifeslot[DEBUG ? AP_THREADS : 1];
+    __shared__ unsigned short s_mask[AP_THREADS], s_ord[AP_THREADS];
+    __shared__ u32 s_hist[GF + 1], s_tail;
     __shared__ u32 s_occ[GF], s_free[GF], s_new[GF];
     __shared__ u32 s_dmax[GF], s_dgt10[GF], s_lifenew;
     __shared__ u64 s_dlife[GF];
     __shared__ double s_sum[4][SUMT];
     __shared__ bool s_last;
-    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 tid = threadIdx.x, lane = tid & 31;
     const u32 lt_mask = (1u << lane) - 1;
     const DevParams &p = a.p;
     if (tid < GF) { s_occ[tid] = 0; s_free[tid] = 0; s_new[tid] = 0; s_dmax[tid] = 0; s_dgt10[tid] = 0; s_dlife[tid] = 0; }
-    if (tid == 0) s_lifenew = 0;
+    if (tid <= GF) s_hist[tid] = 0;
+    if (tid == 0) { s_lifenew = 0; s_tail = 0; }
     for (int q = tid; q < 4 * SUMT; q += AP_THREADS) (&s_sum[0][0])[q] = a.sum_tab[q];
     __syncthreads();
-    u64 *qkey = s_qkey[warp]; u32 *qslot = s_qslot[warp];
     constexpr int ROWW = ap_row_words<CT>();
     constexpr int NV = (int)(sizeof(CT) * GF / 16);
-    u32 *my_row = reinterpret_cast<u32 *>(s_dyn) + ((size_t)warp * 32 + lane) * ROWW;   // this lane's staged counter lanes
+    u32 *rows = reinterpret_cast<u32 *>(s_dyn);
     CT *scnt = static_cast<CT *>(a.scnt);
     LocalAcc acc; acc_init(acc);
     u32 pk_occ[4] = {0, 0, 0, 0}, pk_free[4] = {0, 0, 0, 0};     // byte f%4 of word f/4: voxels updated as occupied / free in frame f
     u32 pk_rounds = 0;
-    u32 q_head = 0, q_tail = 0;                                   // warp-uniform ring positions
+    u32 head = 0;                                                 // block-uniform: list entries already taken
 
     auto flush_packed = [&]() {
 #pragma unroll
@@ -963,14 +1140,14 @@ k_apply_chunk(const ApplyArgs a)
         pk_rounds = 0;
     };
 
-    // one round: lanes < n take the entries at the head of the queue
-    auto process = [&](u32 n) {
-        const bool have = lane < n;
-        const u32 qi = (q_head + lane) & (AP_QCAP - 1);
-        const u64 key = have ? qkey[qi] : 0ull;
-        const u32 s = have ? qslot[qi] : 0u;
-        q_head += n;
+    // one batch: threads < n take the entries at the head of the list.  Block-wide.
+    auto batch = [&](u32 n) {
+        const bool have = tid < n;
+        u32 nfr = 0, rank = 0;                                     // frames that touched my entry; my rank among the entries with as many
         if (have) {
+            const u32 li = (head + tid) & (AP_LCAP - 1);
+            const u64 key = s_lkey[li];
+            const u32 s = s_lslot[li];
             // ---- all loads of the entry first: counter lanes + home sector of the voxel (+ lifetime table)
             uint4 *cp = reinterpret_cast<uint4 *>(scnt + (size_t)s * GF);
             uint4 raw[NV];
@@ -990,6 +1167,7 @@ k_apply_chunk(const ApplyArgs a)
             for (int q = 0; q < NV; ++q) cp[q] = make_uint4(0u, 0u, 0u, 0u);
             // ---- frames that saw the voxel at all / occupied (occupied has priority, :544-545); stage the lanes
             u32 m_occ = 0, m_any = 0;
+            u32 *my_row = rows + (size_t)tid * ROWW;
 #pragma unroll
             for (int q = 0; q < NV; ++q) {
                 reinterpret_cast<uint4 *>(my_row)[q] = raw[q];
@@ -1008,39 +1186,21 @@ k_apply_chunk(const ApplyArgs a)
                     }
                 }
             }
+            u64 slot = ~0ull; double L = 0.0;
             if (m_any) {
-                bool fresh; double L;
-                const u64 slot = table_resolve(a.table, a.tmask, key, pair, t0, t1, fresh, L);
-                if (slot == ~0ull) atomicOr(&mc->err, ERR_TABLEFULL);
+                bool fresh;
+                slot = table_resolve(a.table, a.tmask, key, pair, t0, t1, fresh, L);
+                if (slot == ~0ull) { atomicOr(&mc->err, ERR_TABLEFULL); m_any = 0; }
                 else {
                     if (fresh) atomicAdd(&s_new[__ffs(m_any) - 1], 1u);       // len(voxels) grows at the first frame that touched it
-                    u64 life = 0, lslot = 0;
                     if (DEBUG) {
                         bool lfresh; double lv;
-                        lslot = table_resolve(a.life, a.tmask, key, pair, l0, l1, lfresh, lv);
+                        const u64 lslot = table_resolve(a.life, a.tmask, key, pair, l0, l1, lfresh, lv);
                         if (lslot == ~0ull) atomicOr(&mc->err, ERR_TABLEFULL);
-                        else { life = lfresh ? 0ull : (u64)__double_as_longlong(lv); if (lfresh) atomicAdd(&s_lifenew, 1u); }
-                    }
-                    const CT *row = reinterpret_cast<const CT *>(my_row);
-                    u32 todo = m_any;
-                    while (todo) {                                              // only the frames that touched the voxel, in order
-                        const int f = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        const CT cf = row[f];
-                        const u32 n_occ = Lane<CT>::n_occ(cf), n_free = Lane<CT>::n_free(cf);
-                        L = apply_one(L, seq_avg(n_free, n_occ, s_sum, p), n_occ > 0, p);
-                        if (DEBUG) {
-                            const u32 nn = n_occ + n_free;                      // frame_update_counts[key] (:550)
-                            life += nn;                                         // voxel_update_counts[key] (:551)
-                            atomicMax(&s_dmax[f], nn);
-                            if (nn > 10u) atomicAdd(&s_dgt10[f], 1u);
-                            atomicMax(&s_dlife[f], life);
-                        }
-                    }
-                    a.table[slot].val = L;
-                    if (DEBUG) {
-                        if (lslot != ~0ull) a.life[lslot].val = __longlong_as_double((long long)life);
-                        const CT last = row[a.g - 1];                           // frame_update_counts of the chunk's last frame
+                        else if (lfresh) atomicAdd(&s_lifenew, 1u);
+                        s_lifeslot[tid] = lslot;
+                        s_life[tid] = (lslot == ~0ull || lfresh) ? 0ull : (u64)__double_as_longlong(lv);
+                        const CT last = reinterpret_cast<const CT *>(my_row)[a.g - 1];   // frame_update_counts of the chunk's last frame
                         if (last != 0) {
                             const u32 at = atomicAdd(a.last_n, 1u);
                             if (at < a.last_cap) a.last[at] = make_ulonglong2(key, (u64)(Lane<CT>::n_occ(last) + Lane<CT>::n_free(last)));
@@ -1053,41 +1213,89 @@ k_apply_chunk(const ApplyArgs a)
                     for (int w = 0; w < 4; ++w) { pk_occ[w] += spread4(m_occ >> (4 * w)); pk_free[w] += spread4(m_free >> (4 * w)); }
                 }
             }
+            s_L[tid] = L; s_tslot[tid] = slot; s_mask[tid] = (unsigned short)m_any;
+            nfr = (u32)__popc(m_any);
+        }
+        {
+            // rank among the batch's entries with the same frame count (one shared atomic per distinct count per warp)
+            const u32 peers = __match_any_sync(0xffffffffu, have ? nfr : 0xffffu);
+            u32 base = 0;
+            if (have && lane == (u32)__ffs(peers) - 1) base = atomicAdd(&s_hist[nfr], (u32)__popc(peers));
+            base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
+            rank = base + __popc(peers & lt_mask);
         }
         if (++pk_rounds == 255u) flush_packed();
+        __syncthreads();
+        if (have) {
+            u32 pos = rank;                                       // longest chains first
+            for (u32 c = nfr + 1; c <= (u32)GF; ++c) pos += s_hist[c];
+            s_ord[pos] = (unsigned short)tid;
+        }
+        __syncthreads();
+        if (tid <= GF) s_hist[tid] = 0;
+        if (have) {
+            const u32 e = s_ord[tid];
+            u32 todo = s_mask[e];
+            if (todo) {
+                double L = s_L[e];
+                u64 life = DEBUG ? s_life[e] : 0ull;
+                const CT *row = reinterpret_cast<const CT *>(rows + (size_t)e * ROWW);
+                while (todo) {                                                  // only the frames that touched the voxel, in order
+                    const int f = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const CT cf = row[f];
+                    const u32 n_occ = Lane<CT>::n_occ(cf), n_free = Lane<CT>::n_free(cf);
+                    if (n_occ == 0u && n_free < (u32)SUMT) {                     // the common case: a free update (:565-567)
+                        L += s_sum[2][n_free];
+                        L = L < p.lo_min ? p.lo_min : (L > p.lo_max ? p.lo_max : L);
+                    } else {
+                        L = apply_one(L, seq_avg(n_free, n_occ, s_sum, p), n_occ > 0, p);
+                    }
+                    if (DEBUG) {
+                        const u32 nn = n_occ + n_free;                          // frame_update_counts[key] (:550)
+                        life += nn;                                             // voxel_update_counts[key] (:551)
+                        atomicMax(&s_dmax[f], nn);
+                        if (nn > 10u) atomicAdd(&s_dgt10[f], 1u);
+                        atomicMax(&s_dlife[f], life);
+                    }
+                }
+                a.table[s_tslot[e]].val = L;
+                if (DEBUG && s_lifeslot[e] != ~0ull) a.life[s_lifeslot[e]].val = __longlong_as_double((long long)life);
+            }
+        }
+        head += n;
+        __syncthreads();
     };
 
-    const u32 n_strips = a.n_slots / AP_STRIP;
-    u32 strip = blockIdx.x * AP_WARPS + warp;
-    bool more = strip < n_strips;
-    for (;;) {
-        if (more) {
-            const u32 s0 = strip * AP_STRIP;
-            u64 k[AP_SCAN];
+    const u32 n_tiles = a.n_slots / AP_TILE;
+    u32 tile = blockIdx.x;
+    bool more = tile < n_tiles;
+    while (more) {
+        const u32 s0 = tile * AP_TILE;
+        u64 k[AP_SCAN];
 #pragma unroll
-            for (int j = 0; j < AP_SCAN; ++j) k[j] = __ldcg(&a.skeys[s0 + j * 32 + lane]);
+        for (int j = 0; j < AP_SCAN; ++j) k[j] = __ldcg(&a.skeys[s0 + j * AP_THREADS + tid]);
 #pragma unroll
-            for (int j = 0; j < AP_SCAN; ++j) {
-                const bool live = k[j] != EMPTY_KEY;
-                const u32 m = __ballot_sync(0xffffffffu, live);
-                if (live) {
-                    const u32 qi = (q_tail + __popc(m & lt_mask)) & (AP_QCAP - 1);
-                    qkey[qi] = k[j]; qslot[qi] = s0 + j * 32 + lane;
-                }
-                q_tail += __popc(m);
+        for (int j = 0; j < AP_SCAN; ++j) {
+            const bool live = k[j] != EMPTY_KEY;
+            const u32 m = __ballot_sync(0xffffffffu, live);
+            u32 at = 0;
+            if (lane == 0 && m) at = atomicAdd(&s_tail, (u32)__popc(m));
+            at = __shfl_sync(0xffffffffu, at, 0);
+            if (live) {
+                const u32 li = (at + __popc(m & lt_mask)) & (AP_LCAP - 1);
+                s_lkey[li] = k[j]; s_lslot[li] = s0 + j * AP_THREADS + tid;
             }
-            strip += gridDim.x * AP_WARPS;
-            more = strip < n_strips;
-            __syncwarp();
         }
-        u32 avail = q_tail - q_head;
-        while (avail >= 32u || (!more && avail > 0u)) {          // full rounds; the last one may be ragged
-            const u32 n = min(avail, 32u);
-            process(n);
+        tile += gridDim.x;
+        more = tile < n_tiles;
+        __syncthreads();
+        u32 avail = s_tail - head;                                // (nobody appends before the next barrier)
+        while (avail >= (u32)AP_THREADS || (!more && avail > 0u)) {   // full batches; the last one may be ragged
+            const u32 n = min(avail, (u32)AP_THREADS);
+            batch(n);
             avail -= n;
         }
-        __syncwarp();
-        if (!more) break;
     }
     flush_packed();
     acc_publish(acc, mc, false);
@@ -1578,6 +1786,8 @@ struct s3d_map {
     DevTables tab{};
     DevBuf<int> d_beam_col, d_nv_free, d_nv_occ;
     DevBuf<double> d_cos_b, d_sin_b, d_range, d_cos_va, d_sin_va;
+    DevBuf<float2> d_csva32;
+    bool tma_ok = true, fast32_ok = true, verify_fast = false;   // S3D_NO_TMA, S3D_NO_FAST32, S3D_VERIFY_FAST
     u64 samples_max = 0;             // worst-case samples per frame for these tables
     // chunk working set
     // chunk dedupe table: one allocation {counters[C][GF], keys[C], list[C]} so that a single L2
@@ -1636,8 +1846,8 @@ template <typename F> int preload(F f) { cudaFuncAttributes at; CU(cudaFuncGetAt
 int preload_pipeline_kernels()
 {
     int rc;
-    if ((rc = preload(k_expand<u32, false, true>)) || (rc = preload(k_expand<u32, true, true>)) ||
-        (rc = preload(k_expand<u64, false, true>)) || (rc = preload(k_expand<u32, false, false>)) ||
+    if ((rc = preload(k_expand<u32, false, true, false>)) || (rc = preload(k_expand<u32, true, true, false>)) ||
+        (rc = preload(k_expand<u64, false, true, false>)) || (rc = preload(k_expand<u32, false, false, false>)) ||
         (rc = preload(k_apply_chunk<u32, false>)) || (rc = preload(k_apply_chunk<u64, false>)) ||
         (rc = preload(k_route_signal)) || (rc = preload(k_route_wait)) ||
         (rc = preload(k_route_merge<u32, true>)) || (rc = preload(k_route_merge<u32, false>)) ||
@@ -1689,6 +1899,7 @@ int fatal_from_flags(s3d_map *m, u32 err)
     u32 zero = 0;   // clear so that the map stays usable after the caller handles the error
     cudaMemcpyAsync(&m->mc->err, &zero, sizeof zero, cudaMemcpyHostToDevice, m->stream);
     cudaStreamSynchronize(m->stream);
+    if (err & ERR_VERIFY) return fail(S3D_ECUDA, "S3D_VERIFY_FAST: an accepted fp32 voxel-index estimate differed from the fp64 key");
     if (err & ERR_TABLEFULL) return fail(S3D_ETABLEFULL, "voxel table full (capacity %llu slots)", (unsigned long long)m->cap);
     if (err & ERR_ROUTE_FULL) return fail(S3D_EROUTE, "routed map: a peer inbox overflowed (%llu records per pair; export a larger one)",
                                           (unsigned long long)m->route_cap);
@@ -1841,23 +2052,72 @@ int ensure_scratch(s3d_map *m, u64 want_cap, bool wipe, bool force_realloc = fal
     return 0;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tma_encoder()
+{
+    static EncodeTiledFn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+template <typename CT, bool CHECK>
+void launch_expand_t(s3d_map *m, const ExpandArgs &a, const CUtensorMap &tmap, int grid, size_t smem, cudaStream_t st)
+{
+    if (a.rt.world > 1) k_expand<CT, CHECK, true, false><<<grid, EX_THREADS, smem, st>>>(a, tmap);
+    else if (m->verify_fast) k_expand<CT, CHECK, false, true><<<grid, EX_THREADS, smem, st>>>(a, tmap);
+    else k_expand<CT, CHECK, false, false><<<grid, EX_THREADS, smem, st>>>(a, tmap);
+}
+
 void launch_expand(s3d_map *m, ExpandArgs &a, int n_beams, int g, cudaStream_t st)
 {
-    const size_t smem = expand_smem_bytes(a.tab.H, a.tab.free_step, a.tab.occ_window);
-    // beams per block: all warps of a block share the passes of its beams, so fewer beams per
-    // block means shorter blocks.  A small slice (a rank of a routed map) is cut finer so that
-    // the grid still has a few hundred blocks.
-    a.bpb = m->bpb_env > 0 ? std::min(m->bpb_env, EX_WARPS) : std::max(1, std::min(EX_WARPS, n_beams / 16));
-    const dim3 grid((n_beams + a.bpb - 1) / a.bpb, g);
-    if (a.rt.world > 1) {
-        if (m->wide) k_expand<u64, false, true><<<grid, EX_THREADS, smem, st>>>(a);
-        else if (m->narrow_safe) k_expand<u32, false, true><<<grid, EX_THREADS, smem, st>>>(a);
-        else k_expand<u32, true, true><<<grid, EX_THREADS, smem, st>>>(a);
-    } else {
-        if (m->wide) k_expand<u64, false, false><<<grid, EX_THREADS, smem, st>>>(a);
-        else if (m->narrow_safe) k_expand<u32, false, false><<<grid, EX_THREADS, smem, st>>>(a);
-        else k_expand<u32, true, false><<<grid, EX_THREADS, smem, st>>>(a);
+    const DevTables &t = a.tab;
+    a.n_frames = g;
+    a.fast32_ok = m->fast32_ok ? 1 : 0;
+    a.box_rows = strip_box_rows(t.H);
+    // The image strip of a tile goes through TMA when the frames can be described as a 2-D byte tensor
+    // whose 16-byte column strips hold whole groups of processed beams: regular beam columns, 16 | W,
+    // 16-byte aligned frames, and a strip that fits the combiner's memory.
+    const int per_strip = (t.col_step > 0 && TMA_STRIP_BYTES % t.col_step == 0) ? TMA_STRIP_BYTES / t.col_step : 0;
+    bool tma = m->tma_ok && tma_encoder() && per_strip > 0 && t.W % 16 == 0 && (reinterpret_cast<uintptr_t>(a.imgs) % 16 == 0) &&
+               a.img_stride % 16 == 0 && strip_smem_bytes(t.H) <= (sizeof(u32) * 2 + sizeof(unsigned short)) * LT_CAP &&
+               (u64)g * (u64)t.H < (1ull << 31);
+    // beams per tile: all warps of a block share the passes of its beams, so fewer beams per tile means
+    // shorter tiles.  A small slice (a rank of a routed map) is cut finer so that the launch still has a
+    // few hundred tiles.  With strips, a tile must not straddle two of them.
+    int bpb = m->bpb_env > 0 ? std::min(m->bpb_env, EX_MAXB) : std::max(1, std::min(EX_WARPS, n_beams / 16));
+    if (tma) {
+        int q = per_strip;
+        while (q > 1 && q > bpb) q /= 2;                 // largest power-of-two fraction of a strip that is <= the target
+        if (per_strip % q != 0 || a.beam_lo % q != 0) tma = false; else bpb = q;
     }
+    size_t smem = expand_smem_bytes(t.H, t.free_step, t.occ_window, bpb);
+    while (smem > 200 * 1024 && bpb > 1) { bpb = tma ? bpb / 2 : bpb - 1; smem = expand_smem_bytes(t.H, t.free_step, t.occ_window, bpb); }
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    if (tma) {
+        const cuuint64_t dims[2] = {(cuuint64_t)t.W, (cuuint64_t)g * (cuuint64_t)t.H};
+        const cuuint64_t strides[1] = {(cuuint64_t)t.W};
+        const cuuint32_t box[2] = {(cuuint32_t)TMA_STRIP_BYTES, (cuuint32_t)a.box_rows};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = tma_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(a.imgs), dims, strides, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) tma = false;
+    }
+    a.use_tma = tma ? 1 : 0;
+    a.bpb = bpb;
+    const int tiles = ((n_beams + bpb - 1) / bpb) * g;
+    const int grid = std::max(1, std::min(tiles, m->n_sm * EX_BPS));
+    if (m->wide) launch_expand_t<u64, false>(m, a, tmap, grid, smem, st);
+    else if (m->narrow_safe) launch_expand_t<u32, false>(m, a, tmap, grid, smem, st);
+    else launch_expand_t<u32, true>(m, a, tmap, grid, smem, st);
     m->launches += 1;
 }
 
@@ -1869,9 +2129,9 @@ u64 *trace_slot(s3d_map *m, int which)
 
 void launch_apply(s3d_map *m, u64 *skeys, void *scnt, int g, ChunkCtr *cc, DevStats *st, cudaStream_t stream)
 {
-    // autonomous warps, AP_STRIP slots per scan step; up to `apply_bps` blocks per SM
-    const u64 strips = m->scratch_cap / AP_STRIP;
-    const int blocks = (int)std::max<u64>(1, std::min<u64>((strips + AP_WARPS - 1) / AP_WARPS, (u64)m->n_sm * (u64)m->apply_bps));
+    // one tile of AP_TILE slots per block and step; up to `apply_bps` blocks per SM
+    const u64 tiles = m->scratch_cap / AP_TILE;
+    const int blocks = (int)std::max<u64>(1, std::min<u64>(tiles, (u64)m->n_sm * (u64)m->apply_bps));
     ApplyArgs a;
     a.skeys = skeys; a.scnt = scnt; a.n_slots = (u32)m->scratch_cap; a.g = g; a.cc = cc; a.st = st;
     a.table = m->table; a.tmask = m->cap - 1; a.p = m->p; a.sum_tab = m->sum_tab.p; a.mc = m->mc;
@@ -2251,6 +2511,9 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
     { const char *e = getenv("S3D_LOOKAHEAD"); if (e) m->lookahead_env = atoi(e); }
     { const char *e = getenv("S3D_BEAMS_PER_BLOCK"); if (e) m->bpb_env = atoi(e); }
     { const char *e = getenv("S3D_APPLY_BPS"); if (e && atoi(e) > 0) m->apply_bps = std::min(atoi(e), 8); }
+    { const char *e = getenv("S3D_NO_TMA"); if (e && atoi(e) != 0) m->tma_ok = false; }
+    { const char *e = getenv("S3D_NO_FAST32"); if (e && atoi(e) != 0) m->fast32_ok = false; }
+    { const char *e = getenv("S3D_VERIFY_FAST"); if (e && atoi(e) != 0) m->verify_fast = true; }
     { const char *e = getenv("S3D_SCRATCH_CAP"); if (e && atoll(e) > 0) m->scratch_env = (u64)atoll(e); }
     if (const char *e = getenv("S3D_TRACE")) if (atoi(e) != 0) {
         if (m->trace.ensure(s3d_map::TRACE_CHUNKS * s3d_map::TRACE_W)) return S3D_ENOMEM;
@@ -2316,6 +2579,7 @@ int s3d_destroy(s3d_map *m)
     if (m->stats_host) cudaFreeHost(m->stats_host);
     m->d_beam_col.release(); m->d_nv_free.release(); m->d_nv_occ.release();
     m->d_cos_b.release(); m->d_sin_b.release(); m->d_range.release(); m->d_cos_va.release(); m->d_sin_va.release();
+    m->d_csva32.release();
     m->spool.release(); m->sum_tab.release(); m->stats.release();
     m->img_dev.release(); m->T_dev.release(); m->img16_dev.release();
     for (Staging &s : m->stg) {
@@ -2381,7 +2645,7 @@ int s3d_set_tables(s3d_map *m, const s3d_tables *t)
         return fail(S3D_EINVAL, "bad table shape");
     if (t->free_step < 1 || t->occ_window < 0) return fail(S3D_EINVAL, "bad free_step/occ_window");
     if (t->H >= (1 << 16) || t->nv_max >= (1 << 15)) return fail(S3D_EINVAL, "H or nv_max too large");
-    const size_t ex_smem = expand_smem_bytes(t->H, t->free_step, t->occ_window);
+    const size_t ex_smem = expand_smem_bytes(t->H, t->free_step, t->occ_window, 1);
     if (ex_smem > 200 * 1024) return fail(S3D_EINVAL, "image height %d needs %zu bytes of shared memory per block", t->H, ex_smem);
     int rc = set_device(m); if (rc) return rc;
     if ((rc = sync_counters(m))) return rc;
@@ -2413,19 +2677,31 @@ int s3d_set_tables(s3d_map *m, const s3d_tables *t)
     if ((rc = upload(m->d_nv_occ, t->nv_occ, H, m->stream))) return rc;
     if ((rc = upload(m->d_cos_va, t->cos_va, nfan, m->stream))) return rc;
     if ((rc = upload(m->d_sin_va, t->sin_va, nfan, m->stream))) return rc;
+    std::vector<float2> cs32(std::max<size_t>(nfan, 1));
+    for (size_t i = 0; i < nfan; ++i) cs32[i] = make_float2((float)t->cos_va[i], (float)t->sin_va[i]);   // fp32 copy for the fast path
+    if ((rc = upload(m->d_csva32, cs32.data(), cs32.size(), m->stream))) return rc;
+    int col_step = nb > 1 ? t->beam_col[1] - t->beam_col[0] : 1;
+    for (size_t b = 0; b < nb && col_step > 0; ++b) if (t->beam_col[b] != (int)b * col_step) col_step = 0;
     CU(cudaStreamSynchronize(m->stream));     // host vectors go out of scope
     DevTables &d = m->tab;
     d.H = t->H; d.W = t->W; d.n_beams = t->n_beams; d.nv_max = t->nv_max;
     d.free_step = t->free_step; d.occ_window = t->occ_window;
     d.beam_col = m->d_beam_col.p; d.cos_b = m->d_cos_b.p; d.sin_b = m->d_sin_b.p; d.range_m = m->d_range.p;
     d.nv_free = m->d_nv_free.p; d.nv_occ = m->d_nv_occ.p; d.cos_va = m->d_cos_va.p; d.sin_va = m->d_sin_va.p;
+    d.csva32 = m->d_csva32.p; d.col_step = col_step > 0 ? col_step : 0;
     m->have_tables = true;
-    CU(cudaFuncSetAttribute(k_expand<u32, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
-    CU(cudaFuncSetAttribute(k_expand<u32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
-    CU(cudaFuncSetAttribute(k_expand<u64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
-    CU(cudaFuncSetAttribute(k_expand<u32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
-    CU(cudaFuncSetAttribute(k_expand<u32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
-    CU(cudaFuncSetAttribute(k_expand<u64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+    {
+        const int cap = 200 * 1024;
+        CU(cudaFuncSetAttribute(k_expand<u32, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(k_expand<u32, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(k_expand<u64, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(k_expand<u32, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(k_expand<u32, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(k_expand<u64, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(k_expand<u32, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(k_expand<u32, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(k_expand<u64, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    }
     CU(cudaFuncSetAttribute(k_apply_chunk<u64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes<u64>()));
     CU(cudaFuncSetAttribute(k_apply_chunk<u64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes<u64>()));
     m->h_range.assign(t->range_m, t->range_m + H);

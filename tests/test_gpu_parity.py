@@ -448,3 +448,27 @@ def test_api_fidelity_lists_bounds_and_float_images(s3d):
     sb = b.process_sonar_image(images[0].astype(np.float32) + 0.25, list(pos[0]), list(quat[0]))
     assert _stats3(sa) == _stats3(sb)
     assert_same_map(*a.octree.voxels.to_arrays(), *b.octree.voxels.to_arrays(), 0.0, "float image")
+
+
+@pytest.mark.parametrize("cfg_name,n_frames", [("cfg1", 6), ("cfg2", 8), ("cfg3", 2)])
+def test_fp32_estimate_never_disagrees_with_the_fp64_key(s3d, monkeypatch, cfg_name, n_frames):
+    """k_expand accepts the fp32 voxel-index estimate only outside a proven error band; with
+    S3D_VERIFY_FAST=1 every sample also takes the reference's fp64 arithmetic and an accepted estimate
+    that differs raises an error (millions of samples per config).  The same frames without TMA
+    staging and without the fp32 path must give the same map."""
+    from oracle.oracle import OracleMapper
+    from sonar_3d_reconstruction_b200 import synthetic
+    images, pos, quat, cfg = synthetic.make_sequence(cfg_name, n_frames, seed=5)
+    monkeypatch.setenv("S3D_VERIFY_FAST", "1")
+    v = s3d.SonarTo3DMapper(cfg)
+    sv = [_stats3(x) for x in v.process_sonar_images(images, pos, quat)]     # raises on a mismatch
+    monkeypatch.delenv("S3D_VERIFY_FAST")
+    cpu = OracleMapper(cfg)
+    want = [_stats3(cpu.process_sonar_image(images[f], pos[f], quat[f])) for f in range(n_frames)]
+    assert sv == want
+    assert assert_same_map(*v.octree.voxels.to_arrays(), *cpu.dump(), LOGODDS_ATOL, cfg_name) <= 1e-9
+    monkeypatch.setenv("S3D_NO_TMA", "1")
+    monkeypatch.setenv("S3D_NO_FAST32", "1")
+    plain = s3d.SonarTo3DMapper(cfg)
+    assert [_stats3(x) for x in plain.process_sonar_images(images, pos, quat)] == want
+    assert_same_map(*v.octree.voxels.to_arrays(), *plain.octree.voxels.to_arrays(), 0.0, "fp64-only, plain loads")

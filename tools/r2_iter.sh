@@ -1,11 +1,12 @@
 #!/bin/bash
-# usage: tools/r2_iter.sh <tag> [pytest-args]  -- GPU parity tests + cfg2/cfg3 bench lines
+# usage: tools/r2_iter.sh <tag> [pytest-args]  -- smoke, GPU parity tests, cfg2/cfg3 bench lines (each under its own timeout)
 TAG=$1; shift
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q "$@" 2>&1 | tail -15
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 || { echo "SMOKE FAILED/HUNG"; exit 1; }
+timeout 900 python -m pytest tests -m gpu -x -q "$@" 2>&1 | tail -15
 for wl in cfg2 cfg3; do
   extra=""; [ $wl = cfg3 ] && extra="--frames-per-step 128 --steps 4 --distinct-images 64"
-  python bench.py --workload $wl --no-cpu-baseline --no-e2e $extra > gpurun_out/${TAG}_$wl.json 2> gpurun_out/${TAG}_$wl.err || tail -c 800 gpurun_out/${TAG}_$wl.err
+  timeout 300 python bench.py --workload $wl --no-cpu-baseline --no-e2e $extra > gpurun_out/${TAG}_$wl.json 2> gpurun_out/${TAG}_$wl.err || tail -c 800 gpurun_out/${TAG}_$wl.err
 done
 python - <<PY
 import json
