@@ -1825,7 +1825,7 @@ struct s3d_map {
     bool debug_on = false;
     Slot *life = nullptr;            // same capacity / probing as the voxel table; val holds a u64 count
     DevBuf<ulonglong2> dbg_last; u32 *dbg_last_n = nullptr;
-    int apply_bps = 3;               // k_apply_chunk blocks per SM (S3D_APPLY_BPS)
+    int apply_bps = 2;               // k_apply_chunk blocks per SM (S3D_APPLY_BPS; measured at cfg2: 2 > 3 > 1 > 4 beside k_expand)
     // measurement
     bool prof_on = false;
     std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
@@ -2091,7 +2091,8 @@ void launch_expand(s3d_map *m, ExpandArgs &a, int n_beams, int g, cudaStream_t s
     // beams per tile: all warps of a block share the passes of its beams, so fewer beams per tile means
     // shorter tiles.  A small slice (a rank of a routed map) is cut finer so that the launch still has a
     // few hundred tiles.  With strips, a tile must not straddle two of them.
-    int bpb = m->bpb_env > 0 ? std::min(m->bpb_env, EX_MAXB) : std::max(1, std::min(EX_WARPS, n_beams / 16));
+    // (measured at cfg2: 4 beams per tile -- 1024 tiles per 16 frames -- beats 8, 2 and 1)
+    int bpb = m->bpb_env > 0 ? std::min(m->bpb_env, EX_MAXB) : std::max(1, std::min(EX_WARPS / 2, n_beams / 16));
     if (tma) {
         int q = per_strip;
         while (q > 1 && q > bpb) q /= 2;                 // largest power-of-two fraction of a strip that is <= the target
