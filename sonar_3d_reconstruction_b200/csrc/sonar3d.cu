@@ -96,6 +96,7 @@ struct MapCtr {       // device-resident map counters
     u32 last_unique;  // voxels touched by the last applied chunk
     u64 life_count;   // debug counters: keys in the lifetime sample-count table
     u64 life_max;     // debug counters: largest lifetime sample count of any voxel (3d_mapper.py:578)
+    u64 route_sent;   // routed map: 16-byte records this rank has written into peers' inboxes (NVLink traffic)
 };
 
 struct ChunkCtr {     // working counters of the chunk in flight (chunks are serialised on the stream)
@@ -244,12 +245,13 @@ __device__ __forceinline__ void route_wait_word(const u64 *word, u64 want, u64 t
 
 // publish to every peer how many records it got from this rank for the chunk, then the chunk's
 // sequence number + 1 (threads o < world of one block; all record stores are fenced before)
-__device__ __forceinline__ void route_signal(const RouteCtx &rt)
+__device__ __forceinline__ void route_signal(const RouteCtx &rt, MapCtr *mc)
 {
     const u32 o = threadIdx.x;
     if (o >= rt.world || o == rt.rank) return;
     u32 *cur = &rt.cursor[rt.parity * ROUTE_MAX_WORLD + o];
     const u64 cnt = min((u64)atomicAdd(cur, 0u), rt.cap);
+    if (mc) atomicAdd(&mc->route_sent, cnt);
     *cur = 0;                                              // this parity's next use is ROUTE_DEPTH chunks away, on this stream
     RouteHdr *h = reinterpret_cast<RouteHdr *>(rt.peer[o]);
     __threadfence_system();
@@ -491,7 +493,7 @@ __device__ __forceinline__ void expand_finish(const ExpandArgs &a)
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    route_signal(a.rt);
+    route_signal(a.rt, a.mc);
     if (threadIdx.x == 0) a.cc->xticket = 0;
 }
 
@@ -1446,7 +1448,7 @@ __global__ void k_route_wait(const u64 *words, u32 world, u32 rank, u64 want, u6
 }
 
 // a rank whose beam slice is empty still has to tell its peers that nothing is coming
-__global__ void k_route_signal(RouteCtx rt) { route_signal(rt); }
+__global__ void k_route_signal(RouteCtx rt) { route_signal(rt, nullptr); }
 
 // Owner side (its own stream: it runs beside this rank's own k_expand of the chunk -- both add into
 // the same dedupe table with atomics -- and beside the apply of the chunk before): merge the
@@ -1676,7 +1678,7 @@ __global__ void k_reset_ctr(MapCtr *mc)
     for (int q = 0; q < 3; ++q) { mc->kmin[q] = INT_MAX; mc->kmax[q] = INT_MIN; }
 }
 
-__global__ void k_init_life_ctr(MapCtr *mc) { mc->life_count = 0; mc->life_max = 0; }
+__global__ void k_init_life_ctr(MapCtr *mc) { mc->life_count = 0; mc->life_max = 0; mc->route_sent = 0; }
 
 // compact the lifetime table into {key, count} pairs (debug view voxel_update_counts)
 __global__ void k_dump_life(const Slot *__restrict__ life, u64 n_slots, ulonglong2 *out, u64 out_cap, u64 *cursor)
@@ -1772,6 +1774,7 @@ struct s3d_map {
     std::vector<unsigned char *> peer_ptr; std::vector<void *> ipc_opened;
     DevBuf<unsigned char *> d_peers; DevBuf<u32> route_cursor;
     u64 route_seq = 0;               // chunks routed so far (the same on every rank)
+    u64 route_sent_seen = 0;         // MapCtr::route_sent at the last s3d_profile_read
     u64 route_timeout_ns = 30000000000ull;   // S3D_ROUTE_TIMEOUT_MS
     int lookahead_env = 0;           // S3D_LOOKAHEAD (experiments)
     u64 scratch_env = 0;             // S3D_SCRATCH_CAP: first size of the chunk dedupe tables (tests force retries with a tiny one)
@@ -1788,6 +1791,7 @@ struct s3d_map {
     DevBuf<double> d_cos_b, d_sin_b, d_range, d_cos_va, d_sin_va;
     DevBuf<float2> d_csva32;
     bool tma_ok = true, fast32_ok = true, verify_fast = false;   // S3D_NO_TMA, S3D_NO_FAST32, S3D_VERIFY_FAST
+    bool serial = false;             // S3D_SERIAL_KERNELS: every pipeline kernel on one stream (exclusive per-kernel timings)
     u64 samples_max = 0;             // worst-case samples per frame for these tables
     // chunk working set
     // chunk dedupe table: one allocation {counters[C][GF], keys[C], list[C]} so that a single L2
@@ -2159,6 +2163,10 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     const int n_buf = (m->route_on && m->shard_world > 1) ? s3d_map::NBUF : s3d_map::NBUF - 1;
     s3d_map::ChunkBuf &cb = m->buf[m->chunk_seq % (u64)n_buf];
     cudaStream_t xs = (m->chunk_seq & 1) ? m->xstream2 : m->xstream, as = m->stream;
+    if (m->serial) {                 // measurement mode: no overlap, so the event spans are kernel durations
+        xs = as;
+        CU(cudaStreamWaitEvent(as, m->x_ev, 0));     // (submit_frames zeroed the counters on the expand stream)
+    }
     // ---- expand stream: first hits + expansion into this chunk's dedupe buffer.  It may run while
     // earlier chunks are still being expanded or applied; it only waits for its own buffer to be drained.
     if (cb.used) CU(cudaStreamWaitEvent(xs, cb.freed, 0));
@@ -2513,6 +2521,7 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
     { const char *e = getenv("S3D_BEAMS_PER_BLOCK"); if (e) m->bpb_env = atoi(e); }
     { const char *e = getenv("S3D_APPLY_BPS"); if (e && atoi(e) > 0) m->apply_bps = std::min(atoi(e), 8); }
     { const char *e = getenv("S3D_NO_TMA"); if (e && atoi(e) != 0) m->tma_ok = false; }
+    { const char *e = getenv("S3D_SERIAL_KERNELS"); if (e && atoi(e) != 0) m->serial = true; }
     { const char *e = getenv("S3D_NO_FAST32"); if (e && atoi(e) != 0) m->fast32_ok = false; }
     { const char *e = getenv("S3D_VERIFY_FAST"); if (e && atoi(e) != 0) m->verify_fast = true; }
     { const char *e = getenv("S3D_SCRATCH_CAP"); if (e && atoll(e) > 0) m->scratch_env = (u64)atoll(e); }
@@ -3438,6 +3447,12 @@ int s3d_profile_read(s3d_map *m, s3d_profile *out)
     CU(cudaStreamSynchronize(m->stream));
     m->prof.total_launches = m->launches;
     m->prof.retries = m->n_retries; m->prof.grows = m->n_grows;
+    {
+        MapCtr h;
+        CU(cudaMemcpy(&h, m->mc, sizeof h, cudaMemcpyDeviceToHost));
+        m->prof.route_records_sent = h.route_sent - m->route_sent_seen;
+        m->route_sent_seen = h.route_sent;
+    }
     *out = m->prof;
     m->prof = s3d_profile{};
     m->launches = 0; m->n_retries = 0; m->n_grows = 0;

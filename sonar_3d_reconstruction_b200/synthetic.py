@@ -91,13 +91,14 @@ def make_poses(rng: np.random.Generator, n: int, *, step_m: float = 0.05, leg_m:
     return pos, quat
 
 
-def make_sequence(name_or_spec, n_frames: int, seed: int = 0, distinct_images: int = 0):
+def make_sequence(name_or_spec, n_frames: int, seed: int = 0, distinct_images: int = 0, cycle: bool = True):
     """Frames + poses for a named workload.
 
     Returns (images uint8[n,H,W], positions[n,3], quaternions[n,4], config dict).  With
     ``distinct_images`` > 0 only that many distinct images are generated and cycled
     (poses stay distinct) -- generating thousands of 256 KB frames on the host is slow
     and the kernels' work depends on the pose, not on which speckle realisation is used.
+    ``cycle=False`` returns only the distinct images (frame f uses image f % len(images)).
     """
     spec = CONFIGS[name_or_spec] if isinstance(name_or_spec, str) else name_or_spec
     cfg = dict(spec["config"])
@@ -108,6 +109,6 @@ def make_sequence(name_or_spec, n_frames: int, seed: int = 0, distinct_images: i
                                 max_range=cfg.get("max_range", 10.0),
                                 threshold=cfg.get("intensity_threshold", 35),
                                 seabed_depth=spec.get("seabed_depth", 4.0)) for _ in range(k)])
-    images = base if k == n_frames else base[np.arange(n_frames) % k]
+    images = base if (k == n_frames or not cycle) else base[np.arange(n_frames) % k]
     pos, quat = make_poses(rng, n_frames, step_m=spec.get("step_m", 0.05))
     return images, pos, quat, cfg

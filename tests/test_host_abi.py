@@ -43,7 +43,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_native.Params) == 8 * 8 + 4 * 4
     assert C.sizeof(_native.FrameStats) == 64 and _native.STATS_DTYPE.itemsize == 64
     assert C.sizeof(_native.Tables) == 6 * 4 + 8 * 8
-    assert C.sizeof(_native.Profile) == 3 * 8 + 3 * 8 + 4 * 8
+    assert C.sizeof(_native.Profile) == 3 * 8 + 3 * 8 + 5 * 8
 
 
 @pytest.mark.skipif(_cuda(), reason="only meaningful on a host without a GPU")
@@ -170,7 +170,8 @@ def test_reference_arm_of_the_bench_prints_one_json_line():
     import subprocess
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                        "--ref-frames-per-step", "4"], capture_output=True, text=True, timeout=300)
+                        "--ref-frames-per-step", "4", "--ref-port", "--frames-per-step", "16", "--distinct-images", "8"],
+                       capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -179,3 +180,11 @@ def test_reference_arm_of_the_bench_prints_one_json_line():
     assert d["value"] > 0 and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # with the unmodified reference shipped next to the repo (baseline/_ref, copied by build() in the build
+    # container) the same arm times that file instead
+    if os.path.exists(os.path.join(ROOT, "baseline", "_ref", "3d_mapper.py")):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                            "--frames-per-step", "4", "--distinct-images", "4"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        d = json.loads([l for l in r.stdout.strip().splitlines() if l.startswith("{")][0])
+        assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["port_value"] > d["value"] > 0
