@@ -595,7 +595,7 @@ def run_sharded(args, rank, world, local_rank):
             same_keys = len(ks64) == len(kp64) and bool(np.array_equal(ks64[o1], kp64[o2]))
             same_L = same_keys and bool(np.array_equal(np.asarray(ls)[o1], np.asarray(lp)[o2]))
             same_stats = bool(np.array_equal(stats_sh[:, :4], pst[:, :4]))
-            par = parity_check(pst, kp, lp, wl, cfg, min(n_par, 48))
+            par = parity_check(pst, kp, lp, wl, cfg, n_par)
             par["sharded_vs_single_gpu"] = {"frames": n_par, "keys_identical": same_keys, "logodds_bit_identical": same_L,
                                             "counters_identical": same_stats}
             par["ok"] = bool(par["ok"] and same_keys and same_L and same_stats)

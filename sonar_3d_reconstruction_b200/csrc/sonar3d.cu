@@ -2721,8 +2721,12 @@ int s3d_set_tables(s3d_map *m, const s3d_tables *t)
     update_count_bound(m);
     // first guess for the chunk dedupe table; it doubles on demand (retry) from here
     // (a rank of a sharded map holds about 1/world of the entries; 1.5x margin, it doubles on demand)
-    const u64 share = m->shard_world > 1 ? (m->samples_max / 4) * 3 / (2 * (u64)m->shard_world) : m->samples_max / 4;
-    return ensure_scratch(m, m->scratch_env ? m->scratch_env : std::min<u64>(1u << 20, std::max<u64>(1u << 14, share)), false);
+    // (a rank of a routed map cannot re-run a chunk -- its peers have moved on -- so it starts from half the
+    // worst case, every sample of 16 frames a voxel of its own, split over the ranks; from then on the table
+    // doubles ahead of need from the counts of the chunks before, as on a single map)
+    u64 want = std::min<u64>(1u << 20, std::max<u64>(1u << 14, m->samples_max / 4));
+    if (m->shard_world > 1) want = std::min<u64>(1u << 22, std::max<u64>(1u << 16, m->samples_max * GF / (2 * (u64)m->shard_world)));
+    return ensure_scratch(m, m->scratch_env ? m->scratch_env : want, false);
 }
 
 int s3d_ingest_batch_dev(s3d_map *m, const uint8_t *images_dev, int64_t n, const double *T_dev,
