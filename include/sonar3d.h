@@ -207,6 +207,14 @@ int s3d_export_read(s3d_map *map, double *xyz, double *prob, int8_t *cls, int32_
 /* Same result as the PointCloud2 payload of the reference node: little-endian float32
  * x, y, z, intensity=probability, 16-byte stride (scripts/3d_mapper_node.py:419-443). */
 int s3d_export_read_xyzi32(s3d_map *map, float *xyzi, uint64_t n);
+/* The node's classified display (publish_marker_array, scripts/3d_mapper_node.py:448-527) fills one
+ * CUBE_LIST marker per class with the voxel centres as geometry_msgs/Point (3 x float64).
+ * s3d_export_markers classifies as s3d_export_begin does and stages all centres grouped by class --
+ * [FREE | UNKNOWN | OCCUPIED], counts[c] points each -- so that each marker's `points` is one contiguous
+ * block; s3d_export_read_markers copies the 3 * (counts[0] + counts[1] + counts[2]) doubles out
+ * (SURVEY.md section 8f, row n1). */
+int s3d_export_markers(s3d_map *map, double thr_occ, double thr_free, uint64_t counts[3]);
+int s3d_export_read_markers(s3d_map *map, double *xyz, uint64_t n_total);
 
 /* ---- sharded map (one process per GPU) ---------------------------------- */
 

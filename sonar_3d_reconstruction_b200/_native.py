@@ -21,7 +21,7 @@ SYMBOLS = (
     "s3d_shard_config", "s3d_shard_filter", "s3d_shard_owner", "s3d_shard_expand", "s3d_shard_apply",
     "s3d_route_export", "s3d_route_attach", "s3d_route_enable", "s3d_trace_read", "s3d_ingest_batch_mono16",
     "s3d_ingest_submit", "s3d_ingest_collect",
-    "s3d_extend_bounds", "s3d_reset_bounds", "s3d_debug_counters", "s3d_debug_last_frame", "s3d_debug_totals",
+    "s3d_export_markers", "s3d_export_read_markers", "s3d_extend_bounds", "s3d_reset_bounds", "s3d_debug_counters", "s3d_debug_last_frame", "s3d_debug_totals",
 )
 
 
@@ -123,6 +123,8 @@ def load_library():
     L.s3d_shard_owner.argtypes = [i32p, C.c_int64, C.c_int, i32p]
     L.s3d_shard_expand.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(vp), u64p]
     L.s3d_shard_apply.argtypes = [vp, vp, C.c_uint64, C.c_int, vp]
+    L.s3d_export_markers.argtypes = [vp, C.c_double, C.c_double, u64p]
+    L.s3d_export_read_markers.argtypes = [vp, dp, C.c_uint64]
     L.s3d_extend_bounds.argtypes = [vp, i32p, i32p]
     L.s3d_reset_bounds.argtypes = [vp]
     L.s3d_debug_counters.argtypes = [vp, C.c_int]
@@ -375,6 +377,17 @@ class NativeMap:
         kmax = np.zeros(3, dtype=np.int32)
         _check(self._lib.s3d_bounds(self._h, _ptr(kmin, C.c_int32), _ptr(kmax, C.c_int32)))
         return kmin, kmax
+
+    def export_markers(self, thr_occ: float, thr_free: float):
+        """Voxel centres grouped by class: {class id: float64[n_c, 3]} (views of one buffer)."""
+        counts = (C.c_uint64 * 3)()
+        _check(self._lib.s3d_export_markers(self._h, float(thr_occ), float(thr_free), counts))
+        n = [int(c) for c in counts]
+        buf = np.empty((sum(n), 3), dtype=np.float64)
+        if sum(n):
+            _check(self._lib.s3d_export_read_markers(self._h, _ptr(buf, C.c_double), sum(n)))
+        a, b = n[0], n[0] + n[1]
+        return {self.CLASS_FREE: buf[:a], self.CLASS_UNKNOWN: buf[a:b], self.CLASS_OCCUPIED: buf[b:]}
 
     # -- export -------------------------------------------------------------------------
     def export(self, thr_occ: float, thr_free: float, class_mask: int, want=("xyz", "prob", "cls")):

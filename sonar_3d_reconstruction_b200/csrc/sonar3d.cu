@@ -1648,6 +1648,44 @@ k_export(const Slot *__restrict__ table, u64 n_slots, double res, double thr_occ
     if (threadIdx.x < 3 && s_cnt[threadIdx.x]) atomicAdd(&o.counts[threadIdx.x], (u64)s_cnt[threadIdx.x]);
 }
 
+// CUBE_LIST payloads (scripts/3d_mapper_node.py:448-527): the voxel centres of each class as one contiguous run of
+// geometry_msgs/Point (3 x float64); base[c] = first point of class c (from a counting pass), cursor[c] = fill
+__global__ void __launch_bounds__(256)
+k_export_grouped(const Slot *__restrict__ table, u64 n_slots, double res, double thr_occ, double thr_free,
+                 const u64 *__restrict__ base, u64 *cursor, double *__restrict__ xyz)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const u64 n_iter = (n_slots + stride - 1) / stride;      // uniform trip count keeps ballots full-warp
+    const u32 lane = threadIdx.x & 31;
+    for (u64 it = 0; it < n_iter; ++it) {
+        const u64 i = it * stride + blockIdx.x * (u64)blockDim.x + threadIdx.x;
+        int cls = -1; u64 key = 0;
+        if (i < n_slots) {
+            const ulonglong2 raw = __ldcs(reinterpret_cast<const ulonglong2 *>(&table[i]));
+            if (raw.x != EMPTY_KEY) {
+                key = raw.x;
+                const double L = __longlong_as_double((long long)raw.y);
+                cls = L < thr_free ? S3D_CLASS_FREE : (L > thr_occ ? S3D_CLASS_OCCUPIED : S3D_CLASS_UNKNOWN);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const u32 b = __ballot_sync(0xffffffffu, cls == c);
+            if (!b) continue;
+            u64 at = 0;
+            if (lane == (u32)__ffs(b) - 1) at = atomicAdd(&cursor[c], (u64)__popc(b));
+            at = __shfl_sync(0xffffffffu, at, __ffs(b) - 1);
+            if (cls == c) {
+                const u64 dst = base[c] + at + __popc(b & ((1u << lane) - 1));
+                int ki, kj, kk; unpack_key(key, ki, kj, kk);
+                xyz[3 * dst] = __dmul_rn((double)ki + 0.5, res);         // key_to_world (:78-80)
+                xyz[3 * dst + 1] = __dmul_rn((double)kj + 0.5, res);
+                xyz[3 * dst + 2] = __dmul_rn((double)kk + 0.5, res);
+            }
+        }
+    }
+}
+
 __global__ void k_pack_xyzi32(const double *__restrict__ xyz, const double *__restrict__ prob, u64 n,
                               float4 *__restrict__ out)
 {
@@ -1825,6 +1863,7 @@ struct s3d_map {
     // export staging
     DevBuf<double> ex_xyz, ex_prob, ex_L; DevBuf<int8_t> ex_cls; DevBuf<int> ex_ijk; DevBuf<float4> ex_f32;
     u64 *ex_counts = nullptr; u64 *ex_counts_host = nullptr; u64 ex_n = 0; bool ex_valid = false;
+    u64 mk_n = ~0ull;                // points staged by s3d_export_markers (~0 = none)
     // debug counters: lifetime sample counts per voxel key + the last frame's per-key counts
     bool debug_on = false;
     Slot *life = nullptr;            // same capacity / probing as the voxel table; val holds a u64 count
@@ -2250,7 +2289,7 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     CU(cudaEventRecord(m->snap_ev[ri], m->snap_stream));
     m->inflight[ri] = InFlight{m->chunk_seq, j.id, base, g};
     ++m->chunk_seq;
-    m->ex_valid = false;
+    m->ex_valid = false; m->mk_n = ~0ull;
     return 0;
 }
 
@@ -3309,6 +3348,39 @@ int s3d_export_read(s3d_map *m, double *xyz, double *prob, int8_t *cls, int32_t 
     if (prob) CU(cudaMemcpyAsync(prob, m->ex_prob.p, sizeof(double) * n, cudaMemcpyDeviceToHost, m->stream));
     if (cls) CU(cudaMemcpyAsync(cls, m->ex_cls.p, n, cudaMemcpyDeviceToHost, m->stream));
     if (ijk) CU(cudaMemcpyAsync(ijk, m->ex_ijk.p, sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int s3d_export_markers(s3d_map *m, double thr_occ, double thr_free, uint64_t counts[3])
+{
+    if (!m || !m->have_params || !counts) return fail(S3D_EINVAL, "map not ready (params) or null argument");
+    uint64_t n_staged = 0;
+    int rc = s3d_export_begin(m, thr_occ, thr_free, 0u, counts, &n_staged);      // counting pass: nothing staged
+    if (rc) return rc;
+    const u64 total = counts[0] + counts[1] + counts[2];
+    m->ex_valid = false;
+    m->mk_n = total;
+    if (total == 0) return 0;
+    if ((rc = m->ex_xyz.ensure(3 * (size_t)total))) return rc;
+    u64 h[6] = {0, counts[S3D_CLASS_FREE], counts[S3D_CLASS_FREE] + counts[S3D_CLASS_UNKNOWN], 0, 0, 0};   // bases, cursors
+    DevBuf<u64> d; if ((rc = d.ensure(6))) return rc;
+    CU(cudaMemcpyAsync(d.p, h, sizeof h, cudaMemcpyHostToDevice, m->stream));
+    const int blocks = (int)std::min<u64>((m->cap + 255) / 256, (u64)m->n_sm * 8);
+    k_export_grouped<<<blocks, 256, 0, m->stream>>>(m->table, m->cap, m->p.res, thr_occ, thr_free, d.p, d.p + 3, m->ex_xyz.p);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(m->stream));
+    d.release();
+    return 0;
+}
+
+int s3d_export_read_markers(s3d_map *m, double *xyz, uint64_t n_total)
+{
+    if (!m || !xyz) return fail(S3D_EINVAL, "null argument");
+    if (n_total != m->mk_n) return fail(S3D_EINVAL, "n_total does not match the staged markers (call s3d_export_markers; the map must not change in between)");
+    if (n_total == 0) return 0;
+    int rc = set_device(m); if (rc) return rc;
+    CU(cudaMemcpyAsync(xyz, m->ex_xyz.p, sizeof(double) * 3 * n_total, cudaMemcpyDeviceToHost, m->stream));
     CU(cudaStreamSynchronize(m->stream));
     return 0;
 }

@@ -645,6 +645,23 @@ class SonarTo3DMapper:
         r = self.octree._export_occupied(self.min_probability, want=("xyzi32",))
         return r["xyzi32"]
 
+    def get_marker_arrays(self) -> Dict[str, Dict[str, Any]]:
+        """The node's classified display without per-voxel Python objects (extension): for each
+        class the CUBE_LIST marker's `points` as one float64[n,3] block (geometry_msgs/Point layout), its
+        colour and scale exactly as publish_marker_array sets them (scripts/3d_mapper_node.py:459-522);
+        classes are those of get_all_voxels_classified(self.min_probability), grouped on the device."""
+        oc = self.octree
+        oc._push_params()
+        free_threshold = float(np.log(0.3 / 0.7))
+        occupied_threshold = float(np.log(self.min_probability / (1.0 - self.min_probability)))
+        r = oc._native.export_markers(occupied_threshold, free_threshold)
+        res = self.voxel_resolution
+        return {
+            'occupied': {'points': r[NativeMap.CLASS_OCCUPIED], 'rgba': (1.0, 0.0, 0.0, 0.8), 'scale': res},
+            'free': {'points': r[NativeMap.CLASS_FREE], 'rgba': (0.0, 0.0, 1.0, 0.3), 'scale': res},
+            'unknown': {'points': r[NativeMap.CLASS_UNKNOWN], 'rgba': (1.0, 1.0, 0.0, 0.5), 'scale': res},
+        }
+
     def reset_map(self):
         self.octree.clear()
         self.frame_count = 0

@@ -148,6 +148,12 @@ class Exchange:
             _dist().all_reduce(t, group=self.group)
         return t
 
+    def all_reduce_max(self, t):
+        if self.world > 1:
+            dist = _dist()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
     def all_gather_rows(self, t):
         """Concatenate per-rank [n_r, ...] tensors (n_r differs) along dim 0, same result on every rank."""
         import torch
@@ -283,6 +289,15 @@ class CudaShardBackend:
         r = self.mapper.octree._export_occupied(min_probability)
         return r["xyz"], r["prob"]
 
+    def export_classified(self, min_probability: float):
+        """{class name: (centres float64[n,3], probabilities float64[n])} of this rank's shard."""
+        cl = self.mapper.octree.get_all_voxels_classified(min_probability)
+        return {name: (seq.points.reshape(-1, 3), seq.probabilities.reshape(-1)) for name, seq in cl.items()}
+
+    def bounds(self):
+        oc = self.mapper.octree
+        return oc.min_bounds.copy(), oc.max_bounds.copy()
+
     def dump(self):
         return self.native.dump()
 
@@ -395,7 +410,25 @@ class ShardedSonarMapper:
 
     def get_point_cloud(self, include_free: bool = False) -> Dict[str, Any]:
         if include_free:
-            raise NotImplementedError("sharded export covers the occupied cloud (include_free=False)")
+            # every rank classifies its shard on the device (:155-188), the three lists are all-gathered and the
+            # bounds (:113-115) reduced: the same dict as the reference's :612-633 on every rank
+            from .mapper import _PointProbList
+            cl = self.backend.export_classified(self.mapper.min_probability)
+            out = {}
+            for name in ("occupied", "free", "unknown"):
+                xyz, prob = cl[name]
+                both = np.concatenate([np.asarray(xyz, dtype=np.float64).reshape(-1, 3), np.asarray(prob, dtype=np.float64).reshape(-1, 1)], axis=1)
+                allp = self.ex.all_gather_rows(self.backend.tensor(both)).cpu().numpy()
+                out[name] = _PointProbList(np.ascontiguousarray(allp[:, :3]), np.ascontiguousarray(allp[:, 3]))
+            mn, mx = self.backend.bounds()
+            ext = self.ex.all_reduce_max(self.backend.tensor(np.concatenate([-np.asarray(mn, dtype=np.float64),
+                                                                             np.asarray(mx, dtype=np.float64)]))).cpu().numpy()
+            dyn = bool(getattr(self.mapper, "dynamic_expansion", True))
+            return {'occupied': out['occupied'], 'free': out['free'], 'unknown': out['unknown'],
+                    'num_voxels': self.num_voxels(), 'num_occupied': len(out['occupied']), 'num_free': len(out['free']),
+                    'num_unknown': len(out['unknown']), 'frame_count': self.frame_count,
+                    'processed_count': self.processed_frame_count,
+                    'bounds': {'min': -ext[:3] if dyn else None, 'max': ext[3:] if dyn else None}}
         xyz, prob = self.backend.export_occupied(self.mapper.min_probability)
         both = np.concatenate([xyz.reshape(-1, 3), prob.reshape(-1, 1)], axis=1)
         allp = self.ex.all_gather_rows(self.backend.tensor(both)).cpu().numpy()

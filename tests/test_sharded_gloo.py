@@ -165,6 +165,19 @@ class _OracleBackend:
         pc = self.o.get_point_cloud()
         return pc["points"], pc["probabilities"]
 
+    def export_classified(self, min_probability):
+        self.o.min_probability = min_probability
+        pc = self.o.get_point_cloud(True)
+        out = {}
+        for name in ("occupied", "free", "unknown"):
+            pts = np.array([p for p, _ in pc[name]], dtype=np.float64).reshape(-1, 3)
+            out[name] = (pts, np.array([q for _, q in pc[name]], dtype=np.float64))
+        return out
+
+    def bounds(self):
+        pc = self.o.get_point_cloud(True)
+        return np.asarray(pc["bounds"]["min"], dtype=np.float64), np.asarray(pc["bounds"]["max"], dtype=np.float64)
+
     def dump(self):
         return self.o.dump()
 
@@ -193,9 +206,14 @@ def _worker(rank, world, port, out_dir, mode):
     stats = m.process_sonar_images(images, pos, quat)
     keys, L = m.gather_map()
     pc = m.get_point_cloud()
+    pcf = m.get_point_cloud(include_free=True)
     nv = m.num_voxels()
     if rank == 0:
+        cls_pts = {n: np.array([p for p, _ in pcf[n]], dtype=np.float64).reshape(-1, 3) for n in ("occupied", "free", "unknown")}
         np.savez(os.path.join(out_dir, "sharded.npz"), keys=keys, L=L,
+                 cls_counts=np.array([pcf["num_occupied"], pcf["num_free"], pcf["num_unknown"], pcf["num_voxels"]]),
+                 cls_occupied=cls_pts["occupied"], cls_free=cls_pts["free"], cls_unknown=cls_pts["unknown"],
+                 bounds_min=pcf["bounds"]["min"], bounds_max=pcf["bounds"]["max"],
                  stats=np.array([[s["num_occupied"], s["num_free"], s["num_voxels"], s["num_samples"]] for s in stats]),
                  pc_points=pc["points"], pc_prob=pc["probabilities"], nv=nv, exch=m.last_exchange_bytes)
     dist.barrier()
@@ -226,6 +244,14 @@ def test_two_rank_gloo_equals_single_rank_oracle(tmp_path, mode):
     b = sort_by_key(np.floor(pc["points"] / res), pc["probabilities"])
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     assert (int(z["exch"]) > 0) == (mode == "route")
+    # classified export (include_free=True): the three class sets and the bounds of the 1-rank map
+    pcf = o.get_point_cloud(True)
+    assert z["cls_counts"].tolist() == [pcf["num_occupied"], pcf["num_free"], pcf["num_unknown"], len(k)]
+    for name in ("occupied", "free", "unknown"):
+        want_pts = np.array([p for p, _ in pcf[name]], dtype=np.float64).reshape(-1, 3)
+        got = z["cls_" + name]
+        assert np.array_equal(got[np.lexsort(got.T[::-1])], want_pts[np.lexsort(want_pts.T[::-1])]), name
+    assert np.array_equal(z["bounds_min"], pcf["bounds"]["min"]) and np.array_equal(z["bounds_max"], pcf["bounds"]["max"])
 
 
 def test_owner_hash_and_key_packing_match_the_library():
