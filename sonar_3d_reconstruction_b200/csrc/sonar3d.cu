@@ -209,7 +209,7 @@ constexpr float MAGICF = 12582912.0f;        // 1.5 * 2^23: adding it (round dow
 // waits for all sources, merges the records into its dedupe table, and acknowledges, which
 // lets the sources reuse that parity for chunk c + ROUTE_DEPTH.
 constexpr int ROUTE_MAX_WORLD = 64;
-constexpr int ROUTE_DEPTH = 4;            // inbox regions per source: chunk c uses region c % ROUTE_DEPTH ("parity")
+constexpr int ROUTE_DEPTH = 16;           // inbox regions per source: chunk c uses region c % ROUTE_DEPTH ("parity")
 struct __align__(16) RouteRec { u64 key; u32 counts; u32 frame; };      // counts = n_occ << 16 | n_free
 struct RouteHdr {
     u64 flag_count[ROUTE_DEPTH][ROUTE_MAX_WORLD];   // [parity][source]: records the source wrote for the chunk
@@ -1795,7 +1795,7 @@ struct s3d_map {
     MapCtr *mc_host = nullptr;       // pinned mirror
     u64 count_known = 0;             // live voxels at the last sync / chunk snapshot
     u64 unique_est = 0;              // voxels touched by a recent chunk (upper bound of what it can insert)
-    static constexpr int RING = 8;   // per-chunk counter snapshots (bounded launch-ahead)
+    static constexpr int RING = 40;  // per-chunk counter snapshots (bounded launch-ahead)
     MapCtr *snap_host = nullptr;     // pinned [RING]
     cudaEvent_t snap_ev[RING] = {};
     InFlight inflight[RING];
@@ -1808,6 +1808,7 @@ struct s3d_map {
     bool shard_filter = false;       // replicated expansion: s3d_ingest* keeps only the voxels this rank owns
     // routed map: exchange block (flags + inboxes) of this rank, the peers' blocks, local cursors
     bool route_on = false;
+    bool route_by_chunk = true;      // routed map: ranks take turns expanding whole chunks (S3D_ROUTE_SPLIT=beams: beam slices)
     unsigned char *xblock = nullptr; size_t xblock_bytes = 0; u64 route_cap = 0;
     std::vector<unsigned char *> peer_ptr; std::vector<void *> ipc_opened;
     DevBuf<unsigned char *> d_peers; DevBuf<u32> route_cursor;
@@ -2223,9 +2224,17 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     a.rt = RouteCtx{1u, 0u, 0u, 0ull, nullptr, nullptr, 0ull, 0ull};
     const bool routed = m->route_on && m->shard_world > 1;
     if (routed) {
-        // this rank's contiguous slice of the processed beams; voxels of other owners travel to them
-        a.beam_lo = (int)((int64_t)tab.n_beams * m->shard_rank / m->shard_world);
-        a.beam_hi = (int)((int64_t)tab.n_beams * (m->shard_rank + 1) / m->shard_world);
+        if (m->route_by_chunk) {
+            // split by chunks: rank (c mod world) expands every beam of chunk c -- a launch as large as a single
+            // GPU's, so the expansion scales with the ranks -- and the others only tell their peers that nothing is
+            // coming from them; voxels of other owners travel to them
+            const bool mine = (int)(m->route_seq % (u64)m->shard_world) == m->shard_rank;
+            a.beam_lo = 0; a.beam_hi = mine ? tab.n_beams : 0;
+        } else {
+            // split by beams: this rank's contiguous slice of the processed beams of every chunk
+            a.beam_lo = (int)((int64_t)tab.n_beams * m->shard_rank / m->shard_world);
+            a.beam_hi = (int)((int64_t)tab.n_beams * (m->shard_rank + 1) / m->shard_world);
+        }
         a.own_world = 1u;
         a.rt = RouteCtx{(u32)m->shard_world, (u32)m->shard_rank, (u32)(m->route_seq % ROUTE_DEPTH), m->route_cap, m->d_peers.p,
                         m->route_cursor.p, m->route_seq, m->route_timeout_ns};
@@ -2342,8 +2351,10 @@ int pump(s3d_map *m, bool drain)
     // its chunk buffers (buffer reuse is ordered on the device by events), which keeps the host's
     // wait for an old snapshot and its launch latency off the critical path of the exchange; a
     // single map runs best with a short queue (more chunks in flight only fight over L2).
+    // (split by chunks: `world` chunks are being expanded at a time, one per rank, so the queue must reach past them)
+    const bool routed_q = m->route_on && m->shard_world > 1;
     const int LOOKAHEAD = m->lookahead_env > 0 ? std::min(m->lookahead_env, s3d_map::RING - 2)
-                                               : (m->route_on && m->shard_world > 1 ? 5 : 2);
+                                               : (routed_q ? (m->route_by_chunk ? std::min(s3d_map::RING - 2, std::max(6, 2 * m->shard_world + 2)) : 5) : 2);
     // (an inbox region is reused on the expand stream that used it before; a chunk buffer may change
     // streams, its reuse is ordered by the `freed` event behind the apply that drained it)
     static_assert(ROUTE_DEPTH % 2 == 0, "an inbox region is always reused on the same expand stream");
@@ -2560,6 +2571,7 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
     { const char *e = getenv("S3D_BEAMS_PER_BLOCK"); if (e) m->bpb_env = atoi(e); }
     { const char *e = getenv("S3D_APPLY_BPS"); if (e && atoi(e) > 0) m->apply_bps = std::min(atoi(e), 8); }
     { const char *e = getenv("S3D_NO_TMA"); if (e && atoi(e) != 0) m->tma_ok = false; }
+    { const char *e = getenv("S3D_ROUTE_SPLIT"); if (e && !strcmp(e, "beams")) m->route_by_chunk = false; }
     { const char *e = getenv("S3D_SERIAL_KERNELS"); if (e && atoi(e) != 0) m->serial = true; }
     { const char *e = getenv("S3D_NO_FAST32"); if (e && atoi(e) != 0) m->fast32_ok = false; }
     { const char *e = getenv("S3D_VERIFY_FAST"); if (e && atoi(e) != 0) m->verify_fast = true; }

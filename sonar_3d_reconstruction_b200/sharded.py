@@ -329,9 +329,11 @@ class ShardedSonarMapper:
         else:
             self.mapper, self.backend = backend_factory(config, self.rank, self.world)
         if mode == "fused":
-            # records per (source, owner, chunk) inbox region; 16 bytes each, 4 regions deep (config key, optional)
+            # records per (source, owner, chunk) inbox region; 16 bytes each, 16 regions deep: at most 4 GiB per rank
+            # unless the config says otherwise (a region must hold every record one rank sends to one owner for a chunk)
+            default = min(1 << 22, (4 << 30) // (16 * 16 * max(1, self.world)))
             self.backend.set_mode(mode, exchange=self.ex,
-                                  inbox_records=int((config or {}).get("route_inbox_records", 1 << 22)))
+                                  inbox_records=int((config or {}).get("route_inbox_records", default)))
         else:
             self.backend.set_mode(mode)
         self.frame_count = 0
