@@ -222,10 +222,10 @@ int s3d_export_read_markers(s3d_map *map, double *xyz, uint64_t n_total);
  * rank expands its slice of the processed beams of every frame, the per-(voxel, frame) integer
  * counts travel to the owning rank by all-to-all (the caller moves the bytes, e.g. with NCCL
  * through torch.distributed), and the owner merges and applies them.  Integer merges make the
- * N-rank result identical to the 1-rank result.  A record is 17 uint64: the packed key and the
- * (n_occ << 32 | n_free) counter of each of the up-to-16 frames of the chunk. */
-#define S3D_RECORD_WORDS 17
+ * N-rank result identical to the 1-rank result.  A record is 1 + S3D_CHUNK_FRAMES uint64: the packed key and
+ * the (n_occ << 32 | n_free) counter of each of the frames of the chunk. */
 #define S3D_CHUNK_FRAMES 16
+#define S3D_RECORD_WORDS (1 + S3D_CHUNK_FRAMES)
 
 int s3d_shard_config(s3d_map *map, int rank, int world);
 /* Replicated expansion (the alternative to routing): with the filter on, s3d_ingest* on every rank

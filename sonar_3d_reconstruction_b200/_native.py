@@ -250,8 +250,8 @@ class NativeMap:
         return int(self._lib.s3d_capacity(self._h))
 
     # -- sharded map --------------------------------------------------------------------
-    RECORD_WORDS = 17
-    CHUNK_FRAMES = 16
+    CHUNK_FRAMES = 16                   # include/sonar3d.h S3D_CHUNK_FRAMES (a build-time constant of the library: 16 or 32)
+    RECORD_WORDS = 1 + CHUNK_FRAMES     # S3D_RECORD_WORDS
 
     def shard_config(self, rank: int, world: int):
         _check(self._lib.s3d_shard_config(self._h, int(rank), int(world)))

@@ -37,7 +37,11 @@ typedef unsigned int u32;
 constexpr u64 EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
 constexpr int KEY_BITS = 21;
 constexpr int KEY_BIAS = 1 << 20;
-constexpr int GF = 16;                                      // frames per chunk = counter lanes per dedupe entry
+#ifndef S3D_GF
+#define S3D_GF S3D_CHUNK_FRAMES
+#endif
+constexpr int GF = S3D_GF;                                  // frames per chunk = counter lanes per dedupe entry
+static_assert(GF == S3D_CHUNK_FRAMES && (GF == 16 || GF == 32), "frames per chunk: 16 or 32 (one mask bit per frame)");
 constexpr int N_CHUNK_BUF = 4;                              // chunk dedupe buffers (a single map cycles through 3 of them)
 constexpr u32 ERR_KEYRANGE = 1u, ERR_TABLEFULL = 2u;        // fatal
 constexpr u32 ERR_ROUTE_FULL = 4u, ERR_ROUTE_TIMEOUT = 8u;  // fatal (routed map): a peer inbox overflowed / a peer never signalled
@@ -1079,7 +1083,6 @@ template <typename CT, bool DEBUG>
 __global__ void __launch_bounds__(AP_THREADS, 3)
 k_apply_chunk(const ApplyArgs a)
 {
-    static_assert(GF == 16, "the packed per-frame counters assume 16 frames per chunk");
     trace_begin(a.trace);
     MapCtr *mc = a.mc; ChunkCtr *cc = a.cc;
     // a retry was asked for by this chunk or an earlier one: stay side-effect free.  (An older
@@ -1104,7 +1107,8 @@ k_apply_chunk(const ApplyArgs a)
     __shared__ double s_L[AP_THREADS];
     __shared__ u64 s_tslot[AP_THREADS];
     __shared__ u64 s_life[DEBUG ? AP_THREADS : 1], s_lifeslot[DEBUG ? AP_THREADS : 1];
-    __shared__ unsigned short s_mask[AP_THREADS], s_ord[AP_THREADS];
+    __shared__ u32 s_mask[AP_THREADS];
+    __shared__ unsigned short s_ord[AP_THREADS];
     __shared__ u32 s_hist[GF + 1], s_tail;
     __shared__ u32 s_occ[GF], s_free[GF], s_new[GF];
     __shared__ u32 s_dmax[GF], s_dgt10[GF], s_lifenew;
@@ -1124,13 +1128,15 @@ k_apply_chunk(const ApplyArgs a)
     u32 *rows = reinterpret_cast<u32 *>(s_dyn);
     CT *scnt = static_cast<CT *>(a.scnt);
     LocalAcc acc; acc_init(acc);
-    u32 pk_occ[4] = {0, 0, 0, 0}, pk_free[4] = {0, 0, 0, 0};     // byte f%4 of word f/4: voxels updated as occupied / free in frame f
+    u32 pk_occ[GF / 4], pk_free[GF / 4];                          // byte f%4 of word f/4: voxels updated as occupied / free in frame f
+#pragma unroll
+    for (int w = 0; w < GF / 4; ++w) { pk_occ[w] = 0; pk_free[w] = 0; }
     u32 pk_rounds = 0;
     u32 head = 0;                                                 // block-uniform: list entries already taken
 
     auto flush_packed = [&]() {
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
+        for (int w = 0; w < GF / 4; ++w) {
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const u32 so = __reduce_add_sync(0xffffffffu, (pk_occ[w] >> (8 * b)) & 0xffu);
@@ -1212,10 +1218,10 @@ k_apply_chunk(const ApplyArgs a)
                     // num_occupied / num_free of every frame that touched the voxel (:562-567)
                     const u32 m_free = m_any & ~m_occ;
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) { pk_occ[w] += spread4(m_occ >> (4 * w)); pk_free[w] += spread4(m_free >> (4 * w)); }
+                    for (int w = 0; w < GF / 4; ++w) { pk_occ[w] += spread4(m_occ >> (4 * w)); pk_free[w] += spread4(m_free >> (4 * w)); }
                 }
             }
-            s_L[tid] = L; s_tslot[tid] = slot; s_mask[tid] = (unsigned short)m_any;
+            s_L[tid] = L; s_tslot[tid] = slot; s_mask[tid] = m_any;
             nfr = (u32)__popc(m_any);
         }
         {
@@ -1358,6 +1364,7 @@ k_apply_chunk(const ApplyArgs a)
 // and the owner merges what it receives (integer adds, so the result does not depend on how the
 // beams were split) before the ordinary apply kernel runs on its shard of the table.
 constexpr int REC_WORDS = 1 + GF;
+static_assert(REC_WORDS == S3D_RECORD_WORDS, "record layout of the NCCL route");
 
 // pass 1: how many of the chunk's dedupe entries go to each owner
 __global__ void k_shard_count(const u64 *__restrict__ skeys, u32 n_slots, u32 world, u32 *owner_count)
@@ -2763,6 +2770,8 @@ int s3d_set_tables(s3d_map *m, const s3d_tables *t)
         CU(cudaFuncSetAttribute(k_expand<u32, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
         CU(cudaFuncSetAttribute(k_expand<u64, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
     }
+    CU(cudaFuncSetAttribute(k_apply_chunk<u32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes<u32>()));
+    CU(cudaFuncSetAttribute(k_apply_chunk<u32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes<u32>()));
     CU(cudaFuncSetAttribute(k_apply_chunk<u64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes<u64>()));
     CU(cudaFuncSetAttribute(k_apply_chunk<u64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes<u64>()));
     m->h_range.assign(t->range_m, t->range_m + H);

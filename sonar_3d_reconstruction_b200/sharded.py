@@ -33,8 +33,8 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-RECORD_WORDS = 17      # include/sonar3d.h S3D_RECORD_WORDS: packed key + 16 frame counters
-CHUNK_FRAMES = 16      # include/sonar3d.h S3D_CHUNK_FRAMES
+CHUNK_FRAMES = 16                  # include/sonar3d.h S3D_CHUNK_FRAMES
+RECORD_WORDS = 1 + CHUNK_FRAMES    # include/sonar3d.h S3D_RECORD_WORDS: packed key + one counter per frame of the chunk
 KEY_BIAS = 1 << 20
 STATS_WORDS = 8       # int64 words per s3d_frame_stats (include/sonar3d.h)
 
@@ -102,7 +102,7 @@ class Exchange:
             self.backend = dist.get_backend(group)
 
     def all_to_all_records(self, send, send_counts: Sequence[int]):
-        """send: [n, 17] int64 tensor grouped by destination rank.  Returns (recv, recv_counts)."""
+        """send: [n, RECORD_WORDS] int64 tensor grouped by destination rank.  Returns (recv, recv_counts)."""
         import torch
         if self.world == 1:
             return send, list(send_counts)

@@ -361,10 +361,12 @@ def test_retry_of_a_later_chunk_leaves_earlier_chunks_whole(s3d, monkeypatch):
     from sonar_3d_reconstruction_b200 import synthetic
     monkeypatch.setenv("S3D_SCRATCH_CAP", "4096")
     spec = dict(H=200, W=128, seabed_depth=3.0, config=dict(voxel_resolution=0.1, intensity_threshold=40), step_m=0.05)
-    images, pos, quat, cfg = synthetic.make_sequence(spec, 64, seed=17)
+    from sonar_3d_reconstruction_b200._native import NativeMap
+    cf = NativeMap.CHUNK_FRAMES
+    images, pos, quat, cfg = synthetic.make_sequence(spec, 4 * cf, seed=17)
     images = images.copy()
-    images[:16] = 0
-    images[:16, 12, :] = 255                        # first hit at 0.6 m: a few hundred voxels per frame
+    images[:cf] = 0
+    images[:cf, 12, :] = 255                        # chunk 0: first hit at 0.6 m, a few hundred voxels per frame
     for rep in range(3):                            # the race is timing dependent: a few tries
         gpu, cpu = s3d.SonarTo3DMapper(cfg), OracleMapper(cfg)
         got = gpu.process_sonar_images(images, pos, quat)
@@ -373,8 +375,9 @@ def test_retry_of_a_later_chunk_leaves_earlier_chunks_whole(s3d, monkeypatch):
         assert assert_same_map(*gpu.octree.voxels.to_arrays(), *cpu.dump(), LOGODDS_ATOL, "retry") <= 1e-9
         # the same through two pending asynchronous batches
         gpu2 = s3d.SonarTo3DMapper(cfg)
-        h1 = gpu2.process_sonar_images_async(images[:40], pos[:40], quat[:40])
-        h2 = gpu2.process_sonar_images_async(images[40:], pos[40:], quat[40:])
+        cut = cf * 2 + 8
+        h1 = gpu2.process_sonar_images_async(images[:cut], pos[:cut], quat[:cut])
+        h2 = gpu2.process_sonar_images_async(images[cut:], pos[cut:], quat[cut:])
         got2 = h1.result() + h2.result()
         assert [_stats3(x) for x in got2] == [_stats3(x) for x in want], f"async try {rep}"
         assert assert_same_map(*gpu2.octree.voxels.to_arrays(), *cpu.dump(), LOGODDS_ATOL, "retry async") <= 1e-9

@@ -118,7 +118,7 @@ class _OracleBackend:
             for typ, shift in ((0, 0), (1, 32)):
                 u, c = np.unique(packed[occ == typ], return_counts=True)
                 for k, n in zip(u.tolist(), c.tolist()):
-                    acc.setdefault(k, [0] * 16)[f] += n << shift
+                    acc.setdefault(k, [0] * S.CHUNK_FRAMES)[f] += n << shift
         self.o.set_beam_slice(0, 2**31 - 1)
         keys = np.array(sorted(acc), dtype=np.uint64)
         owners = S.owner_of_packed(keys, self.world) if len(keys) else np.zeros(0, dtype=np.int64)
@@ -135,7 +135,7 @@ class _OracleBackend:
         rec = recv.numpy()
         merged = {}
         for row in rec:
-            a = merged.setdefault(int(row[0]), np.zeros(16, dtype=np.int64))
+            a = merged.setdefault(int(row[0]), np.zeros(S.CHUNK_FRAMES, dtype=np.int64))
             a += row[1:]
         keys = np.array(sorted(merged), dtype=np.uint64)
         ijk = S.unpack_keys(keys) if len(keys) else np.zeros((0, 3), dtype=np.int64)
@@ -201,7 +201,7 @@ def _worker(rank, world, port, out_dir, mode):
     from sonar_3d_reconstruction_b200 import synthetic
     from sonar_3d_reconstruction_b200.sharded import ShardedSonarMapper
     spec = dict(H=90, W=48, config=dict(voxel_resolution=0.12, intensity_threshold=40, max_range=6.0), step_m=0.04)
-    images, pos, quat, cfg = synthetic.make_sequence(spec, 19, seed=5)      # 19 frames: a full chunk + a ragged one
+    images, pos, quat, cfg = synthetic.make_sequence(spec, 37, seed=5)      # 37 frames: a full chunk + a ragged one
     m = ShardedSonarMapper(cfg, group=dist.group.WORLD, backend_factory=_factory, mode=mode)
     stats = m.process_sonar_images(images, pos, quat)
     keys, L = m.gather_map()
@@ -228,7 +228,7 @@ def test_two_rank_gloo_equals_single_rank_oracle(tmp_path, mode):
     from oracle.oracle import OracleMapper
     from sonar_3d_reconstruction_b200 import synthetic
     spec = dict(H=90, W=48, config=dict(voxel_resolution=0.12, intensity_threshold=40, max_range=6.0), step_m=0.04)
-    images, pos, quat, cfg = synthetic.make_sequence(spec, 19, seed=5)
+    images, pos, quat, cfg = synthetic.make_sequence(spec, 37, seed=5)
     o = OracleMapper(cfg)
     want = []
     for f in range(len(images)):

@@ -39,14 +39,16 @@ def main():
         nat = m.octree._native
         nat.shard_config(r, world)
         nat.reserve(4 * len(k1) // world + 100000)          # a routed map cannot re-run a chunk
-        handles.append(nat.route_export(1 << 18))
+        handles.append(nat.route_export(1 << 21))
     for m in maps:
         m.octree._native.route_attach(b"".join(handles), same_process=True)
     for m in maps:
         m.octree._native.route_enable(True)
     torch.cuda.synchronize()
-    for f0 in range(0, n, 16):                               # one chunk per rank, in turn
-        g = min(16, n - f0)
+    from sonar_3d_reconstruction_b200._native import NativeMap
+    cf = NativeMap.CHUNK_FRAMES
+    for f0 in range(0, n, cf):                               # one chunk per rank, in turn
+        g = min(cf, n - f0)
         for r, m in enumerate(maps):
             m.octree._native.ingest_batch_dev(d_img.data_ptr() + f0 * H * W, g, d_T.data_ptr() + f0 * 128,
                                               want_stats=False, stats_dev_ptr=stats[r].data_ptr() + f0 * 64)
