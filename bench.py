@@ -68,12 +68,20 @@ def load_peaks():
 
 
 def load_traffic(workload):
-    """DRAM bytes per k_apply_chunk launch from the committed cold-cache ncu capture (profiles/), or None."""
+    """DRAM bytes per k_apply_chunk launch from the committed cold-cache ncu capture (profiles/r2_traffic.json:
+    `ncu --cache-control all`, 16 frames per launch), or None."""
     path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(path):
         with open(path) as f:
-            return json.load(f).get(workload)
+            return json.load(f).get(workload, {}).get("k_apply_chunk", {}).get("dram_bytes_per_launch")
     return None
+
+
+# tools/microbench_rmw.cu on this pool's B200 (profiles/r2_microbench_rmw.txt): random 16-byte slot reads with an
+# 8-byte write-back into a table far larger than L2 -- the access pattern of the update kernel -- sustain
+# 14-19 G slots/s (about 1.0-1.2 TB/s of 32-byte sectors); the lower figures belong to the grid sizes a kernel
+# sharing the GPU can use.  Reported beside the streaming-bandwidth fraction, not instead of it.
+RANDOM_RMW_GSLOTS_PER_S = 17.0
 
 
 class ClockSampler:
@@ -464,6 +472,14 @@ def run_config(args, name: str, fps_step: int, local_rank: int, barrier, ref_bud
             kern[k_] = {"us_per_launch_exclusive": us, "launches": sprof["launches"][k_],
                         "alg_bytes_per_launch": ab, "gbs": ab / (us * 1e-6) / 1e9, "frac": ab / (us * 1e-6) / 1e9 / peak}
     ka = kern.get("k_apply", {"gbs": 0.0, "frac": 0.0})
+    if "k_apply" in kern:
+        probes_per_s = sprof["voxel_probes"] / (sprof["ms"]["k_apply"] * 1e-3)
+        kern["k_apply"]["voxel_probes_per_launch"] = sprof["voxel_probes"] / sprof["launches"]["k_apply"]
+        kern["k_apply"]["table_probes_per_s"] = probes_per_s
+        kern["k_apply"]["frac_of_random_rmw_bound"] = probes_per_s / (RANDOM_RMW_GSLOTS_PER_S * 1e9)
+        kern["k_apply"]["random_rmw_bound"] = (f"{RANDOM_RMW_GSLOTS_PER_S} G slot read-modify-writes/s measured on this pool's B200 "
+                                               "(tools/microbench_rmw.cu, profiles/r2_microbench_rmw.txt): the kernel touches one random "
+                                               "32-byte sector of a table >> L2 per voxel per launch, so this, not the streaming peak, bounds it")
     line = {
         "metric": METRIC, "value": n_frames / secs, "unit": UNIT,
         "ms_per_step": ms_total / args.steps,

@@ -282,6 +282,7 @@ typedef struct s3d_profile {
     uint64_t retries;                /* chunks re-run after the device gate asked for more room */
     uint64_t grows;                  /* voxel-table rehash-grows */
     uint64_t route_records_sent;     /* routed map: 16-byte records written into peers' inboxes over NVLink since the last read */
+    uint64_t voxel_probes;           /* voxel-table find-or-insert probes since the last read: one per voxel per applied chunk */
 } s3d_profile;
 
 int s3d_profile_enable(s3d_map *map, int on);

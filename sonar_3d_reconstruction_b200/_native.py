@@ -59,7 +59,7 @@ STATS_BYTES = 8 * STATS_WORDS
 class Profile(C.Structure):
     _fields_ = [("ms", C.c_double * 3), ("launches", C.c_uint64 * 3), ("frames", C.c_uint64),
                 ("total_launches", C.c_uint64), ("retries", C.c_uint64), ("grows", C.c_uint64),
-                ("route_records_sent", C.c_uint64)]
+                ("route_records_sent", C.c_uint64), ("voxel_probes", C.c_uint64)]
 
 
 KERNEL_NAMES = ("k_first_hit", "k_expand", "k_apply")
@@ -302,7 +302,8 @@ class NativeMap:
         return {"ms": {k: p.ms[i] for i, k in enumerate(KERNEL_NAMES)},
                 "launches": {k: int(p.launches[i]) for i, k in enumerate(KERNEL_NAMES)},
                 "frames": int(p.frames), "total_launches": int(p.total_launches),
-                "retries": int(p.retries), "grows": int(p.grows), "route_records_sent": int(p.route_records_sent)}
+                "retries": int(p.retries), "grows": int(p.grows), "route_records_sent": int(p.route_records_sent),
+                "voxel_probes": int(p.voxel_probes)}
 
     # -- store --------------------------------------------------------------------------
     def apply_updates(self, ijk: np.ndarray, delta: np.ndarray, adaptive: np.ndarray):

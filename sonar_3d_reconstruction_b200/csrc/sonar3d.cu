@@ -101,6 +101,7 @@ struct MapCtr {       // device-resident map counters
     u64 life_count;   // debug counters: keys in the lifetime sample-count table
     u64 life_max;     // debug counters: largest lifetime sample count of any voxel (3d_mapper.py:578)
     u64 route_sent;   // routed map: 16-byte records this rank has written into peers' inboxes (NVLink traffic)
+    u64 probes;       // voxel-table probes so far: one per voxel per applied chunk
 };
 
 struct ChunkCtr {     // working counters of the chunk in flight (chunks are serialised on the stream)
@@ -1352,6 +1353,7 @@ k_apply_chunk(const ApplyArgs a)
         }
         mc->last_new = (u32)(run - count0);
         mc->last_unique = atomicAdd(&cc->n_unique, 0u);
+        mc->probes += mc->last_unique;
         atomicExch(&mc->count, run);
         cc->n_unique = 0; cc->ticket = 0;
     }
@@ -1723,7 +1725,7 @@ __global__ void k_reset_ctr(MapCtr *mc)
     for (int q = 0; q < 3; ++q) { mc->kmin[q] = INT_MAX; mc->kmax[q] = INT_MIN; }
 }
 
-__global__ void k_init_life_ctr(MapCtr *mc) { mc->life_count = 0; mc->life_max = 0; mc->route_sent = 0; }
+__global__ void k_init_life_ctr(MapCtr *mc) { mc->life_count = 0; mc->life_max = 0; mc->route_sent = 0; mc->probes = 0; }
 
 // compact the lifetime table into {key, count} pairs (debug view voxel_update_counts)
 __global__ void k_dump_life(const Slot *__restrict__ life, u64 n_slots, ulonglong2 *out, u64 out_cap, u64 *cursor)
@@ -1821,6 +1823,7 @@ struct s3d_map {
     DevBuf<unsigned char *> d_peers; DevBuf<u32> route_cursor;
     u64 route_seq = 0;               // chunks routed so far (the same on every rank)
     u64 route_sent_seen = 0;         // MapCtr::route_sent at the last s3d_profile_read
+    u64 probes_seen = 0;             // MapCtr::probes at the last s3d_profile_read
     u64 route_timeout_ns = 30000000000ull;   // S3D_ROUTE_TIMEOUT_MS
     int lookahead_env = 0;           // S3D_LOOKAHEAD (experiments)
     u64 scratch_env = 0;             // S3D_SCRATCH_CAP: first size of the chunk dedupe tables (tests force retries with a tiny one)
@@ -3549,6 +3552,8 @@ int s3d_profile_read(s3d_map *m, s3d_profile *out)
         CU(cudaMemcpy(&h, m->mc, sizeof h, cudaMemcpyDeviceToHost));
         m->prof.route_records_sent = h.route_sent - m->route_sent_seen;
         m->route_sent_seen = h.route_sent;
+        m->prof.voxel_probes = h.probes - m->probes_seen;
+        m->probes_seen = h.probes;
     }
     *out = m->prof;
     m->prof = s3d_profile{};

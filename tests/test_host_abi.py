@@ -43,7 +43,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_native.Params) == 8 * 8 + 4 * 4
     assert C.sizeof(_native.FrameStats) == 64 and _native.STATS_DTYPE.itemsize == 64
     assert C.sizeof(_native.Tables) == 6 * 4 + 8 * 8
-    assert C.sizeof(_native.Profile) == 3 * 8 + 3 * 8 + 5 * 8
+    assert C.sizeof(_native.Profile) == 3 * 8 + 3 * 8 + 6 * 8
 
 
 @pytest.mark.skipif(_cuda(), reason="only meaningful on a host without a GPU")
