@@ -700,6 +700,40 @@ def run_sharded(args, rank, world, local_rank):
             del one, on, o_stats
         barrier()
 
+    # ---- BASELINE config 5's ablation: the same timed steps with the adaptive rule switched off
+    ablation = None
+    if fused_like and not args.no_ablation:
+        off = ShardedSonarMapper(dict(cfg, adaptive_update=not bool(cfg.get("adaptive_update", True)), table_capacity=cap),
+                                 group=dist.group.WORLD, mode=args.shard_mode)
+        off.mapper._check_width(W)
+        off.mapper._sync_device_config(H, W)
+        onat = off.backend.native
+        a_stats = torch.zeros((n_total, STATS_WORDS), dtype=torch.int64, device=dev)
+
+        def off_step(s):
+            onat.ingest_batch_dev(d_img.data_ptr() + s * fps_step * img_bytes, fps_step, d_T.data_ptr() + s * fps_step * 128,
+                                  want_stats=False, stats_dev_ptr=a_stats.data_ptr() + s * fps_step * 8 * STATS_WORDS)
+        for s in range(args.warmup):
+            off_step(s)
+        onat.sync()
+        onat.reserve(int(1.5 * rate * n_frames / world) + 100000)
+        astream = torch.cuda.ExternalStream(onat.stream, device=local_rank)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(astream)
+        for s in range(args.warmup, args.warmup + args.steps):
+            off_step(s)
+        onat.sync()
+        a1.record()
+        torch.cuda.synchronize()
+        barrier()
+        t_off = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_off, op=dist.ReduceOp.MAX)
+        ablation = {"adaptive_update": not bool(cfg.get("adaptive_update", True)), "value": n_frames / (float(t_off[0]) * 1e-3), "unit": UNIT,
+                    "note": "BASELINE config 5: the same timed frames with the adaptive rule toggled (batched ingest, "
+                            f"{fps_step} frames per call)"}
+        del off, onat, a_stats
+
     e2e_s = float("nan")
     if not args.no_e2e:
         sh2 = ShardedSonarMapper(dict(cfg, table_capacity=cap), group=dist.group.WORLD, mode=args.shard_mode)
@@ -764,6 +798,8 @@ def run_sharded(args, rank, world, local_rank):
             line["speedup_vs_one_gpu_same_workload"] = line["value"] / single["value"]
         if par is not None:
             line["parity"] = par
+        if ablation is not None:
+            line["adaptive_ablation"] = ablation
         if not args.no_e2e:
             line["e2e"] = {"value": n_frames / e2e_s, "unit": UNIT,
                            "h2d_bytes_per_step": fps_step * H * W + world * fps_step * 128, "d2h_bytes_per_step": fps_step * 8 * STATS_WORDS,
@@ -861,6 +897,7 @@ def main():
     ap.add_argument("--no-cfg3", action="store_true", help="N = 1: skip the cfg3 object of the line")
     ap.add_argument("--no-single-ref", action="store_true", help="N > 1: skip the single-GPU run of the same frames on rank 0")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (profiling runs only)")
+    ap.add_argument("--no-ablation", action="store_true", help="N > 1: skip the adaptive on/off pass")
     ap.add_argument("--no-adaptive", action="store_true",
                     help="ablation (BASELINE config 5): adaptive_update off -- every update is applied unscaled")
     ap.add_argument("--shard-mode", default="fused", choices=["fused", "replicate", "route"],

@@ -9,7 +9,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsonar3d.so")
+LIB_PATH = os.environ.get("S3D_LIB_PATH") or os.path.join(_HERE, "csrc", "libsonar3d.so")   # (override: kernel-variant experiments)
 
 # every symbol include/sonar3d.h declares (tests check the list against the header and the .so)
 SYMBOLS = (

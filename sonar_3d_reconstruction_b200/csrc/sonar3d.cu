@@ -183,12 +183,21 @@ __device__ __forceinline__ u32 mix32(u64 key)
 constexpr int EX_WARPS = 8;                  // warps per block
 constexpr int EX_MAXB = 16;                  // beams per tile at most (a 16-byte image strip at bearing step 1)
 constexpr int EX_THREADS = EX_WARPS * 32;
-constexpr int EX_BPS = 4;                    // resident blocks per SM the kernel is compiled for
-constexpr int EX_ILP = 2;                    // samples per lane per pass
+#ifndef S3D_EX_BPS
+#define S3D_EX_BPS 4
+#endif
+constexpr int EX_BPS = S3D_EX_BPS;           // resident blocks per SM the kernel is compiled for
+#ifndef S3D_LT_BITS
+#define S3D_LT_BITS 12        // log2 of the block combiner's entries
+#endif
+#ifndef S3D_EX_ILP
+#define S3D_EX_ILP 2
+#endif
+constexpr int EX_ILP = S3D_EX_ILP;           // samples per lane per pass
 constexpr int EX_PASS = 32 * EX_ILP;         // samples per warp per pass
-constexpr int EX_ROUND = 6;                  // passes between two block-wide flush votes
+constexpr int EX_ROUND = (S3D_LT_BITS >= 12 ? 12 : 6) / EX_ILP;   // passes between two block-wide flush votes
 constexpr int EX_ROUND_SAMPLES = EX_WARPS * EX_PASS * EX_ROUND;
-constexpr int LT_BITS = 12;
+constexpr int LT_BITS = S3D_LT_BITS;
 constexpr int LT_CAP = 1 << LT_BITS;         // combiner entries
 constexpr int LT_LIMIT = LT_CAP * 3 / 4;     // load bound
 constexpr int LT_MAX_SAMPLES = 0xFFFF;       // 16-bit counts cannot overflow between two flushes
@@ -785,8 +794,20 @@ k_expand(const ExpandArgs a, const __grid_constant__ CUtensorMap tmap)
                 // fans that start inside this pass: bit (start - base) of a 64-bit mask (a fan has >= 3 samples)
                 const int kf = c0 + 1 + lane;
                 const int rel = (kf <= nfan ? fans[kf].off : INT_MAX) - base;
-                const u32 m_lo = __reduce_or_sync(0xffffffffu, (rel > 0 && rel < 32) ? 1u << rel : 0u);
-                const u32 m_hi = __reduce_or_sync(0xffffffffu, (rel >= 32 && rel < 64) ? 1u << (rel - 32) : 0u);
+                // (word j of the mask covers samples base + 32 j .. base + 32 j + 31; a lane looks at one later fan,
+                // and a fan has >= 3 samples, so 32 lanes see every start inside 96 samples -- the pass is 128 at most:
+                // lanes also take fan c0 + 33 + lane)
+                u32 fm[EX_ILP];
+                {
+                    const int kf2 = kf + 32;
+                    const int rel2 = EX_ILP > 2 ? (kf2 <= nfan ? fans[kf2].off : INT_MAX) - base : INT_MAX;
+#pragma unroll
+                    for (int j = 0; j < EX_ILP; ++j) {
+                        const bool in1 = rel > 0 && rel >= 32 * j && rel < 32 * j + 32;
+                        const bool in2 = rel2 >= 32 * j && rel2 < 32 * j + 32;
+                        fm[j] = __reduce_or_sync(0xffffffffu, (in1 ? 1u << (rel - 32 * j) : 0u) | (in2 ? 1u << (rel2 - 32 * j) : 0u));
+                    }
+                }
                 const u32 upto = 0xffffffffu >> (31 - lane);                // bits 0..lane
                 bool made[EX_ILP]; u32 made_at[EX_ILP];
 #pragma unroll
@@ -794,7 +815,10 @@ k_expand(const ExpandArgs a, const __grid_constant__ CUtensorMap tmap)
                     made[j] = false; made_at[j] = 0;
                     const int w = base + j * 32 + lane;
                     if (w >= total) continue;
-                    const Fan f = fans[c0 + (j == 0 ? __popc(m_lo & upto) : __popc(m_lo) + __popc(m_hi & upto))];
+                    int fpos = c0 + __popc(fm[j] & upto);
+#pragma unroll
+                    for (int q = 0; q < j; ++q) fpos += __popc(fm[q]);
+                    const Fan f = fans[fpos];
                     const int nv = (int)((f.code >> 16) & 0x7fffu);
                     const bool occ = (f.code >> 31) != 0u;
                     const int ti = nv * nv - 1 + (w - f.off);               // row nv, entry v_step + nv
@@ -882,14 +906,18 @@ k_expand(const ExpandArgs a, const __grid_constant__ CUtensorMap tmap)
                     }
                 }
                 // combiner slots created by this pass join the live list: one shared-memory atomic per pass
-                static_assert(EX_ILP == 2, "two ballots below");
-                const u32 mk0 = __ballot_sync(0xffffffffu, made[0]), mk1 = __ballot_sync(0xffffffffu, made[1]);
-                if (mk0 | mk1) {
+                u32 mk[EX_ILP], n_made = 0;
+#pragma unroll
+                for (int j = 0; j < EX_ILP; ++j) { mk[j] = __ballot_sync(0xffffffffu, made[j]); n_made += __popc(mk[j]); }
+                if (n_made) {
                     u32 at = 0;
-                    if (lane == 0) at = atomicAdd(&s_count, (u32)(__popc(mk0) + __popc(mk1)));
+                    if (lane == 0) at = atomicAdd(&s_count, n_made);
                     at = __shfl_sync(0xffffffffu, at, 0);
-                    if (made[0]) live[at + __popc(mk0 & lt_mask)] = (unsigned short)made_at[0];
-                    if (made[1]) live[at + __popc(mk0) + __popc(mk1 & lt_mask)] = (unsigned short)made_at[1];
+#pragma unroll
+                    for (int j = 0; j < EX_ILP; ++j) {
+                        if (made[j]) live[at + __popc(mk[j] & lt_mask)] = (unsigned short)made_at[j];
+                        at += __popc(mk[j]);
+                    }
                 }
             }
             if (free_run) break;
