@@ -59,6 +59,11 @@ DESCR = {
 }
 
 
+def note(msg):
+    if os.environ.get("BENCH_DEBUG"):
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -329,7 +334,9 @@ def run_config(args, name: str, fps_step: int, local_rank: int, barrier, ref_bud
         return ev0.elapsed_time(ev1), nat.profile_read(), clocks
 
     # ------------------------------------------------------------- value: inputs resident in HBM
+    note(f"{name}: timed pass, {n_total} frames resident")
     ms_total, prof, clocks = timed_pass(native, d_stats, reserve=True)
+    note(f"{name}: timed pass done, table {native.capacity} slots")
     st_all = d_stats.cpu().numpy()
     st = st_all[args.warmup * fps_step:]
     n_frames = args.steps * fps_step
@@ -337,10 +344,12 @@ def run_config(args, name: str, fps_step: int, local_rank: int, barrier, ref_bud
     samples = int(st[:, 3].sum())
     n_voxels = int(st[-1, 2])
     cap = native.capacity
+    mapper.close()
     del mapper, native
 
     # ------------------------------------------------------------- parity of the timed sequence's first frames
     par = None
+    note(f"{name}: parity")
     if parity_frames > 0:
         n_par = min(parity_frames, n_total)
         pm = fresh()
@@ -351,9 +360,11 @@ def run_config(args, name: str, fps_step: int, local_rank: int, barrier, ref_bud
         assert np.array_equal(pst[:, :4], st_all[:n_par, :4]), "two GPU passes over the same frames disagree"
         keys, L = pm.octree.voxels.to_arrays()
         par = parity_check(pst, keys, L, wl, cfg, n_par)
+        pm.close()
         del pm
 
     # ------------------------------------------------------------- exclusive per-kernel times (no overlap)
+    note(f"{name}: exclusive pass")
     sm = fresh(table_capacity=cap, env={"S3D_SERIAL_KERNELS": "1"})
     sn = sm.octree._native
     s_stats = torch.zeros((n_total, STATS_WORDS), dtype=torch.int64, device=dev)
@@ -370,10 +381,12 @@ def run_config(args, name: str, fps_step: int, local_rank: int, barrier, ref_bud
     sn.profile_enable(False)
     sst = s_stats[args.warmup * fps_step:(args.warmup + k_steps) * fps_step].cpu().numpy()
     s_updates, s_frames = int((sst[:, 0] + sst[:, 1]).sum()), k_steps * fps_step
+    sm.close()
     del sm, sn, s_stats
 
     # ------------------------------------------------------------- no pre-sizing: rehash-grows inside the timed region
     unres = None
+    note(f"{name}: unreserved / e2e")
     if unreserved:
         um = fresh()
         u_stats = torch.zeros((n_total, STATS_WORDS), dtype=torch.int64, device=dev)
@@ -382,6 +395,7 @@ def run_config(args, name: str, fps_step: int, local_rank: int, barrier, ref_bud
         unres = {"value": n_frames / (u_ms * 1e-3), "unit": UNIT, "table_grows_timed": u_prof["grows"],
                  "chunk_retries": u_prof["retries"], "table_slots_end": um.octree._native.capacity,
                  "note": "same timed frames, table not pre-sized: every rehash-grow (allocate, re-insert, free) is inside the timed region"}
+        um.close()
         del um, u_stats
 
     # ------------------------------------------------------------- e2e: public API, host buffers
@@ -413,6 +427,7 @@ def run_config(args, name: str, fps_step: int, local_rank: int, barrier, ref_bud
         torch.cuda.synchronize()
         blocking_s = time.perf_counter() - t0
         assert out[-1]["num_voxels"] == n_voxels, (out[-1]["num_voxels"], n_voxels)
+        m2.close()
         del m2
         # (b) the asynchronous form of the call, two steps pending at a time: step s+1 is uploaded and expanded
         # while step s finishes; every step still copies its frames from pinned host memory and reads its
@@ -432,6 +447,7 @@ def run_config(args, name: str, fps_step: int, local_rank: int, barrier, ref_bud
         torch.cuda.synchronize()
         async_s = time.perf_counter() - t0
         assert out[-1]["num_voxels"] == n_voxels, (out[-1]["num_voxels"], n_voxels)      # both arms built the same map
+        m3.close()
         del m3
         # (c) the reference's own call: one frame per process_sonar_image (the only call the ROS2 node makes)
         n_single = min(args.single_frames, fps_step)
@@ -444,6 +460,7 @@ def run_config(args, name: str, fps_step: int, local_rank: int, barrier, ref_bud
         for i, f in enumerate(range(f0, f0 + n_single)):
             m4.process_sonar_image(frames[i], list(wl.pos[f]), list(wl.quat[f]))
         single_s = time.perf_counter() - t0
+        m4.close()
         del m4
         e2e = {"value": n_frames / async_s, "unit": UNIT,
                "h2d_bytes_per_step": fps_step * (H * W + 128), "d2h_bytes_per_step": fps_step * 8 * STATS_WORDS,
@@ -529,7 +546,7 @@ def run_single(args, local_rank):
     def barrier():
         torch.cuda.synchronize()
 
-    fps_step = args.frames_per_step or (5000 if args.workload != "cfg3" else args.cfg3_frames_per_step)
+    fps_step = args.frames_per_step or (4000 if args.workload != "cfg3" else args.cfg3_frames_per_step)
     head = run_config(args, args.workload, fps_step, local_rank, barrier,
                       ref_budget_s=18.0 if args.workload != "cfg3" else 1.0, parity_frames=args.parity_frames if args.workload != "cfg3"
                       else min(args.parity_frames, 12), port_frames=args.cpu_frames if args.workload != "cfg3" else 24,
@@ -615,6 +632,7 @@ def run_sharded(args, rank, world, local_rank):
             par["sharded_vs_single_gpu"] = {"frames": n_par, "keys_identical": same_keys, "logodds_bit_identical": same_L,
                                             "counters_identical": same_stats}
             par["ok"] = bool(par["ok"] and same_keys and same_L and same_stats)
+            plain.close()
             del plain
         sh.reset_map()
 
@@ -697,6 +715,7 @@ def run_sharded(args, rank, world, local_rank):
             assert int(o_stats[-1, 2]) == n_voxels, (int(o_stats[-1, 2]), n_voxels)
             single = {"value": n_frames / (one_ms * 1e-3), "unit": UNIT,
                       "note": "the same timed frames through one unsharded map on rank 0's GPU, after the sharded run"}
+            one.close()
             del one, on, o_stats
         barrier()
 
@@ -732,6 +751,7 @@ def run_sharded(args, rank, world, local_rank):
         ablation = {"adaptive_update": not bool(cfg.get("adaptive_update", True)), "value": n_frames / (float(t_off[0]) * 1e-3), "unit": UNIT,
                     "note": "BASELINE config 5: the same timed frames with the adaptive rule toggled (batched ingest, "
                             f"{fps_step} frames per call)"}
+        off.mapper.close()
         del off, onat, a_stats
 
     e2e_s = float("nan")
@@ -830,7 +850,7 @@ def run_reference(args, rank, world):
     kind = "reference" if ref_cls is not None else "port"
     make = ref_cls if ref_cls is not None else OracleMapper
     per_step = args.ref_frames_per_step or (1 if kind == "reference" else 40)
-    gpu_step = args.frames_per_step or ((5000 if args.gpus == 1 else 2000) if name != "cfg3" else args.cfg3_frames_per_step)
+    gpu_step = args.frames_per_step or ((4000 if args.gpus == 1 else 2000) if name != "cfg3" else args.cfg3_frames_per_step)
     n_total = (args.steps + args.warmup) * gpu_step
     wl = Workload(name, n_total, args.seed, args.distinct_images, gpu_step)
     cfg = dict(wl.cfg)
@@ -884,8 +904,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(synthetic.CONFIGS))
-    ap.add_argument("--frames-per-step", type=int, default=0, help="default: 5000 at N = 1, 2000 at N > 1 (cfg3: --cfg3-frames-per-step)")
-    ap.add_argument("--cfg3-frames-per-step", type=int, default=600)
+    ap.add_argument("--frames-per-step", type=int, default=0, help="default: 4000 at N = 1 (an asynchronous batch is limited to 1 GiB of frames), 2000 at N > 1 (cfg3: --cfg3-frames-per-step)")
+    ap.add_argument("--cfg3-frames-per-step", type=int, default=500)
     ap.add_argument("--ref-frames-per-step", type=int, default=0)
     ap.add_argument("--ref-port", action="store_true", help="--impl reference: time the C restatement even if baseline/_ref exists")
     ap.add_argument("--distinct-images", type=int, default=250)

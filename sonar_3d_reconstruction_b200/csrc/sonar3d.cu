@@ -45,6 +45,7 @@ static_assert(GF == S3D_CHUNK_FRAMES && (GF == 16 || GF == 32), "frames per chun
 constexpr int N_CHUNK_BUF = 4;                              // chunk dedupe buffers (a single map cycles through 3 of them)
 constexpr u32 ERR_KEYRANGE = 1u, ERR_TABLEFULL = 2u;        // fatal
 constexpr u32 ERR_ROUTE_FULL = 4u, ERR_ROUTE_TIMEOUT = 8u;  // fatal (routed map): a peer inbox overflowed / a peer never signalled
+constexpr u32 ERR_INTERNAL = 32u;                           // a bounds guard tripped (should be impossible): reported, not faulted
 constexpr u32 ERR_VERIFY = 16u;                             // S3D_VERIFY_FAST: an accepted fp32 estimate differed from the fp64 key
 constexpr u32 ABORT_SCRATCH = 1u, ABORT_TABLE = 2u;         // retryable: the host enlarges and re-runs the chunk
 constexpr u32 ABORT_NARROW = 4u;                            // retryable: a 16-bit sample count overflowed -> wide lanes
@@ -87,6 +88,7 @@ struct DevTables {
     const double *cos_va, *sin_va;
     const float2 *csva32;     // {cos, sin}(va) rounded to fp32 (fast path)
     int col_step;             // beam_col[b] == b * col_step for every beam (0 = irregular: no strip staging)
+    int n_trig;               // entries of the cos_va / sin_va / csva32 tables
 };
 
 struct MapCtr {       // device-resident map counters
@@ -306,6 +308,7 @@ struct ExpandArgs {
     RouteCtx rt;                 // rt.world > 1: voxels of other owners are routed to them (routed map)
     u64 seq;                     // chunk sequence number (for abort bookkeeping)
     u64 *trace;                  // S3D_TRACE: {start, end} of this launch, or null
+    u64 *marks;                  // S3D_MARKS (fault localisation): mapped host counters {blocks started, blocks finished}, or null
 };
 
 __device__ __forceinline__ void raise_abort(MapCtr *mc, u32 why, u64 seq)
@@ -422,7 +425,8 @@ __device__ __forceinline__ void flush_combiner(const ExpandArgs &a, u32 *tkey, u
                                                volatile u32 *s_count, const int (&o)[3], int g, u32 &emitted)
 {
     const int tid = threadIdx.x, lane = tid & 31;
-    const int n = (int)*s_count;                 // live[0..n) lists the combiner slots in use
+    int n = (int)*s_count;                       // live[0..n) lists the combiner slots in use
+    if (n > LT_CAP) { atomicOr(&a.mc->err, ERR_INTERNAL); n = LT_CAP; }
     // FL_ILP entries per thread at a time: home buckets are fetched together, then resolved
     for (int base = 0; base < n; base += EX_THREADS * FL_ILP) {
         u64 key[FL_ILP]; u32 inc[FL_ILP], home[FL_ILP]; bool ok[FL_ILP]; Bucket bk[FL_ILP];
@@ -433,8 +437,9 @@ __device__ __forceinline__ void flush_combiner(const ExpandArgs &a, u32 *tkey, u
             const int e = base + j * EX_THREADS + tid;
             ok[j] = false; key[j] = 0; inc[j] = 0; home[j] = 0; dst[j] = ~0u;
             bk[j].a = bk[j].b = make_ulonglong2(0ull, 0ull);
-            if (e < n) {
-                const int idx = live[e];
+            int idx = e < n ? (int)live[e] : -1;
+            if (idx >= LT_CAP) { atomicOr(&a.mc->err, ERR_INTERNAL); idx = -1; }
+            if (idx >= 0) {
                 const u32 lk = tkey[idx], c = tcnt[idx];
                 tkey[idx] = LT_EMPTY; tcnt[idx] = 0;
                 const int ki = (int)(lk & (2 * LK_HALF - 1)) - LK_HALF + o[0];
@@ -499,6 +504,7 @@ template <bool ROUTE>
 __device__ __forceinline__ void expand_finish(const ExpandArgs &a)
 {
     trace_end(a.trace);
+    if (a.marks && threadIdx.x == 0) atomicAdd_system(a.marks + 1, 1ull);
     if (!ROUTE || a.rt.world <= 1) return;
     __shared__ bool s_last;
     __threadfence_system();                     // this thread's record stores, before the ticket
@@ -606,10 +612,12 @@ k_expand(const ExpandArgs a, const __grid_constant__ CUtensorMap tmap)
         if (a.use_tma) mbar_init(&s_bar, 1);
     }
     trace_begin(a.trace);
+    if (a.marks && tid == 0) atomicAdd_system(a.marks, 1ull);
     for (int i = tid; i < LT_CAP / 4; i += EX_THREADS) {
         reinterpret_cast<uint4 *>(tkey)[i] = make_uint4(LT_EMPTY, LT_EMPTY, LT_EMPTY, LT_EMPTY);
         reinterpret_cast<uint4 *>(tcnt)[i] = make_uint4(0u, 0u, 0u, 0u);
     }
+    if (a.use_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (s_abort) {                      // stay side-effect free (block-uniform)
         expand_finish<ROUTE>(a);
@@ -818,10 +826,12 @@ k_expand(const ExpandArgs a, const __grid_constant__ CUtensorMap tmap)
                     int fpos = c0 + __popc(fm[j] & upto);
 #pragma unroll
                     for (int q = 0; q < j; ++q) fpos += __popc(fm[q]);
+                    if (fpos > nfan) { atomicOr(&a.mc->err, ERR_INTERNAL); continue; }
                     const Fan f = fans[fpos];
                     const int nv = (int)((f.code >> 16) & 0x7fffu);
                     const bool occ = (f.code >> 31) != 0u;
                     const int ti = nv * nv - 1 + (w - f.off);               // row nv, entry v_step + nv
+                    if ((u32)ti >= (u32)tab.n_trig) { atomicOr(&a.mc->err, ERR_INTERNAL); continue; }
                     bool need_exact = true, to_comb = false;
                     u32 lk = 0;
                     if (fast32) {
@@ -937,6 +947,8 @@ k_expand(const ExpandArgs a, const __grid_constant__ CUtensorMap tmap)
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
         if (lane == 0 && emitted) atomicAdd(&a.stats[g].n_samples, (u64)emitted);
+        // (every thread orders its generic-proxy accesses to the combiner before the async proxy's next strip)
+        if (a.use_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();                 // the tile's shared state is reused by the next one
     }
     expand_finish<ROUTE>(a);
@@ -1086,6 +1098,7 @@ struct ApplyArgs {
     Slot *table; u64 tmask;
     DevParams p; const double *sum_tab;
     MapCtr *mc; u64 table_limit; u64 seq; u64 *trace;
+    u64 *marks;                 // S3D_MARKS: mapped host counters {blocks started, blocks finished}, or null
     // debug counters (DEBUG instantiation only)
     Slot *life;                 // lifetime sample counts: same geometry as the voxel table, val = u64 count
     ulonglong2 *last; u32 *last_n; u32 last_cap;   // {key, samples} of the chunk's last frame
@@ -1130,6 +1143,7 @@ k_apply_chunk(const ApplyArgs a)
             return;
         }
     }
+    if (a.marks && threadIdx.x == 0) atomicAdd_system(a.marks + 2, 1ull);
     extern __shared__ __align__(16) unsigned char s_dyn[];          // staged counter lanes [AP_THREADS][ROWW]
     __shared__ u64 s_lkey[AP_LCAP];                                 // live list: key ...
     __shared__ u32 s_lslot[AP_LCAP];                                // ... and dedupe slot
@@ -1352,6 +1366,7 @@ k_apply_chunk(const ApplyArgs a)
     // last block out: len(voxels) after each frame (:592), publish the new count, re-arm the chunk
     __syncthreads();
     trace_end(a.trace);
+    if (a.marks && tid == 0) atomicAdd_system(a.marks + 3, 1ull);
     if (tid == 0) {
         __threadfence();
         const u32 t = atomicAdd(&cc->ticket, 1u);
@@ -1869,6 +1884,9 @@ struct s3d_map {
     DevBuf<float2> d_csva32;
     bool tma_ok = true, fast32_ok = true, verify_fast = false;   // S3D_NO_TMA, S3D_NO_FAST32, S3D_VERIFY_FAST
     bool serial = false;             // S3D_SERIAL_KERNELS: every pipeline kernel on one stream (exclusive per-kernel timings)
+    bool debug_sync = false;         // S3D_DEBUG_SYNC: synchronise and check after every pipeline launch (fault localisation)
+    bool one_xstream = false;        // S3D_ONE_XSTREAM: consecutive chunks are expanded one after the other (they still overlap the apply)
+    u64 *marks_host = nullptr, *marks_dev = nullptr;   // S3D_MARKS: mapped host counters of started / finished blocks per kernel
     u64 samples_max = 0;             // worst-case samples per frame for these tables
     // chunk working set
     // chunk dedupe table: one allocation {counters[C][GF], keys[C], list[C]} so that a single L2
@@ -1981,6 +1999,7 @@ int fatal_from_flags(s3d_map *m, u32 err)
     u32 zero = 0;   // clear so that the map stays usable after the caller handles the error
     cudaMemcpyAsync(&m->mc->err, &zero, sizeof zero, cudaMemcpyHostToDevice, m->stream);
     cudaStreamSynchronize(m->stream);
+    if (err & ERR_INTERNAL) return fail(S3D_ECUDA, "internal: a bounds guard of the expansion kernel tripped");
     if (err & ERR_VERIFY) return fail(S3D_ECUDA, "S3D_VERIFY_FAST: an accepted fp32 voxel-index estimate differed from the fp64 key");
     if (err & ERR_TABLEFULL) return fail(S3D_ETABLEFULL, "voxel table full (capacity %llu slots)", (unsigned long long)m->cap);
     if (err & ERR_ROUTE_FULL) return fail(S3D_EROUTE, "routed map: a peer inbox overflowed (%llu records per pair; export a larger one)",
@@ -2008,6 +2027,8 @@ int grow_table(s3d_map *m, u64 new_cap)
 {
     new_cap = next_pow2(new_cap);
     if (new_cap <= m->cap) return 0;
+    if (getenv("S3D_LOG")) fprintf(stderr, "[s3d] grow_table: %llu -> %llu at chunk %llu\n", (unsigned long long)m->cap, (unsigned long long)new_cap,
+                                   (unsigned long long)m->chunk_seq);
     Slot *nt = nullptr;
     cudaError_t e = cudaMalloc(&nt, new_cap * sizeof(Slot));
     if (e != cudaSuccess) return fail(S3D_ETABLEFULL, "cannot grow voxel table to %llu slots: %s",
@@ -2100,6 +2121,8 @@ int ensure_scratch(s3d_map *m, u64 want_cap, bool wipe, bool force_realloc = fal
     want_cap = next_pow2(std::max<u64>(want_cap, 1u << 12));
     if (want_cap > (1ull << 31)) return fail(S3D_ENOMEM, "chunk dedupe table would exceed 2^31 entries");
     const bool realloc = want_cap > m->scratch_cap || force_realloc;
+    if (getenv("S3D_LOG")) fprintf(stderr, "[s3d] ensure_scratch: %llu -> %llu realloc=%d wipe=%d at chunk %llu\n", (unsigned long long)m->scratch_cap,
+                                   (unsigned long long)want_cap, (int)realloc, (int)wipe, (unsigned long long)m->chunk_seq);
     const size_t cnt_bytes = lane_bytes(m) * (size_t)std::max<u64>(want_cap, m->scratch_cap) * GF;
     if (realloc) {
         want_cap = std::max<u64>(want_cap, m->scratch_cap);
@@ -2219,6 +2242,7 @@ void launch_apply(s3d_map *m, u64 *skeys, void *scnt, int g, ChunkCtr *cc, DevSt
     a.skeys = skeys; a.scnt = scnt; a.n_slots = (u32)m->scratch_cap; a.g = g; a.cc = cc; a.st = st;
     a.table = m->table; a.tmask = m->cap - 1; a.p = m->p; a.sum_tab = m->sum_tab.p; a.mc = m->mc;
     a.table_limit = table_limit(m); a.seq = m->chunk_seq; a.trace = trace_slot(m, 4);
+    a.marks = m->marks_dev;
     a.life = m->life; a.last = m->dbg_last.p; a.last_n = m->dbg_last_n; a.last_cap = (u32)std::min<size_t>(m->dbg_last.n, 0xffffffffu);
     if (m->debug_on) {
         cudaMemsetAsync(m->dbg_last_n, 0, sizeof(u32), stream);      // the list restarts with every chunk: it ends up holding the last frame
@@ -2241,6 +2265,7 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     const int n_buf = (m->route_on && m->shard_world > 1) ? s3d_map::NBUF : s3d_map::NBUF - 1;
     s3d_map::ChunkBuf &cb = m->buf[m->chunk_seq % (u64)n_buf];
     cudaStream_t xs = (m->chunk_seq & 1) ? m->xstream2 : m->xstream, as = m->stream;
+    if (m->one_xstream) xs = m->xstream;
     if (m->serial) {                 // measurement mode: no overlap, so the event spans are kernel durations
         xs = as;
         CU(cudaStreamWaitEvent(as, m->x_ev, 0));     // (submit_frames zeroed the counters on the expand stream)
@@ -2257,6 +2282,7 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     a.cc = cb.cc; a.stats = j.stats + base; a.mc = m->mc;
     a.seq = m->chunk_seq;
     a.trace = trace_slot(m, 1);
+    a.marks = m->marks_dev;
     a.beam_lo = 0; a.beam_hi = tab.n_beams;
     a.own_rank = (u32)m->shard_rank; a.own_world = m->shard_filter ? (u32)m->shard_world : 1u;
     a.rt = RouteCtx{1u, 0u, 0u, 0ull, nullptr, nullptr, 0ull, 0ull};
@@ -2286,6 +2312,11 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     }
     // (routed: the kernel's last block publishes the record counts to the peers)
     if (a.beam_hi > a.beam_lo) launch_expand(m, a, a.beam_hi - a.beam_lo, g, xs);
+    if (m->debug_sync) {
+        cudaError_t e = cudaStreamSynchronize(xs);
+        if (e != cudaSuccess) return fail(S3D_ECUDA, "k_expand of chunk %llu (frames %lld.., g=%d, tma=%d, bpb=%d): %s", (unsigned long long)m->chunk_seq,
+                                          (long long)base, g, a.use_tma, a.bpb, cudaGetErrorString(e));
+    }
     else if (routed) { k_route_signal<<<1, ROUTE_MAX_WORLD, 0, xs>>>(a.rt); m->launches += 1; }
     const size_t e2 = m->prof_on ? prof_mark(m, xs) : 0;
     CU(cudaEventRecord(cb.expanded, xs));
@@ -2319,6 +2350,11 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     const size_t e3 = m->prof_on ? prof_mark(m, as) : 0;
     launch_apply(m, cb.skeys, cb.scnt, g, cb.cc, j.stats + base, as);
     CU(cudaGetLastError());
+    if (m->debug_sync) {
+        cudaError_t e = cudaStreamSynchronize(as);
+        if (e != cudaSuccess) return fail(S3D_ECUDA, "k_apply_chunk of chunk %llu (frames %lld.., g=%d, cap=%llu, scratch=%llu): %s", (unsigned long long)m->chunk_seq,
+                                          (long long)base, g, (unsigned long long)m->cap, (unsigned long long)m->scratch_cap, cudaGetErrorString(e));
+    }
     CU(cudaEventRecord(cb.freed, as));
     cb.used = true;
     if (m->prof_on) {
@@ -2356,6 +2392,9 @@ int recover(s3d_map *m)
         return fail(S3D_EROUTE, "routed map: chunk %llu needs a re-run (flags %u: 1 = dedupe table, 2 = voxel table, 4 = counter width); "
                                 "peers cannot replay it -- reserve capacity (s3d_reserve) before ingesting",
                     (unsigned long long)mc.abort_seq, mc.abort);
+    if (getenv("S3D_LOG")) fprintf(stderr, "[s3d] recover: abort=%u abort_seq=%llu chunk_seq=%llu count=%llu cap=%llu scratch=%llu\n", mc.abort,
+                                   (unsigned long long)mc.abort_seq, (unsigned long long)m->chunk_seq, (unsigned long long)mc.count,
+                                   (unsigned long long)m->cap, (unsigned long long)m->scratch_cap);
     const InFlight inf = m->inflight[mc.abort_seq % s3d_map::RING];
     if (inf.seq != mc.abort_seq) return fail(S3D_ECUDA, "internal: lost track of chunk %llu", (unsigned long long)mc.abort_seq);
     ++m->n_retries;
@@ -2378,6 +2417,10 @@ int recover(s3d_map *m)
             CU(cudaMemsetAsync(j.stats + j.next, 0, sizeof(DevStats) * (size_t)(j.n - j.next), m->stream));
     }
     if (!hit) return fail(S3D_ECUDA, "internal: retry for an unknown job");
+    // The cleared retry flag and the zeroed counters were queued on the apply stream; the re-run's k_expand goes to
+    // an expand stream that is not ordered behind it.  Without this wait a block of the re-run could still see the
+    // old flag and leave without expanding its tile -- frames lost without a trace (found with tools/stress_growth.py).
+    CU(cudaStreamSynchronize(m->stream));
     return 0;
 }
 
@@ -2405,7 +2448,17 @@ int pump(s3d_map *m, bool drain)
                 // wait for the counters of chunk q-1-LOOKAHEAD: bounds the launch-ahead and is
                 // where retries and growth needs are noticed early
                 const int ri = (int)((q - 1 - LOOKAHEAD) % s3d_map::RING);
-                CU(cudaEventSynchronize(m->snap_ev[ri]));
+                {
+                    cudaError_t e_ = cudaEventSynchronize(m->snap_ev[ri]);
+                    if (e_ != cudaSuccess) {
+                        if (m->marks_host)
+                            return fail(S3D_ECUDA, "%s while waiting for chunk %llu of %llu queued; blocks started/finished: k_expand %llu/%llu, k_apply_chunk %llu/%llu",
+                                        cudaGetErrorString(e_), (unsigned long long)(q - 1 - LOOKAHEAD), (unsigned long long)q,
+                                        (unsigned long long)m->marks_host[0], (unsigned long long)m->marks_host[1],
+                                        (unsigned long long)m->marks_host[2], (unsigned long long)m->marks_host[3]);
+                        return fail(S3D_ECUDA, "cudaEventSynchronize(m->snap_ev[ri]): %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__);
+                    }
+                }
                 const MapCtr &sn = m->snap_host[ri];
                 if (sn.abort) { int rc = recover(m); if (rc) return rc; continue; }
                 m->count_known = sn.count;
@@ -2611,6 +2664,13 @@ int s3d_create(int device, uint64_t initial_capacity, s3d_map **out)
     { const char *e = getenv("S3D_NO_TMA"); if (e && atoi(e) != 0) m->tma_ok = false; }
     { const char *e = getenv("S3D_ROUTE_SPLIT"); if (e && !strcmp(e, "beams")) m->route_by_chunk = false; }
     { const char *e = getenv("S3D_SERIAL_KERNELS"); if (e && atoi(e) != 0) m->serial = true; }
+    { const char *e = getenv("S3D_DEBUG_SYNC"); if (e && atoi(e) != 0) m->debug_sync = true; }
+    { const char *e = getenv("S3D_ONE_XSTREAM"); if (e && atoi(e) != 0) m->one_xstream = true; }
+    if (const char *e = getenv("S3D_MARKS")) if (atoi(e) != 0) {
+        CU(cudaHostAlloc(&m->marks_host, 8 * sizeof(u64), cudaHostAllocMapped));
+        memset(m->marks_host, 0, 8 * sizeof(u64));
+        CU(cudaHostGetDevicePointer(&m->marks_dev, m->marks_host, 0));
+    }
     { const char *e = getenv("S3D_NO_FAST32"); if (e && atoi(e) != 0) m->fast32_ok = false; }
     { const char *e = getenv("S3D_VERIFY_FAST"); if (e && atoi(e) != 0) m->verify_fast = true; }
     { const char *e = getenv("S3D_SCRATCH_CAP"); if (e && atoll(e) > 0) m->scratch_env = (u64)atoll(e); }
@@ -2787,7 +2847,7 @@ int s3d_set_tables(s3d_map *m, const s3d_tables *t)
     d.free_step = t->free_step; d.occ_window = t->occ_window;
     d.beam_col = m->d_beam_col.p; d.cos_b = m->d_cos_b.p; d.sin_b = m->d_sin_b.p; d.range_m = m->d_range.p;
     d.nv_free = m->d_nv_free.p; d.nv_occ = m->d_nv_occ.p; d.cos_va = m->d_cos_va.p; d.sin_va = m->d_sin_va.p;
-    d.csva32 = m->d_csva32.p; d.col_step = col_step > 0 ? col_step : 0;
+    d.csva32 = m->d_csva32.p; d.col_step = col_step > 0 ? col_step : 0; d.n_trig = (int)nfan;
     m->have_tables = true;
     {
         const int cap = 200 * 1024;
@@ -3132,7 +3192,7 @@ int s3d_shard_expand(s3d_map *m, const uint8_t *images_dev, const double *T_dev,
             a.skeys = m->skeys; a.scnt = m->scnt; a.smask = (u32)(m->scratch_cap - 1);
             a.cc = m->cc; a.stats = st; a.mc = m->mc;
             a.seq = m->chunk_seq;                                // the owner gates growth, not the expander
-            a.trace = nullptr;
+            a.trace = nullptr; a.marks = nullptr;
             a.beam_lo = lo; a.beam_hi = hi;
             a.own_rank = 0; a.own_world = 1;
             a.rt = RouteCtx{1u, 0u, 0u, 0ull, nullptr, nullptr, 0ull, 0ull};

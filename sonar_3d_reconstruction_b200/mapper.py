@@ -14,6 +14,7 @@ without a visible GPU raises.
 from __future__ import annotations
 
 import time
+import weakref
 from collections import defaultdict
 from typing import Any, Dict, Iterator, List, Optional, Tuple
 
@@ -109,7 +110,7 @@ class _VoxelView:
     (i, j, k) int tuples, values float log-odds.  Reads go to the GPU table on demand."""
 
     def __init__(self, octree: "SimpleOctree"):
-        self._o = octree
+        self._o = weakref.proxy(octree)      # (no reference cycle: the octree, and with it the device table, is freed with its last user)
 
     @staticmethod
     def _key(key) -> np.ndarray:
@@ -312,6 +313,10 @@ class SimpleOctree:
         self._native.clear()
         self._pt_min = np.array([float("inf")] * 3)
         self._pt_max = np.array([-float("inf")] * 3)
+
+    def close(self):
+        """Release the device memory now (extension; otherwise it goes with the last reference)."""
+        self._native.close()
 
 
 class PendingBatch:
@@ -661,6 +666,10 @@ class SonarTo3DMapper:
             'free': {'points': r[NativeMap.CLASS_FREE], 'rgba': (0.0, 0.0, 1.0, 0.3), 'scale': res},
             'unknown': {'points': r[NativeMap.CLASS_UNKNOWN], 'rgba': (1.0, 1.0, 0.0, 0.5), 'scale': res},
         }
+
+    def close(self):
+        """Release the device memory now (extension; otherwise it goes with the last reference)."""
+        self.octree.close()
 
     def reset_map(self):
         self.octree.clear()
