@@ -1341,12 +1341,19 @@ k_apply_chunk(const ApplyArgs a)
         tile += gridDim.x;
         more = tile < n_tiles;
         __syncthreads();
-        u32 avail = s_tail - head;                                // (nobody appends before the next barrier)
+        u32 avail = s_tail - head;
+        bool ran = false;
         while (avail >= (u32)AP_THREADS || (!more && avail > 0u)) {   // full batches; the last one may be ragged
             const u32 n = min(avail, (u32)AP_THREADS);
             batch(n);
             avail -= n;
+            ran = true;
         }
+        // Nobody may append to the list before every thread has read the tail above: a warp that ran ahead into the
+        // next scan would move `s_tail` under a slower warp, the two would disagree on `avail`, and the block would
+        // split over the barriers inside batch().  A batch ends with a barrier; a tile too sparse for one needs its own.
+        // (found with tools/stress_growth.py: sparse tiles are what the short last chunk of a call produces)
+        if (!ran) __syncthreads();
     }
     flush_packed();
     acc_publish(acc, mc, false);
