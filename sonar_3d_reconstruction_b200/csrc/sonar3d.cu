@@ -2319,12 +2319,12 @@ int enqueue_chunk(s3d_map *m, const Job &j, int64_t base, int g)
     }
     // (routed: the kernel's last block publishes the record counts to the peers)
     if (a.beam_hi > a.beam_lo) launch_expand(m, a, a.beam_hi - a.beam_lo, g, xs);
+    else if (routed) { k_route_signal<<<1, ROUTE_MAX_WORLD, 0, xs>>>(a.rt); m->launches += 1; }
     if (m->debug_sync) {
         cudaError_t e = cudaStreamSynchronize(xs);
         if (e != cudaSuccess) return fail(S3D_ECUDA, "k_expand of chunk %llu (frames %lld.., g=%d, tma=%d, bpb=%d): %s", (unsigned long long)m->chunk_seq,
                                           (long long)base, g, a.use_tma, a.bpb, cudaGetErrorString(e));
     }
-    else if (routed) { k_route_signal<<<1, ROUTE_MAX_WORLD, 0, xs>>>(a.rt); m->launches += 1; }
     const size_t e2 = m->prof_on ? prof_mark(m, xs) : 0;
     CU(cudaEventRecord(cb.expanded, xs));
     if (routed) {

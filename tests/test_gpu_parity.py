@@ -475,3 +475,35 @@ def test_fp32_estimate_never_disagrees_with_the_fp64_key(s3d, monkeypatch, cfg_n
     plain = s3d.SonarTo3DMapper(cfg)
     assert [_stats3(x) for x in plain.process_sonar_images(images, pos, quat)] == want
     assert_same_map(*v.octree.voxels.to_arrays(), *plain.octree.voxels.to_arrays(), 0.0, "fp64-only, plain loads")
+
+
+def test_many_short_calls_equal_one_call(s3d):
+    """Streaming in calls that are not a multiple of the chunk size (24 frames: a full chunk and a half-full one,
+    whose dedupe table is sparse) must give what one call gives -- per-frame counters and the whole map.  A few
+    hundred chunks back to back with nothing drained in between: the shape that exposed a block-level race in the
+    update kernel (tools/stress_growth.py is the long version)."""
+    import torch
+    from sonar_3d_reconstruction_b200 import synthetic
+    n, step = 2400, 24
+    base, pos, quat, cfg = synthetic.make_sequence("cfg2", n, seed=1, distinct_images=250, cycle=False)
+    d_img = torch.from_numpy(np.ascontiguousarray(base)).cuda()[torch.arange(n, device="cuda") % len(base)]
+    H, W = base.shape[1:]
+    maps, stats = [], []
+    for calls in (step, n, step):
+        m = s3d.SonarTo3DMapper(cfg)
+        m._check_width(W); m._sync_device_config(H, W)
+        nat = m.octree._native
+        d_T = torch.from_numpy(np.ascontiguousarray(m.compose_transforms(pos, quat).reshape(n, 16))).cuda()
+        st = torch.zeros((n, 8), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        for f0 in range(0, n, calls):
+            k = min(calls, n - f0)
+            nat.ingest_batch_dev(d_img.data_ptr() + f0 * H * W, k, d_T.data_ptr() + f0 * 128, want_stats=False,
+                                 stats_dev_ptr=st.data_ptr() + f0 * 64)
+        nat.sync()
+        stats.append(st.cpu().numpy()[:, :4])
+        maps.append(sort_by_key(*m.octree.voxels.to_arrays()))
+        m.close()
+    for i in (0, 2):
+        assert np.array_equal(stats[i], stats[1]), f"per-frame counters, run {i}"
+        assert np.array_equal(maps[i][0], maps[1][0]) and np.array_equal(maps[i][1], maps[1][1]), f"map, run {i}"
