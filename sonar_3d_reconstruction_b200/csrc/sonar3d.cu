@@ -1017,14 +1017,11 @@ __device__ __forceinline__ void acc_key(LocalAcc &a, u64 key)
 // the live-voxel counter (the chunk path does that once, from its per-frame totals).
 __device__ __forceinline__ void acc_publish(LocalAcc &a, MapCtr *mc, bool add_count)
 {
+    a.n_new = __reduce_add_sync(0xffffffffu, a.n_new);
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        a.n_new += __shfl_xor_sync(0xffffffffu, a.n_new, d);
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            a.kmin[q] = min(a.kmin[q], __shfl_xor_sync(0xffffffffu, a.kmin[q], d));
-            a.kmax[q] = max(a.kmax[q], __shfl_xor_sync(0xffffffffu, a.kmax[q], d));
-        }
+    for (int q = 0; q < 3; ++q) {
+        a.kmin[q] = __reduce_min_sync(0xffffffffu, a.kmin[q]);
+        a.kmax[q] = __reduce_max_sync(0xffffffffu, a.kmax[q]);
     }
     if ((threadIdx.x & 31) == 0) {
         if (add_count && a.n_new) atomicAdd(&mc->count, (u64)a.n_new);
@@ -1041,6 +1038,7 @@ constexpr int AP_WARPS = AP_THREADS / 32;
 constexpr int AP_SCAN = 2;                   // dedupe slots per thread per scan step (independent loads)
 constexpr int AP_TILE = AP_THREADS * AP_SCAN;   // dedupe slots a block scans per step
 constexpr int AP_LCAP = 1024;                // live list (ring): less than a batch left over + one tile
+constexpr int AP_PK_ROUNDS = 7;              // batches between reductions of the packed per-frame byte counters: 32 lanes x 7 < 256
 constexpr int SUMT = 64;                     // entries of the sequential-sum tables
 static_assert(AP_LCAP >= AP_THREADS + AP_TILE && (AP_LCAP & (AP_LCAP - 1)) == 0, "list holds a leftover batch plus one tile");
 // staged counter lanes of the entries of a batch: one padded row per entry (stride of 5 / 9
@@ -1129,16 +1127,20 @@ k_apply_chunk(const ApplyArgs a)
     MapCtr *mc = a.mc; ChunkCtr *cc = a.cc;
     // a retry was asked for by this chunk or an earlier one: stay side-effect free.  (An older
     // chunk keeps running when a later chunk -- expanded concurrently -- raises the flag.)
-    if (__ldcg(&mc->abort) != 0u && a.seq >= __ldcg(&mc->abort_seq)) return;
+    // (the four counter loads of this prologue are independent: one round trip instead of three)
+    const u32 abort0 = __ldcg(&mc->abort);
+    const u64 abort_seq0 = __ldcg(&mc->abort_seq);
+    const u64 count0 = __ldcg(&mc->count);
+    const u32 uniq0 = __ldcg(&cc->n_unique);
+    if (abort0 != 0u && a.seq >= abort_seq0) return;
     // The gate: the chunk may be applied only if the table keeps its load bound even when every
     // voxel of the chunk is new; otherwise nothing of it touches the table and the host grows the
     // table and re-runs the chunk.  Every block takes the same decision from the same numbers
     // (the previous chunk has finished on this stream, so `count` is final until our last block).
-    const u64 count0 = __ldcg(&mc->count);
     {
         u64 load = count0;
         if (DEBUG) load = max(load, __ldcg(&mc->life_count));
-        if (load + __ldcg(&cc->n_unique) > a.table_limit) {
+        if (load + uniq0 > a.table_limit) {
             if (blockIdx.x == 0 && threadIdx.x == 0) raise_abort(mc, ABORT_TABLE, a.seq);
             return;
         }
@@ -1177,16 +1179,21 @@ k_apply_chunk(const ApplyArgs a)
     u32 pk_rounds = 0;
     u32 head = 0;                                                 // block-uniform: list entries already taken
 
+    // (a byte of a lane counts at most one voxel per batch, so after <= AP_PK_ROUNDS batches the warp's sum of a
+    // byte still fits the byte: the packed words are reduced whole, then lane f takes frame f's byte)
     auto flush_packed = [&]() {
+        u32 xo = 0, xf = 0;
 #pragma unroll
         for (int w = 0; w < GF / 4; ++w) {
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const u32 so = __reduce_add_sync(0xffffffffu, (pk_occ[w] >> (8 * b)) & 0xffu);
-                const u32 sf = __reduce_add_sync(0xffffffffu, (pk_free[w] >> (8 * b)) & 0xffu);
-                if (lane == 0) { if (so) atomicAdd(&s_occ[4 * w + b], so); if (sf) atomicAdd(&s_free[4 * w + b], sf); }
-            }
+            const u32 ro = __reduce_add_sync(0xffffffffu, pk_occ[w]);
+            const u32 rf = __reduce_add_sync(0xffffffffu, pk_free[w]);
+            if ((int)(lane >> 2) == w) { xo = ro; xf = rf; }
             pk_occ[w] = 0; pk_free[w] = 0;
+        }
+        if (lane < (u32)GF) {
+            const u32 so = (xo >> (8 * (lane & 3))) & 0xffu, sf = (xf >> (8 * (lane & 3))) & 0xffu;
+            if (so) atomicAdd(&s_occ[lane], so);
+            if (sf) atomicAdd(&s_free[lane], sf);
         }
         pk_rounds = 0;
     };
@@ -1275,7 +1282,7 @@ k_apply_chunk(const ApplyArgs a)
             base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
             rank = base + __popc(peers & lt_mask);
         }
-        if (++pk_rounds == 255u) flush_packed();
+        if (++pk_rounds == (u32)AP_PK_ROUNDS) flush_packed();
         __syncthreads();
         if (have) {
             u32 pos = rank;                                       // longest chains first
