@@ -76,6 +76,7 @@ struct __align__(16) Slot { u64 key; double val; };
 struct DevParams {
     double res, inv_res, lo_occ, lo_free, lo_min, lo_max, a_thr, a_ratio, zmin;
     double l_skip;   // log-odds above which prob > a_thr for sure (+inf = never skip the exp)
+    double scale0;   // factor of an occupied update on a voxel with L == 0 (prob == 0.5 exactly): (0.5 / a_thr) * a_ratio, or 1 when 0.5 > a_thr
     int adaptive, zfilter, thr;
     u32 fr_hi_lo, fr_hi_span;   // high words bounding the fractional parts the fast quantiser accepts
 };
@@ -961,8 +962,10 @@ __device__ __forceinline__ double apply_one(double L, double upd, bool adaptive,
     if (adaptive && p.adaptive && upd > 0.0) {                  // :95
         // :97 prob = 1/(1+exp(-L)).  Two cases need no exp: L == 0 gives exactly 0.5, and L well
         // above logit(threshold) gives prob > threshold, i.e. no scaling at all.
-        if (!(L > p.l_skip)) {
-            const double prob = (L == 0.0) ? 0.5 : 1.0 / (1.0 + exp(-L));
+        if (L == 0.0) {
+            upd *= p.scale0;                                    // prob == 0.5 exactly: the factor is a constant (1 if 0.5 > threshold)
+        } else if (!(L > p.l_skip)) {
+            const double prob = 1.0 / (1.0 + exp(-L));
             if (prob <= p.a_thr) upd *= (prob / p.a_thr) * p.a_ratio;   // :100-102
         }
     }
@@ -1025,10 +1028,13 @@ __device__ __forceinline__ void acc_publish(LocalAcc &a, MapCtr *mc, bool add_co
     }
     if ((threadIdx.x & 31) == 0) {
         if (add_count && a.n_new) atomicAdd(&mc->count, (u64)a.n_new);
+        int lo[3], hi[3];                                       // (read together: one round trip, not six)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { lo[q] = __ldcg(&mc->kmin[q]); hi[q] = __ldcg(&mc->kmax[q]); }
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            if (a.kmin[q] < __ldcg(&mc->kmin[q])) atomicMin(&mc->kmin[q], a.kmin[q]);
-            if (a.kmax[q] > __ldcg(&mc->kmax[q])) atomicMax(&mc->kmax[q], a.kmax[q]);
+            if (a.kmin[q] < lo[q]) atomicMin(&mc->kmin[q], a.kmin[q]);
+            if (a.kmax[q] > hi[q]) atomicMax(&mc->kmax[q], a.kmax[q]);
         }
     }
 }
@@ -1040,6 +1046,8 @@ constexpr int AP_TILE = AP_THREADS * AP_SCAN;   // dedupe slots a block scans pe
 constexpr int AP_LCAP = 1024;                // live list (ring): less than a batch left over + one tile
 constexpr int AP_PK_ROUNDS = 7;              // batches between reductions of the packed per-frame byte counters: 32 lanes x 7 < 256
 constexpr int SUMT = 64;                     // entries of the sequential-sum tables
+constexpr int AP_MF = 8;                     // mean table: n_free < AP_MF (any n_occ < SUMT), plus the pure-free row
+constexpr int MEAN_WORDS = (AP_MF + 1) * SUMT;
 static_assert(AP_LCAP >= AP_THREADS + AP_TILE && (AP_LCAP & (AP_LCAP - 1)) == 0, "list holds a leftover batch plus one tile");
 // staged counter lanes of the entries of a batch: one padded row per entry (stride of 5 / 9
 // sixteen-byte words: conflict-free 128-bit stores)
@@ -1089,6 +1097,14 @@ __device__ __forceinline__ u64 table_resolve(Slot *table, u64 mask, u64 key, u64
 
 // spread the low 4 bits of x into the low bits of the 4 bytes of a word
 __device__ __forceinline__ u32 spread4(u32 x) { return ((x & 0xFu) * 0x00204081u) & 0x01010101u; }
+
+#ifdef S3D_AP_PHASES
+// build-time instrumentation (tools only): clock64 spans of thread 0 of every block, summed per phase
+__device__ unsigned long long g_ap_phase[16];
+#define AP_PH(i) do { if (tid == 0) { const long long t1_ = clock64(); ph_acc[i] += (unsigned long long)(t1_ - ph_t0); ph_t0 = t1_; } } while (0)
+#else
+#define AP_PH(i) do { } while (0)
+#endif
 
 struct ApplyArgs {
     u64 *skeys; void *scnt; u32 n_slots; int g;
@@ -1158,20 +1174,26 @@ k_apply_chunk(const ApplyArgs a)
     __shared__ u32 s_occ[GF], s_free[GF], s_new[GF];
     __shared__ u32 s_dmax[GF], s_dgt10[GF], s_lifenew;
     __shared__ u64 s_dlife[GF];
-    __shared__ double s_sum[4][SUMT];
+    __shared__ double s_mean[MEAN_WORDS];   // per-voxel mean of a frame's sample deltas by (n_free, n_occ): one lookup per update
     __shared__ bool s_last;
     const u32 tid = threadIdx.x, lane = tid & 31;
     const u32 lt_mask = (1u << lane) - 1;
     const DevParams &p = a.p;
+#ifdef S3D_AP_PHASES
+    unsigned long long ph_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long ph_t0 = clock64();
+#endif
     if (tid < GF) { s_occ[tid] = 0; s_free[tid] = 0; s_new[tid] = 0; s_dmax[tid] = 0; s_dgt10[tid] = 0; s_dlife[tid] = 0; }
     if (tid <= GF) s_hist[tid] = 0;
     if (tid == 0) { s_lifenew = 0; s_tail = 0; }
-    for (int q = tid; q < 4 * SUMT; q += AP_THREADS) (&s_sum[0][0])[q] = a.sum_tab[q];
+    for (int q = tid; q < MEAN_WORDS; q += AP_THREADS) s_mean[q] = a.sum_tab[4 * SUMT + q];
+    const double (*gsum)[SUMT] = reinterpret_cast<const double (*)[SUMT]>(a.sum_tab);    // running sums, for counts beyond the table
     __syncthreads();
     constexpr int ROWW = ap_row_words<CT>();
     constexpr int NV = (int)(sizeof(CT) * GF / 16);
     u32 *rows = reinterpret_cast<u32 *>(s_dyn);
     CT *scnt = static_cast<CT *>(a.scnt);
+    AP_PH(0);
     LocalAcc acc; acc_init(acc);
     u32 pk_occ[GF / 4], pk_free[GF / 4];                          // byte f%4 of word f/4: voxels updated as occupied / free in frame f
 #pragma unroll
@@ -1220,6 +1242,7 @@ k_apply_chunk(const ApplyArgs a)
                 l1 = __ldcg(reinterpret_cast<const ulonglong2 *>(&a.life[pair + 1]));
             }
             // ---- the entry is ready for the next chunk
+            AP_PH(2);
             a.skeys[s] = EMPTY_KEY;
 #pragma unroll
             for (int q = 0; q < NV; ++q) cp[q] = make_uint4(0u, 0u, 0u, 0u);
@@ -1244,6 +1267,7 @@ k_apply_chunk(const ApplyArgs a)
                     }
                 }
             }
+            AP_PH(3);
             u64 slot = ~0ull; double L = 0.0;
             if (m_any) {
                 bool fresh;
@@ -1273,6 +1297,7 @@ k_apply_chunk(const ApplyArgs a)
             }
             s_L[tid] = L; s_tslot[tid] = slot; s_mask[tid] = m_any;
             nfr = (u32)__popc(m_any);
+            AP_PH(4);
         }
         {
             // rank among the batch's entries with the same frame count (one shared atomic per distinct count per warp)
@@ -1284,12 +1309,21 @@ k_apply_chunk(const ApplyArgs a)
         }
         if (++pk_rounds == (u32)AP_PK_ROUNDS) flush_packed();
         __syncthreads();
-        if (have) {
-            u32 pos = rank;                                       // longest chains first
-            for (u32 c = nfr + 1; c <= (u32)GF; ++c) pos += s_hist[c];
-            s_ord[pos] = (unsigned short)tid;
+        AP_PH(5);
+        {
+            // longest chains first: an entry goes behind all entries with more frames.  Lane l holds the number of
+            // entries with l + 1 frames; a warp suffix scan gives every count's offset at once.
+            u32 suf = lane < (u32)GF ? s_hist[lane + 1] : 0u;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 t = __shfl_down_sync(0xffffffffu, suf, d);
+                if (lane + d < 32u) suf += t;
+            }
+            const u32 longer = __shfl_sync(0xffffffffu, suf, nfr & 31u);     // entries with more than nfr frames
+            if (have) s_ord[rank + (nfr < 32u ? longer : 0u)] = (unsigned short)tid;
         }
         __syncthreads();
+        AP_PH(6);
         if (tid <= GF) s_hist[tid] = 0;
         if (have) {
             const u32 e = s_ord[tid];
@@ -1298,17 +1332,21 @@ k_apply_chunk(const ApplyArgs a)
                 double L = s_L[e];
                 u64 life = DEBUG ? s_life[e] : 0ull;
                 const CT *row = reinterpret_cast<const CT *>(rows + (size_t)e * ROWW);
+                // (measured and rejected: unrolling the chain over all GF frames with the lanes and means fetched up
+                // front -- the chains are short on average, and the extra work cost more than the shorter steps saved)
                 while (todo) {                                                  // only the frames that touched the voxel, in order
                     const int f = __ffs(todo) - 1;
                     todo &= todo - 1;
                     const CT cf = row[f];
                     const u32 n_occ = Lane<CT>::n_occ(cf), n_free = Lane<CT>::n_free(cf);
-                    if (n_occ == 0u && n_free < (u32)SUMT) {                     // the common case: a free update (:565-567)
-                        L += s_sum[2][n_free];
-                        L = L < p.lo_min ? p.lo_min : (L > p.lo_max ? p.lo_max : L);
-                    } else {
-                        L = apply_one(L, seq_avg(n_free, n_occ, s_sum, p), n_occ > 0, p);
-                    }
+                    // mean of the frame's sample deltas for this voxel (:557-559): tabulated by (n_free, n_occ), so that
+                    // free, occupied and mixed voxels of a warp take the same few instructions
+                    const bool small = n_free < (u32)AP_MF && n_occ < (u32)SUMT;
+                    const u32 ti = small ? n_free * (u32)SUMT + n_occ : (u32)(AP_MF * SUMT) + n_free;
+                    double upd;
+                    if (small || (n_occ == 0u && n_free < (u32)SUMT)) upd = s_mean[ti];
+                    else upd = seq_avg(n_free, n_occ, gsum, p);
+                    L = apply_one(L, upd, n_occ > 0u, p);                         // :562-567
                     if (DEBUG) {
                         const u32 nn = n_occ + n_free;                          // frame_update_counts[key] (:550)
                         life += nn;                                             // voxel_update_counts[key] (:551)
@@ -1322,7 +1360,9 @@ k_apply_chunk(const ApplyArgs a)
             }
         }
         head += n;
+        AP_PH(7);
         __syncthreads();
+        AP_PH(8);
     };
 
     const u32 n_tiles = a.n_slots / AP_TILE;
@@ -1348,6 +1388,7 @@ k_apply_chunk(const ApplyArgs a)
         tile += gridDim.x;
         more = tile < n_tiles;
         __syncthreads();
+        AP_PH(1);
         u32 avail = s_tail - head;
         bool ran = false;
         while (avail >= (u32)AP_THREADS || (!more && avail > 0u)) {   // full batches; the last one may be ragged
@@ -1387,33 +1428,57 @@ k_apply_chunk(const ApplyArgs a)
         s_last = (t == gridDim.x - 1);
     }
     __syncthreads();
-    if (s_last && tid == 0) {
+    if (s_last && tid < 32u) {
+        // (one warp, lane f = frame f: the per-frame totals are fetched together -- a single L2 round trip, where a
+        // loop over the frames would pay one per frame with every other block already gone -- and turned into running
+        // values by a warp scan)
         __threadfence();
-        u64 run = count0;
-        u64 lmax = DEBUG ? __ldcg(&mc->life_max) : 0ull;
-        for (int f = 0; f < a.g; ++f) {
-            run += atomicAdd(&cc->neu[f], 0u);
-            a.st[f].n_voxels = run;
-            cc->neu[f] = 0;
+        const bool mine = (int)lane < a.g;
+        u32 neu = mine ? atomicAdd(&cc->neu[lane], 0u) : 0u;
+        u64 dl = 0; u32 dm = 0, dg = 0;
+        if (DEBUG && mine) { dl = atomicMax(&cc->dlife[lane], 0ull); dm = atomicMax(&cc->dmax[lane], 0u); dg = atomicAdd(&cc->dgt10[lane], 0u); }
+        const u32 uniq = atomicAdd(&cc->n_unique, 0u);
+        const u32 life_new = DEBUG ? atomicAdd(&cc->life_new, 0u) : 0u;
+        u64 lmax = DEBUG ? max(__ldcg(&mc->life_max), dl) : 0ull;
+        u32 incl = neu;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, d);
+            const u64 tl = __shfl_up_sync(0xffffffffu, lmax, d);
+            if ((int)lane >= d) { incl += t; lmax = max(lmax, tl); }
+        }
+        if (mine) {
+            a.st[lane].n_voxels = count0 + incl;                            // len(voxels) after frame f (:592)
+            cc->neu[lane] = 0;
             if (DEBUG) {
-                lmax = max(lmax, (u64)atomicMax(&cc->dlife[f], 0ull));
-                a.st[f].max_in_frame = atomicMax(&cc->dmax[f], 0u);
-                a.st[f].n_gt10 = atomicAdd(&cc->dgt10[f], 0u);
-                a.st[f].max_total = lmax;                               // max(voxel_update_counts.values()) (:578)
-                cc->dmax[f] = 0; cc->dgt10[f] = 0; cc->dlife[f] = 0;
+                a.st[lane].max_in_frame = dm;
+                a.st[lane].n_gt10 = dg;
+                a.st[lane].max_total = lmax;                                // max(voxel_update_counts.values()) (:578)
+                cc->dmax[lane] = 0; cc->dgt10[lane] = 0; cc->dlife[lane] = 0;
             }
         }
-        if (DEBUG) {
-            mc->life_max = lmax;
-            mc->life_count = __ldcg(&mc->life_count) + atomicAdd(&cc->life_new, 0u);
-            cc->life_new = 0;
+        const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+        const u64 lmax_all = __shfl_sync(0xffffffffu, lmax, 31);
+        if (lane == 0) {
+            if (DEBUG) {
+                mc->life_max = lmax_all;
+                mc->life_count = __ldcg(&mc->life_count) + life_new;
+                cc->life_new = 0;
+            }
+            mc->last_new = total;
+            mc->last_unique = uniq;
+            mc->probes += uniq;
+            atomicExch(&mc->count, count0 + total);
+            cc->n_unique = 0; cc->ticket = 0;
         }
-        mc->last_new = (u32)(run - count0);
-        mc->last_unique = atomicAdd(&cc->n_unique, 0u);
-        mc->probes += mc->last_unique;
-        atomicExch(&mc->count, run);
-        cc->n_unique = 0; cc->ticket = 0;
     }
+#ifdef S3D_AP_PHASES
+    AP_PH(9);
+    if (tid == 0) {
+        for (int i = 0; i < 10; ++i) atomicAdd(&g_ap_phase[i], ph_acc[i]);
+        atomicAdd(&g_ap_phase[15], 1ull);
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------ sharded map
@@ -1921,7 +1986,7 @@ struct s3d_map {
     cudaStream_t snap_stream = nullptr;  // per-chunk counter snapshots (device -> pinned host)
     cudaStream_t mstream = nullptr;      // routed map: owner-side merges
     cudaStream_t ctl_stream = nullptr;   // small reads for s3d_ingest_collect (never behind queued chunks)
-    DevBuf<double> sum_tab;          // [4][SUMT] running sums of n copies of lo_free / lo_occ, and their means
+    DevBuf<double> sum_tab;          // [4][SUMT] running sums of n copies of lo_free / lo_occ and their means, then the (n_free, n_occ) mean table
     ChunkCtr *cc = nullptr;
     DevBuf<DevStats> stats; DevStats *stats_host = nullptr; size_t stats_host_n = 0;
     // staging
@@ -1939,7 +2004,7 @@ struct s3d_map {
     bool debug_on = false;
     Slot *life = nullptr;            // same capacity / probing as the voxel table; val holds a u64 count
     DevBuf<ulonglong2> dbg_last; u32 *dbg_last_n = nullptr;
-    int apply_bps = 2;               // k_apply_chunk blocks per SM (S3D_APPLY_BPS; measured at cfg2: 2 > 3 > 1 > 4 beside k_expand)
+    int apply_bps = 3;               // k_apply_chunk blocks per SM at most (S3D_APPLY_BPS; with the balanced grid: cfg2 equal for 2 and 3, cfg3 update kernel 301 -> 258 us)
     // measurement
     bool prof_on = false;
     std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
@@ -2251,7 +2316,12 @@ void launch_apply(s3d_map *m, u64 *skeys, void *scnt, int g, ChunkCtr *cc, DevSt
 {
     // one tile of AP_TILE slots per block and step; up to `apply_bps` blocks per SM
     const u64 tiles = m->scratch_cap / AP_TILE;
-    const int blocks = (int)std::max<u64>(1, std::min<u64>(tiles, (u64)m->n_sm * (u64)m->apply_bps));
+    // (the fewest blocks that keep the busiest block's tile count: 1024 tiles on 296 block slots are 4 per block
+    // either way, and 256 blocks leave more of the SMs to the expansion running beside)
+    u64 nb = std::max<u64>(1, std::min<u64>(tiles, (u64)m->n_sm * (u64)m->apply_bps));
+    const u64 per = (tiles + nb - 1) / nb;
+    if (per > 0) nb = std::max<u64>(1, (tiles + per - 1) / per);
+    const int blocks = (int)nb;
     ApplyArgs a;
     a.skeys = skeys; a.scnt = scnt; a.n_slots = (u32)m->scratch_cap; a.g = g; a.cc = cc; a.st = st;
     a.table = m->table; a.tmask = m->cap - 1; a.p = m->p; a.sum_tab = m->sum_tab.p; a.mc = m->mc;
@@ -2720,6 +2790,20 @@ int s3d_destroy(s3d_map *m)
     if (!m) return 0;
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
+#ifdef S3D_AP_PHASES
+    {
+        unsigned long long ph[16];
+        if (cudaMemcpyFromSymbol(ph, g_ap_phase, sizeof ph) == cudaSuccess && ph[15]) {
+            unsigned long long tot = 0;
+            for (int i = 0; i < 10; ++i) tot += ph[i];
+            fprintf(stderr, "[s3d] k_apply_chunk phases over %llu blocks (%% of thread-0 time; cycles per block):", ph[15]);
+            for (int i = 0; i < 10; ++i) fprintf(stderr, " p%d %.1f%% %llu;", i, 100.0 * (double)ph[i] / (double)tot, ph[i] / ph[15]);
+            fprintf(stderr, "\n");
+            memset(ph, 0, sizeof ph);
+            cudaMemcpyToSymbol(g_ap_phase, ph, sizeof ph);
+        }
+    }
+#endif
     if (m->table) cudaFree(m->table);
     if (m->life) cudaFree(m->life);
     if (m->dbg_last_n) cudaFree(m->dbg_last_n);
@@ -2783,6 +2867,7 @@ int s3d_set_params(s3d_map *m, const s3d_params *q)
     p.adaptive = q->adaptive_update; p.zfilter = q->z_filter_enabled;
     p.l_skip = (p.a_thr > 1e-3 && p.a_thr < 1.0 - 1e-3) ? std::log(p.a_thr / (1.0 - p.a_thr)) + 1e-6
                                                          : std::numeric_limits<double>::infinity();
+    p.scale0 = (0.5 <= p.a_thr) ? (0.5 / p.a_thr) * p.a_ratio : 1.0;
     p.thr = std::max(-1, std::min(255, q->intensity_threshold));
     {
         // fast quantiser: fractional parts in (1e-6, 1 - 1e-6) are decided by the reciprocal product
@@ -2802,7 +2887,21 @@ int s3d_set_params(s3d_map *m, const s3d_params *q)
             tab[0][n] = tab[0][n - 1] + p.lo_free; tab[1][n] = tab[1][n - 1] + p.lo_occ;
             tab[2][n] = tab[0][n] / (double)n; tab[3][n] = tab[1][n] / (double)n;
         }
-        if ((rc = upload(m->sum_tab, &tab[0][0], (size_t)4 * SUMT, m->stream))) return rc;
+        // ... and the mean of n_free free deltas followed by n_occ occupied ones (:546, :559) for the small counts
+        std::vector<double> all((size_t)4 * SUMT + MEAN_WORDS, 0.0);
+        memcpy(all.data(), &tab[0][0], sizeof tab);
+        for (int nf = 0; nf < SUMT; ++nf)
+            for (int no = 0; no < SUMT; ++no) {
+                if (nf >= AP_MF && no != 0) continue;
+                if (nf + no == 0) continue;
+                double sum = 0.0;
+                for (int q = 0; q < nf; ++q) sum += p.lo_free;
+                for (int q = 0; q < no; ++q) sum += p.lo_occ;
+                const double mean = sum / (double)(nf + no);
+                if (nf < AP_MF) all[(size_t)4 * SUMT + (size_t)nf * SUMT + no] = mean;
+                if (no == 0) all[(size_t)4 * SUMT + (size_t)AP_MF * SUMT + nf] = mean;
+            }
+        if ((rc = upload(m->sum_tab, all.data(), all.size(), m->stream))) return rc;
         CU(cudaStreamSynchronize(m->stream));
     }
     m->have_params = true;
