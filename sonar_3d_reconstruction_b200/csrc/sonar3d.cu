@@ -183,15 +183,20 @@ __device__ __forceinline__ u32 mix32(u64 key)
 //      to ~1 k entries at shared-memory atomic cost;
 //   2. the combiner is flushed, entry by entry, into the chunk's dedupe table in global memory
 //      (one entry per voxel touched by the chunk, one counter lane per frame).
-constexpr int EX_WARPS = 8;                  // warps per block
+// (measured at cfg2 / cfg3, frames/s: 16 warps x 2 blocks per SM with a 8192-entry combiner 221 k / 29.0 k; 8 x 4 with 4096
+// entries 211 k / 29.0 k; 4 x 8 with 2048 151 k / 22.8 k; 32 x 1 with 16384 177 k)
+#ifndef S3D_EX_WARPS
+#define S3D_EX_WARPS 16
+#endif
+constexpr int EX_WARPS = S3D_EX_WARPS;       // warps per block
 constexpr int EX_MAXB = 16;                  // beams per tile at most (a 16-byte image strip at bearing step 1)
 constexpr int EX_THREADS = EX_WARPS * 32;
 #ifndef S3D_EX_BPS
-#define S3D_EX_BPS 4
+#define S3D_EX_BPS 2
 #endif
 constexpr int EX_BPS = S3D_EX_BPS;           // resident blocks per SM the kernel is compiled for
 #ifndef S3D_LT_BITS
-#define S3D_LT_BITS 12        // log2 of the block combiner's entries
+#define S3D_LT_BITS 13        // log2 of the block combiner's entries
 #endif
 #ifndef S3D_EX_ILP
 #define S3D_EX_ILP 2
@@ -2283,7 +2288,9 @@ void launch_expand(s3d_map *m, ExpandArgs &a, int n_beams, int g, cudaStream_t s
         if (per_strip % q != 0 || a.beam_lo % q != 0) tma = false; else bpb = q;
     }
     size_t smem = expand_smem_bytes(t.H, t.free_step, t.occ_window, bpb);
-    while (smem > 200 * 1024 && bpb > 1) { bpb = tma ? bpb / 2 : bpb - 1; smem = expand_smem_bytes(t.H, t.free_step, t.occ_window, bpb); }
+    // (the fan lists grow with H: keep EX_BPS blocks resident per SM -- 227 KB less 2 KB of static + reserved memory per block)
+    const size_t smem_fit = (size_t)(227 * 1024) / EX_BPS - 2048;
+    while (smem > smem_fit && bpb > 1) { bpb = tma ? bpb / 2 : bpb - 1; smem = expand_smem_bytes(t.H, t.free_step, t.occ_window, bpb); }
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
     if (tma) {
