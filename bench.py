@@ -572,8 +572,9 @@ def run_single(args, local_rank):
 # ------------------------------------------------------------------------------- N GPUs
 def run_sharded(args, rank, world, local_rank):
     """N > 1: ONE map sharded by voxel-key hash over the ranks (strong scaling: the same frames on every
-    rank, each rank expands 1/N of the beams and owns 1/N of the voxels; the expansion kernel writes the
-    records of remote owners into their inboxes over NVLink peer memory)."""
+    rank, rank c mod N expands 16-frame chunk c -- or, S3D_ROUTE_SPLIT=beams, every rank 1/N of the beams of
+    every chunk -- and every rank owns 1/N of the voxels; the expansion kernel writes the records of remote
+    owners into their inboxes over NVLink peer memory)."""
     import torch
     import torch.distributed as dist
 
@@ -797,7 +798,11 @@ def run_sharded(args, rank, world, local_rank):
             "config": {"workload": f"{DESCR[name]}; one map sharded by voxel-key hash over {world} GPUs",
                        "frames_per_step": fps_step, "frames_timed": n_frames, "updates_per_frame": updates / n_frames,
                        "map_voxels_end": n_voxels, "table_slots_per_rank": cap,
-                       "parallelism": (f"shard{world} ({sh.mode}): each rank expands beams/{world} of every frame; the "
+                       "parallelism": (f"shard{world} ({sh.mode}, " +
+                                       (f"split by beams: each rank expands beams/{world} of every frame"
+                                        if os.environ.get("S3D_ROUTE_SPLIT") == "beams" else
+                                        f"split by chunks: rank c mod {world} expands every beam of 16-frame chunk c") +
+                                       "); every rank owns 1/N of the voxels; the "
                                        "expansion kernel writes (voxel, frame, counts) records of remote owners into their "
                                        "inboxes over NVLink peer memory (CUDA IPC), device-side flags, the owner merges "
                                        "and applies; no host sync or separate all-to-all per chunk")
