@@ -15,4 +15,5 @@ except Exception as e: print("$wl ERR", e)
 PY
   done
 done
-S3D_LIB_PATH=$PWD/variants/libsonar3d_phases.so timeout 250 python bench.py --workload cfg2 --no-cpu-baseline --no-e2e --no-cfg3 --steps 6 --warmup 3 2>&1 >/dev/null | grep phases | cut -c1-400
+# (the phase-timer build must exist: nvcc ... -DS3D_AP_PHASES -o variants/libsonar3d_phases.so, built in the container before the call)
+[ -f variants/libsonar3d_phases.so ] && S3D_LIB_PATH=$PWD/variants/libsonar3d_phases.so timeout 250 python bench.py --workload cfg2 --no-cpu-baseline --no-e2e --no-cfg3 --steps 6 --warmup 3 2>&1 >/dev/null | grep phases | cut -c1-400
